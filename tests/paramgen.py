@@ -1,0 +1,33 @@
+"""Deterministic synthetic weights shared by the golden generator, the tests and bench.py.
+
+The reference's own init zeroes every Linear bias and sets LayerNorm to (1, 0)
+(model.py:1249-1256), which would hide missing-bias / missing-affine bugs, so every tensor is
+re-drawn here from a seeded CPU generator: keys are visited in sorted order, weights ~ N(0, s)
+with s chosen per kind so activations stay O(1) through 40 blocks."""
+import torch
+
+
+def randomize_state(state: dict, seed: int = 1234) -> dict:
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for k in sorted(state.keys()):
+        v = state[k]
+        if not torch.is_floating_point(v):
+            out[k] = v.clone()                      # relative_position_index (int64 buffer)
+            continue
+        r = torch.randn(v.shape, generator=g, dtype=torch.float32)
+        if k.endswith("norm1.weight") or k.endswith("norm2.weight"):
+            t = 1.0 + 0.1 * r
+        elif k.endswith("relative_position_bias_table"):
+            t = 0.5 * r
+        elif k.endswith("modulator.weight"):
+            t = 0.5 * r
+        elif k.endswith(".bias"):
+            t = 0.1 * r
+        elif v.ndim >= 2:
+            fan_in = v[0].numel() if "deconv" not in k else v.shape[0]
+            t = r * (1.0 / fan_in) ** 0.5
+        else:
+            t = 0.1 * r
+        out[k] = t.to(v.dtype)
+    return out
