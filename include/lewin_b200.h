@@ -1,0 +1,128 @@
+/* lewin_b200.h — C ABI of the B200-native LeWin-block engine (liblewin_b200.so).
+ *
+ * The reference (ZhendongWang6/Uformer) has no FFI: its hot path is the nn.Module surface of
+ * model.py.  Each entry point below replaces the arithmetic of one reference forward; the Python
+ * modules in uformer_b200/modules.py keep the reference's constructor signatures and state-dict
+ * keys and call these functions with raw device pointers.
+ *
+ * Conventions: plain pointers and sizes only (no torch types); every pointer is a DEVICE pointer
+ * unless stated; all activations are bf16, row-major "token" layout (B, H*W, C) exactly as the
+ * reference passes them between modules; parameters that enter GEMMs are pre-packed bf16 "operand
+ * images" (see lw_pack_* in uformer_b200/packing.py), small per-channel parameters are fp32.
+ * Calls are asynchronous on `stream`, never allocate, never synchronise, and return 0 or a negative
+ * LW_ERR_* code (argument validation happens before any launch).  Re-entrant: no global mutable
+ * state, so it is safe under the reference's DataParallel threading (train/train_denoise.py:83).
+ */
+#ifndef LEWIN_B200_H
+#define LEWIN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LW_OK 0
+#define LW_ERR_BAD_SHAPE (-1)   /* unsupported / inconsistent dimensions */
+#define LW_ERR_NULL (-2)        /* required pointer is NULL */
+#define LW_ERR_CUDA (-3)        /* launch failed; see lw_last_cuda_error() */
+#define LW_ERR_ARCH (-4)        /* device is not sm_100 */
+
+typedef void* lw_stream_t;      /* cudaStream_t */
+
+/* Library/ABI version (bumped on any signature change). */
+int lw_abi_version(void);
+/* cudaGetLastError() text of the calling thread's most recent failure ("" if none). */
+const char* lw_last_cuda_error(void);
+/* 0 if the current device is a B200-class (sm_100) part, LW_ERR_ARCH otherwise. */
+int lw_check_device(void);
+
+/* ---- fused W-MSA: replaces LeWinTransformerBlock.forward's attention half (model.py:951-986)
+ * and, with ln_w=NULL / resid=NULL / windowed=1, WindowAttention.forward (model.py:494-522).
+ *   out = resid + reverse( proj( softmax( q k^T * hd^-1/2 + relpos_bias + mask ) v ) )
+ *   q,k,v = Linear( partition( roll( LN(x), -shift ) ) + modulator )
+ * Window size is 8x8 (64 tokens); head_dim in {16, 32}; C in {16,...,512}, C % head_dim == 0. */
+typedef struct lw_wmsa_args {
+  const void* x;           /* bf16 (B, H*W, C) token map, or (n_windows, 64, C) if windowed */
+  void* out;               /* bf16, same layout as x */
+  const void* resid;       /* bf16 residual (same layout) added to the output, or NULL */
+  const float* ln_w;       /* LayerNorm weight/bias (C), or NULL for no normalisation */
+  const float* ln_b;
+  const float* modulator;  /* (64, C) fp32 added after LN inside each window, or NULL */
+  const void* wqkv_img;    /* packed bf16 [heads][KB][3*hd rows x 128B]; q rows pre-scaled */
+  const float* bqkv;       /* (heads, 3*hd) fp32: q (pre-scaled) | k | v bias per head */
+  const void* wproj_img;   /* packed bf16 [C/nch][KB][nch rows x 128B] */
+  const float* bproj;      /* (C) */
+  const float* relpos;     /* (heads, 225) fp32: relative_position_bias_table transposed */
+  const float* mask;       /* optional explicit additive mask (n_mask_windows, 64, 64) fp32 */
+  int32_t n_mask_windows;
+  int32_t n_windows;       /* total windows = B * (H/8) * (W/8) */
+  int32_t H, W;            /* token-map size (ignored if windowed) */
+  int32_t C, head_dim;
+  int32_t shift;           /* cyclic shift (0 or 4); the {0,-100} region mask is computed in-kernel */
+  int32_t windowed;        /* 1: x/out are already window-major (WindowAttention standalone) */
+  float ln_eps;
+} lw_wmsa_args;
+int lw_wmsa_fwd(const lw_wmsa_args* a, lw_stream_t stream);
+
+/* ---- LeFF part 1: h1 = GELU( LN(x) W1^T + b1 )  (model.py:671 with norm2 of :987 folded in) */
+typedef struct lw_leff1_args {
+  const void* x;           /* bf16 (n_tokens, C) */
+  void* h1;                /* bf16 (n_tokens, 4C) */
+  const float* ln_w;       /* NULL: no LayerNorm (LeFF standalone) */
+  const float* ln_b;
+  const void* w1_img;      /* packed bf16 [hidden/nch][KB][nch x 128B] */
+  const float* b1;         /* (hidden) */
+  int32_t n_tokens, C, hidden;
+  float ln_eps;
+} lw_leff1_args;
+int lw_leff1_fwd(const lw_leff1_args* a, lw_stream_t stream);
+
+/* ---- LeFF part 2: out = resid + GELU( dwconv3x3(h1) + bd ) W2^T + b2  (model.py:674-682);
+ * the depthwise conv is staged in shared memory (zero padding on h1) and feeds the GEMM directly. */
+typedef struct lw_leff2_args {
+  const void* h1;          /* bf16 (B, H, W, hidden) */
+  void* out;               /* bf16 (B, H*W, C) */
+  const void* resid;       /* bf16 (B, H*W, C) or NULL */
+  const float* wd;         /* (9, hidden) fp32 depthwise taps, tap = ky*3+kx */
+  const float* bd;         /* (hidden) */
+  const void* w2_img;      /* packed bf16 [hidden/64][C/nch][nch x 128B] */
+  const float* b2;         /* (C) */
+  int32_t B, H, W, C, hidden;
+} lw_leff2_args;
+int lw_leff2_fwd(const lw_leff2_args* a, lw_stream_t stream);
+
+/* ---- Downsample: Conv2d(k4,s2,p1) on the token map as an implicit GEMM (model.py:739-746) */
+typedef struct lw_down_args {
+  const void* x;           /* bf16 (B, H, W, Cin) */
+  void* out;               /* bf16 (B, H/2*W/2, Cout) */
+  const void* w_img;       /* packed bf16 [16*Cin/64][Cout/nch][nch x 128B], K index = tap*Cin+ci */
+  const float* bias;       /* (Cout) */
+  int32_t B, H, W, Cin, Cout;
+} lw_down_args;
+int lw_downsample_fwd(const lw_down_args* a, lw_stream_t stream);
+
+/* ---- Upsample: ConvTranspose2d(k2,s2) = GEMM (N = 4*Cout) + pixel-shuffle scatter
+ * (model.py:765-771).  out may point into a wider concat buffer: row stride out_stride elements. */
+typedef struct lw_up_args {
+  const void* x;           /* bf16 (B, H*W, Cin) */
+  void* out;               /* bf16 (B, 4*H*W, out_stride) — first Cout channels of each row written */
+  const void* w_img;       /* packed bf16 [4*Cout/nch][KB][nch x 128B], N index = (dy*2+dx)*Cout+co */
+  const float* bias;       /* (Cout) */
+  int32_t B, H, W, Cin, Cout, out_stride;
+} lw_up_args;
+int lw_upsample_fwd(const lw_up_args* a, lw_stream_t stream);
+
+/* ---- caller-side projections, HBM-bound direct convolutions ----
+ * InputProj (model.py:781-812): y = LeakyReLU_0.01(conv3x3(x)), NCHW fp32 image -> bf16 tokens. */
+int lw_input_proj_fwd(const float* img, const float* w /* (E,Cin,3,3) */, const float* b, void* tokens,
+                      int32_t B, int32_t Cin, int32_t H, int32_t W, int32_t E, lw_stream_t stream);
+/* OutputProj + global residual (model.py:815-846, :1305): out = img + conv3x3(tokens), NCHW fp32. */
+int lw_output_proj_fwd(const void* tokens, const float* w /* (Cout,Cin,3,3) */, const float* b,
+                       const float* img /* residual or NULL */, float* out, int32_t B, int32_t Cin,
+                       int32_t H, int32_t W, int32_t Cout, lw_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LEWIN_B200_H */

@@ -1,0 +1,107 @@
+"""Generate golden input/output vectors from the UNMODIFIED reference (build container only).
+
+    python tests/golden/make_golden.py
+
+Imports /root/reference/model.py behind the timm shim (tests/refshim.py), builds reference modules
+with the seeded synthetic weights of tests/paramgen.py, runs the reference forward in fp32 on CPU
+and stores inputs + outputs as fp32 .pt files in this directory.  Weights are NOT stored: they are
+re-derived from the seed (paramgen.randomize_state is deterministic), the fixture keeps a checksum.
+The reference cannot travel to the GPU box, these files can.
+"""
+import os
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+from refshim import import_reference_model  # noqa: E402
+from paramgen import randomize_state  # noqa: E402
+
+
+def state_checksum(state):
+    s = 0.0
+    for k in sorted(state):
+        if torch.is_floating_point(state[k]):
+            s += float(state[k].double().abs().sum())
+    return s
+
+
+def load_random(mod, seed):
+    st = randomize_state(mod.state_dict(), seed)
+    mod.load_state_dict(st, strict=True)
+    mod.eval()
+    return st
+
+
+def main():
+    torch.manual_seed(1234)
+    torch.set_grad_enabled(False)
+    m = import_reference_model()
+    out = {}
+
+    # ---- module level: WindowAttention (model.py:452-546), with and without mask ----
+    for name, dim, heads, nwin in [("wattn_c32_h1", 32, 1, 6), ("wattn_c128_h4", 128, 4, 8), ("wattn_c64_h4_hd16", 64, 4, 4)]:
+        mod = m.WindowAttention(dim, win_size=(8, 8), num_heads=heads)
+        st = load_random(mod, 11)
+        x = torch.randn(nwin, 64, dim)
+        mask = torch.where(torch.rand(2, 64, 64) > 0.7, torch.tensor(-100.0), torch.tensor(0.0))
+        out[name] = dict(kind="wattn", dim=dim, heads=heads, seed=11, x=x, y=mod(x), mask=mask,
+                         y_mask=mod(x, mask=mask), checksum=state_checksum(st))
+
+    # ---- LeFF (model.py:654-699) ----
+    for name, dim, B, H in [("leff_c32", 32, 2, 16), ("leff_c128", 128, 1, 24)]:
+        mod = m.LeFF(dim, 4 * dim)
+        st = load_random(mod, 12)
+        x = torch.randn(B, H * H, dim)
+        out[name] = dict(kind="leff", dim=dim, seed=12, x=x, y=mod(x), checksum=state_checksum(st))
+
+    # ---- Downsample / Upsample (model.py:730-778) ----
+    mod = m.Downsample(32, 64)
+    st = load_random(mod, 13)
+    x = torch.randn(2, 16 * 16, 32)
+    out["down_32_64"] = dict(kind="down", cin=32, cout=64, seed=13, x=x, y=mod(x), checksum=state_checksum(st))
+    mod = m.Upsample(64, 16)
+    st = load_random(mod, 14)
+    x = torch.randn(2, 8 * 8, 64)
+    out["up_64_16"] = dict(kind="up", cin=64, cout=16, seed=14, x=x, y=mod(x), checksum=state_checksum(st))
+
+    # ---- LeWinTransformerBlock (model.py:850-1008): shift 0/4, modulator on/off ----
+    for name, dim, heads, H, shift, modu in [("block_c32_s0", 32, 1, 16, 0, False), ("block_c64_s4_mod", 64, 2, 24, 4, True),
+                                            ("block_c128_s4", 128, 4, 16, 4, False), ("block_c32_s0_mod_hd16", 32, 2, 16, 0, True)]:
+        mod = m.LeWinTransformerBlock(dim, (H, H), heads, win_size=8, shift_size=shift, modulator=modu)
+        st = load_random(mod, 15)
+        x = torch.randn(2, H * H, dim)
+        out[name] = dict(kind="block", dim=dim, heads=heads, H=H, shift=shift, modulator=modu, seed=15,
+                         x=x, y=mod(x), checksum=state_checksum(st))
+
+    # ---- whole model, BASELINE config #1: Uformer-T-like, 128x128, batch 1 (depths=[1]*9) ----
+    cfg = dict(img_size=128, embed_dim=16, depths=[1] * 9, win_size=8, token_projection="linear", token_mlp="leff", modulator=True)
+    net = m.Uformer(**cfg)
+    st = load_random(net, 1234)
+    x = torch.rand(1, 3, 128, 128)
+    out["uformer_t1_128"] = dict(kind="model", cfg=cfg, seed=1234, x=x, y=net(x), checksum=state_checksum(st))
+    # real Uformer_T depths ([2]*9) at 128x128: exercises shifted blocks at every stage
+    cfg2 = dict(img_size=128, embed_dim=16, depths=[2] * 9, win_size=8, token_projection="linear", token_mlp="leff", modulator=True)
+    net = m.Uformer(**cfg2)
+    st = load_random(net, 77)
+    x = torch.rand(2, 3, 128, 128)
+    out["uformer_t2_128"] = dict(kind="model", cfg=cfg2, seed=77, x=x, y=net(x), checksum=state_checksum(st))
+    # arbitrary-resolution path: model built for 128, run at 256 (whole-image forward)
+    x = torch.rand(1, 3, 256, 256)
+    out["uformer_t2_128_at256"] = dict(kind="model", cfg=cfg2, seed=77, x=x, y=net(x), checksum=state_checksum(st))
+    # embed_dim=32 (head_dim 32 as in Uformer-S/B), 2 blocks per stage, 128x128
+    cfg3 = dict(img_size=128, embed_dim=32, depths=[2, 2, 2, 2, 2, 2, 2, 2, 2], win_size=8, token_projection="linear", token_mlp="leff", modulator=True)
+    net = m.Uformer(**cfg3)
+    st = load_random(net, 5)
+    x = torch.rand(1, 3, 128, 128)
+    out["uformer_s2_128"] = dict(kind="model", cfg=cfg3, seed=5, x=x, y=net(x), checksum=state_checksum(st))
+
+    for k, v in out.items():
+        path = os.path.join(HERE, k + ".pt")
+        torch.save(v, path)
+        print("%-28s %8.1f KB" % (k, os.path.getsize(path) / 1024))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,87 @@
+"""Shared helpers for the parity tests."""
+import os
+
+import torch
+
+from paramgen import randomize_state
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+# north_star tolerances: 1e-3 relative for fp32 arithmetic, 1e-2 for bf16 arithmetic.
+TOL_FP32 = 1e-3
+TOL_BF16 = 1e-2
+
+
+def load_golden(name):
+    return torch.load(os.path.join(GOLDEN, name + ".pt"), weights_only=False)
+
+
+def golden_names(kind):
+    out = []
+    for f in sorted(os.listdir(GOLDEN)):
+        if f.endswith(".pt"):
+            g = torch.load(os.path.join(GOLDEN, f), weights_only=False)
+            if g["kind"] == kind:
+                out.append(f[:-3])
+    return out
+
+
+def rel_l2(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+def rel_max(a, b):
+    return ((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30)).item()
+
+
+def state_checksum(state):
+    s = 0.0
+    for k in sorted(state):
+        if torch.is_floating_point(state[k]):
+            s += float(state[k].double().abs().sum())
+    return s
+
+
+def build_module(g):
+    """Construct OUR module for a golden fixture (CPU), load the seeded synthetic weights, return (module, state)."""
+    import uformer_b200 as U
+    kind = g["kind"]
+    if kind == "wattn":
+        mod = U.WindowAttention(g["dim"], win_size=(8, 8), num_heads=g["heads"])
+    elif kind == "leff":
+        mod = U.LeFF(g["dim"], 4 * g["dim"])
+    elif kind == "down":
+        mod = U.Downsample(g["cin"], g["cout"])
+    elif kind == "up":
+        mod = U.Upsample(g["cin"], g["cout"])
+    elif kind == "block":
+        mod = U.LeWinTransformerBlock(g["dim"], (g["H"], g["H"]), g["heads"], win_size=8, shift_size=g["shift"], modulator=g["modulator"])
+    elif kind == "model":
+        mod = U.Uformer(**g["cfg"])
+    else:
+        raise KeyError(kind)
+    st = randomize_state(mod.state_dict(), g["seed"])
+    mod.load_state_dict(st, strict=True)
+    return mod.eval(), st
+
+
+def oracle_run(g, st, x, dtype=torch.float32, mask=None):
+    """Run the CPU oracle for a fixture description."""
+    from oracle import lewin_oracle as O
+    st = {k: (v.to(dtype) if torch.is_floating_point(v) else v) for k, v in st.items()}
+    x = x.to(dtype)
+    kind = g["kind"]
+    if kind == "wattn":
+        return O.window_attention(x, st, "", g["heads"], 8, None if mask is None else mask.to(dtype))
+    if kind == "leff":
+        return O.leff(x, st, "")
+    if kind == "down":
+        return O.downsample(x, st["conv.0.weight"], st["conv.0.bias"])
+    if kind == "up":
+        return O.upsample(x, st["deconv.0.weight"], st["deconv.0.bias"])
+    if kind == "block":
+        return O.lewin_block(x, st, "", g["heads"], 8, g["shift"])
+    if kind == "model":
+        c = g["cfg"]
+        return O.uformer_forward(x, st, c["img_size"], c["embed_dim"], c["depths"], win_size=c["win_size"])
+    raise KeyError(kind)

@@ -1,0 +1,106 @@
+"""CPU: host-side logic — operand-image packing, C-ABI surface, module boundary behaviour."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import uformer_b200
+from uformer_b200 import _lib, packing
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("N,K,nch,order", [(96, 32, 96, "nk"), (384, 128, 128, "nk"), (512, 2048, 128, "kn"), (64, 16, 64, "nk"), (32, 256, 32, "kn")])
+def test_pack_roundtrip(N, K, nch, order):
+    w = torch.randn(N, K)
+    img = packing.pack_kmajor(w, nch, order)
+    KB = (K + 63) // 64
+    assert img.dtype == torch.bfloat16 and img.numel() == N * KB * 64
+    back = packing.unpack_kmajor(img, N, K, nch, order)
+    assert torch.equal(back, w.to(torch.bfloat16).float())
+
+
+def test_pack_swizzle_matches_device_formula():
+    """Element (n, k) of a chunk must sit at byte swz<128>(n, 2k) = (n*128 + 2k) ^ ((n & 7) << 4) (csrc/umma.cuh)."""
+    nch = 16
+    w = torch.arange(nch * 64, dtype=torch.float32).reshape(nch, 64) % 251
+    img = packing.pack_kmajor(w, nch, "nk").reshape(-1).float()
+    for n in range(nch):
+        for k in range(64):
+            lin = n * 128 + 2 * k
+            off = lin ^ (((lin >> 7) & 7) << 4)
+            assert img[off // 2] == w[n, k]
+
+
+def test_pack_qkv_rows_and_scale():
+    C, heads = 64, 2
+    hd = C // heads
+    wq, wkv = torch.randn(C, C), torch.randn(2 * C, C)
+    bq, bkv = torch.randn(C), torch.randn(2 * C)
+    img, bias = packing.pack_qkv(wq, bq, wkv, bkv, heads, 0.25)
+    w = packing.unpack_kmajor(img, heads * 3 * hd, C, 3 * hd)
+    assert torch.equal(w[3 * hd + hd:3 * hd + 2 * hd], wkv[hd:2 * hd].to(torch.bfloat16).float())          # k rows of head 1
+    assert torch.equal(w[2 * hd:3 * hd], wkv[C:C + hd].to(torch.bfloat16).float())                           # v rows of head 0
+    assert torch.equal(w[:hd], (wq[:hd] * 0.25).to(torch.bfloat16).float())
+    assert torch.allclose(bias[:hd], bq[:hd] * 0.25) and torch.equal(bias[hd:2 * hd], bkv[:hd])
+
+
+def test_pack_down_up_index_order():
+    w = torch.randn(32, 16, 4, 4)
+    wk = packing.unpack_kmajor(packing.pack_downsample(w, 32), 32, 256, 32, "kn")
+    assert torch.equal(wk[:, (2 * 4 + 1) * 16 + 5], w[:, 5, 2, 1].to(torch.bfloat16).float())
+    wu = torch.randn(64, 16, 2, 2)
+    wn = packing.unpack_kmajor(packing.pack_upsample(wu, 64), 64, 64, 64, "nk")
+    assert torch.equal(wn[(1 * 2 + 0) * 16 + 3], wu[:, 3, 1, 0].to(torch.bfloat16).float())
+
+
+def test_c_abi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "lewin_b200.h")).read()
+    declared = set(re.findall(r"\b(lw_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    lib = _lib.load()
+    for s in declared:
+        assert hasattr(lib, s), s
+    assert lib.lw_abi_version() == 1
+    # struct sizes agree with the header layout (pointers 8 B, ints 4 B)
+    assert ctypes.sizeof(_lib.WmsaArgs) == 12 * 8 + 9 * 4 + 4
+    assert ctypes.sizeof(_lib.Leff2Args) == 7 * 8 + 5 * 4 + 4
+
+
+def test_argument_validation_without_gpu():
+    lib = _lib.load()
+    a = _lib.WmsaArgs()
+    assert lib.lw_wmsa_fwd(ctypes.byref(a), None) == -2          # NULL pointers
+    b = _lib.DownArgs()
+    assert lib.lw_downsample_fwd(ctypes.byref(b), None) == -2
+
+
+def test_no_cpu_fallback_and_no_silent_training():
+    blk = uformer_b200.LeWinTransformerBlock(32, (16, 16), 1, win_size=8, shift_size=0).eval()
+    with pytest.raises(uformer_b200.EngineUnavailable):
+        blk(torch.randn(1, 256, 32))
+    att = uformer_b200.WindowAttention(32, (8, 8), 1)
+    with pytest.raises(uformer_b200.EngineUnavailable):
+        att(torch.randn(2, 64, 32))
+    with pytest.raises(NotImplementedError):
+        uformer_b200.LeWinTransformerBlock(32, (16, 16), 1, token_mlp='ffn')
+
+
+def test_clamp_and_flops_surface():
+    blk = uformer_b200.LeWinTransformerBlock(64, (8, 8), 2, win_size=8, shift_size=4)
+    assert blk.shift_size == 0 and blk.win_size == 8               # model.py:863-865
+    T = 16 * 16
+    blk = uformer_b200.LeWinTransformerBlock(32, (16, 16), 1, win_size=8)
+    expect = 2 * 32 * T + (3 * T * 32 * 32 + 2 * (T / 64) * 64 * 32 * 64 + T * 32 * 32) + (2 * T * 32 * 128 + T * 128 * 9)
+    assert blk.flops() == expect
+
+
+def test_pack_cache_invalidation():
+    att = uformer_b200.WindowAttention(32, (8, 8), 1)
+    p1 = att.packed()
+    assert att.packed() is p1
+    with torch.no_grad():
+        att.proj.weight.add_(1.0)
+    assert att.packed() is not p1

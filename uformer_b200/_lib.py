@@ -1,0 +1,103 @@
+"""ctypes binding of liblewin_b200.so (C ABI: include/lewin_b200.h).
+
+The shared library is built in-tree by ``__graft_entry__.build()`` (plain nvcc, no torch headers).
+There is no fallback: if the library is missing, or the device is not sm_100, every op raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "liblewin_b200.so")
+
+LW_ERRORS = {-1: "LW_ERR_BAD_SHAPE", -2: "LW_ERR_NULL", -3: "LW_ERR_CUDA", -4: "LW_ERR_ARCH"}
+
+
+class EngineUnavailable(RuntimeError):
+    """The native B200 engine cannot run here (library not built / no sm_100 device)."""
+
+
+class WmsaArgs(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("out", C.c_void_p), ("resid", C.c_void_p), ("ln_w", C.c_void_p), ("ln_b", C.c_void_p),
+                ("modulator", C.c_void_p), ("wqkv_img", C.c_void_p), ("bqkv", C.c_void_p), ("wproj_img", C.c_void_p),
+                ("bproj", C.c_void_p), ("relpos", C.c_void_p), ("mask", C.c_void_p), ("n_mask_windows", C.c_int32),
+                ("n_windows", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32), ("head_dim", C.c_int32),
+                ("shift", C.c_int32), ("windowed", C.c_int32), ("ln_eps", C.c_float)]
+
+
+class Leff1Args(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("h1", C.c_void_p), ("ln_w", C.c_void_p), ("ln_b", C.c_void_p), ("w1_img", C.c_void_p),
+                ("b1", C.c_void_p), ("n_tokens", C.c_int32), ("C", C.c_int32), ("hidden", C.c_int32), ("ln_eps", C.c_float)]
+
+
+class Leff2Args(C.Structure):
+    _fields_ = [("h1", C.c_void_p), ("out", C.c_void_p), ("resid", C.c_void_p), ("wd", C.c_void_p), ("bd", C.c_void_p),
+                ("w2_img", C.c_void_p), ("b2", C.c_void_p), ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+                ("C", C.c_int32), ("hidden", C.c_int32)]
+
+
+class DownArgs(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("out", C.c_void_p), ("w_img", C.c_void_p), ("bias", C.c_void_p), ("B", C.c_int32),
+                ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32), ("Cout", C.c_int32)]
+
+
+class UpArgs(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("out", C.c_void_p), ("w_img", C.c_void_p), ("bias", C.c_void_p), ("B", C.c_int32),
+                ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32), ("Cout", C.c_int32), ("out_stride", C.c_int32)]
+
+
+# every symbol include/lewin_b200.h declares
+EXPORTS = ["lw_abi_version", "lw_last_cuda_error", "lw_check_device", "lw_wmsa_fwd", "lw_leff1_fwd", "lw_leff2_fwd",
+           "lw_downsample_fwd", "lw_upsample_fwd", "lw_input_proj_fwd", "lw_output_proj_fwd"]
+
+_lib = None
+
+
+def load():
+    """Load the shared library (works without a GPU; compute calls do not)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise EngineUnavailable(f"{LIB_PATH} not built — run `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = C.CDLL(LIB_PATH)
+    lib.lw_abi_version.restype = C.c_int
+    lib.lw_last_cuda_error.restype = C.c_char_p
+    lib.lw_check_device.restype = C.c_int
+    for name, argt in [("lw_wmsa_fwd", WmsaArgs), ("lw_leff1_fwd", Leff1Args), ("lw_leff2_fwd", Leff2Args),
+                       ("lw_downsample_fwd", DownArgs), ("lw_upsample_fwd", UpArgs)]:
+        fn = getattr(lib, name)
+        fn.restype = C.c_int
+        fn.argtypes = [C.POINTER(argt), C.c_void_p]
+    lib.lw_input_proj_fwd.restype = C.c_int
+    lib.lw_input_proj_fwd.argtypes = [C.c_void_p] * 4 + [C.c_int32] * 5 + [C.c_void_p]
+    lib.lw_output_proj_fwd.restype = C.c_int
+    lib.lw_output_proj_fwd.argtypes = [C.c_void_p] * 5 + [C.c_int32] * 5 + [C.c_void_p]
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        lib = load()
+        detail = lib.lw_last_cuda_error().decode() if rc == -3 else ""
+        raise RuntimeError(f"{what} failed: {LW_ERRORS.get(rc, rc)} {detail}")
+
+
+_device_ok = {}
+
+
+def require_device(device):
+    """Raise unless `device` is a CUDA sm_100 device and the library is loadable."""
+    import torch
+    if device.type != "cuda":
+        raise EngineUnavailable("uformer_b200 runs only on CUDA sm_100 (B200) tensors; there is no CPU fallback "
+                                f"(got a tensor on {device})")
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _device_ok:
+        lib = load()
+        with torch.cuda.device(idx):
+            if lib.lw_check_device() != 0:
+                raise EngineUnavailable("current CUDA device is not sm_100 (B200)")
+        _device_ok[idx] = True

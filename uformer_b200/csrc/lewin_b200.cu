@@ -1,0 +1,177 @@
+// lewin_b200.cu — C ABI (include/lewin_b200.h) over the sm_100a kernels.
+// Validation first, then a template dispatch on the channel count; no allocation, no sync.
+#include <cstdio>
+#include <cstring>
+#include "wmsa.cuh"
+#include "leff.cuh"
+#include "proj.cuh"
+
+using namespace lw;
+
+static thread_local char g_err[256] = "";
+
+static int cuda_fail(cudaError_t e) {
+  snprintf(g_err, sizeof(g_err), "%s", cudaGetErrorString(e));
+  return LW_ERR_CUDA;
+}
+#define LW_TRY(expr)                               \
+  do {                                             \
+    cudaError_t _e = (expr);                       \
+    if (_e != cudaSuccess) return cuda_fail(_e);   \
+  } while (0)
+
+extern "C" int lw_abi_version(void) { return 1; }
+extern "C" const char* lw_last_cuda_error(void) { return g_err; }
+extern "C" int lw_check_device(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return LW_ERR_ARCH;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return LW_ERR_ARCH;
+  return major == 10 ? LW_OK : LW_ERR_ARCH;
+}
+
+static int pow2_cols(int n) {
+  int c = 32;
+  while (c < n) c <<= 1;
+  return c;
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int C, int HD>
+static int launch_wmsa(const lw_wmsa_args* a, cudaStream_t st) {
+  using Cfg = WmsaCfg<C, HD>;
+  static_assert(Cfg::SMEM_BYTES <= 232448, "smem budget");
+  LW_TRY(cudaFuncSetAttribute(wmsa_kernel<C, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  const int tiles = (a->n_windows + 1) / 2;
+  wmsa_kernel<C, HD><<<tiles, kThreads, Cfg::SMEM_BYTES, st>>>(*a);
+  LW_TRY(cudaGetLastError());
+  return LW_OK;
+}
+
+extern "C" int lw_wmsa_fwd(const lw_wmsa_args* a, lw_stream_t stream) {
+  if (!a || !a->x || !a->out || !a->wqkv_img || !a->bqkv || !a->wproj_img || !a->bproj || !a->relpos) return LW_ERR_NULL;
+  if ((a->ln_w == nullptr) != (a->ln_b == nullptr)) return LW_ERR_NULL;
+  if (a->n_windows <= 0) return LW_ERR_BAD_SHAPE;
+  if (!a->windowed) {
+    if (a->H <= 0 || a->W <= 0 || (a->H % 8) || (a->W % 8)) return LW_ERR_BAD_SHAPE;
+    if (a->n_windows % ((a->H / 8) * (a->W / 8))) return LW_ERR_BAD_SHAPE;
+    if (a->shift < 0 || a->shift >= 8) return LW_ERR_BAD_SHAPE;
+  } else if (a->shift != 0) {
+    return LW_ERR_BAD_SHAPE;
+  }
+  if (a->mask && a->n_mask_windows <= 0) return LW_ERR_BAD_SHAPE;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define WMSA_CASE(c, hd) \
+  if (a->C == c && a->head_dim == hd) return launch_wmsa<c, hd>(a, st);
+  WMSA_CASE(32, 32) WMSA_CASE(64, 32) WMSA_CASE(128, 32) WMSA_CASE(256, 32) WMSA_CASE(512, 32)
+  WMSA_CASE(16, 16) WMSA_CASE(32, 16) WMSA_CASE(64, 16) WMSA_CASE(128, 16) WMSA_CASE(256, 16)
+#undef WMSA_CASE
+  return LW_ERR_BAD_SHAPE;
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int K, int EPI>
+static int launch_ares(const AResArgs& a, cudaStream_t st) {
+  using Cfg = AResCfg<K>;
+  static_assert(Cfg::SMEM_BYTES <= 232448, "smem budget");
+  LW_TRY(cudaFuncSetAttribute(ares_kernel<K, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  const int tiles = (a.n_rows + 127) / 128;
+  ares_kernel<K, EPI><<<tiles, kThreads, Cfg::SMEM_BYTES, st>>>(a);
+  LW_TRY(cudaGetLastError());
+  return LW_OK;
+}
+template <int EPI>
+static int dispatch_ares(const AResArgs& a, cudaStream_t st) {
+  switch (a.K) {
+    case 16: return launch_ares<16, EPI>(a, st);
+    case 32: return launch_ares<32, EPI>(a, st);
+    case 64: return launch_ares<64, EPI>(a, st);
+    case 128: return launch_ares<128, EPI>(a, st);
+    case 256: return launch_ares<256, EPI>(a, st);
+    case 512: return launch_ares<512, EPI>(a, st);
+    default: return LW_ERR_BAD_SHAPE;
+  }
+}
+
+extern "C" int lw_leff1_fwd(const lw_leff1_args* p, lw_stream_t stream) {
+  if (!p || !p->x || !p->h1 || !p->w1_img || !p->b1) return LW_ERR_NULL;
+  if ((p->ln_w == nullptr) != (p->ln_b == nullptr)) return LW_ERR_NULL;
+  if (p->n_tokens <= 0 || p->hidden % 64) return LW_ERR_BAD_SHAPE;
+  AResArgs a{};
+  a.x = reinterpret_cast<const bf16*>(p->x); a.n_rows = p->n_tokens; a.K = p->C;
+  a.ln_w = p->ln_w; a.ln_b = p->ln_b; a.ln_eps = p->ln_eps;
+  a.w_img = reinterpret_cast<const uint8_t*>(p->w1_img); a.n_total = p->hidden; a.nch = p->hidden < 128 ? p->hidden : 128;
+  a.bias = p->b1; a.out = reinterpret_cast<bf16*>(p->h1);
+  return dispatch_ares<0>(a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int lw_upsample_fwd(const lw_up_args* p, lw_stream_t stream) {
+  if (!p || !p->x || !p->out || !p->w_img || !p->bias) return LW_ERR_NULL;
+  if (p->B <= 0 || p->H <= 0 || p->W <= 0 || p->Cout % 16 || p->out_stride < p->Cout || p->out_stride % 8) return LW_ERR_BAD_SHAPE;
+  AResArgs a{};
+  a.x = reinterpret_cast<const bf16*>(p->x); a.n_rows = p->B * p->H * p->W; a.K = p->Cin;
+  a.w_img = reinterpret_cast<const uint8_t*>(p->w_img); a.n_total = 4 * p->Cout; a.nch = a.n_total < 128 ? a.n_total : 128;
+  a.bias = p->bias; a.out = reinterpret_cast<bf16*>(p->out);
+  a.H = p->H; a.W = p->W; a.Cout = p->Cout; a.out_stride = p->out_stride;
+  return dispatch_ares<1>(a, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int PROD>
+static int launch_astream(const AStreamArgs& a, int tiles, cudaStream_t st) {
+  static_assert(AStreamCfg::SMEM_BYTES <= 232448, "smem budget");
+  LW_TRY(cudaFuncSetAttribute(astream_kernel<PROD>, cudaFuncAttributeMaxDynamicSharedMemorySize, AStreamCfg::SMEM_BYTES));
+  astream_kernel<PROD><<<tiles, kThreads, AStreamCfg::SMEM_BYTES, st>>>(a, pow2_cols(a.N));
+  LW_TRY(cudaGetLastError());
+  return LW_OK;
+}
+
+extern "C" int lw_leff2_fwd(const lw_leff2_args* p, lw_stream_t stream) {
+  if (!p || !p->h1 || !p->out || !p->wd || !p->bd || !p->w2_img || !p->b2) return LW_ERR_NULL;
+  if (p->B <= 0 || p->H <= 0 || p->W < 8 || p->hidden % 64 || p->C % 16 || p->C > 512) return LW_ERR_BAD_SHAPE;
+  AStreamArgs a{};
+  a.src = reinterpret_cast<const bf16*>(p->h1); a.B = p->B; a.H = p->H; a.W = p->W; a.K = p->hidden;
+  a.wd = p->wd; a.bd = p->bd; a.w_img = reinterpret_cast<const uint8_t*>(p->w2_img);
+  a.N = p->C; a.nch = p->C < 128 ? p->C : 128; a.bias = p->b2;
+  a.resid = reinterpret_cast<const bf16*>(p->resid); a.out = reinterpret_cast<bf16*>(p->out);
+  a.TW = p->W >= 16 ? 16 : 8; a.TH = 128 / a.TW;
+  a.tiles_x = (p->W + a.TW - 1) / a.TW;
+  const int tiles_y = (p->B * p->H + a.TH - 1) / a.TH;
+  return launch_astream<0>(a, a.tiles_x * tiles_y, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int lw_downsample_fwd(const lw_down_args* p, lw_stream_t stream) {
+  if (!p || !p->x || !p->out || !p->w_img || !p->bias) return LW_ERR_NULL;
+  if (p->B <= 0 || p->H % 2 || p->W % 2 || p->Cin % 8 || (16 * p->Cin) % 64 || p->Cout % 16 || p->Cout > 512) return LW_ERR_BAD_SHAPE;
+  if (!((64 % p->Cin == 0) || (p->Cin % 64 == 0))) return LW_ERR_BAD_SHAPE;
+  AStreamArgs a{};
+  a.src = reinterpret_cast<const bf16*>(p->x); a.B = p->B; a.H = p->H; a.W = p->W; a.K = 16 * p->Cin; a.Cin = p->Cin;
+  a.w_img = reinterpret_cast<const uint8_t*>(p->w_img); a.N = p->Cout; a.nch = p->Cout < 128 ? p->Cout : 128;
+  a.bias = p->bias; a.out = reinterpret_cast<bf16*>(p->out);
+  const int rows = p->B * (p->H / 2) * (p->W / 2);
+  return launch_astream<1>(a, (rows + 127) / 128, reinterpret_cast<cudaStream_t>(stream));
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int lw_input_proj_fwd(const float* img, const float* w, const float* b, void* tokens, int32_t B, int32_t Cin,
+                                 int32_t H, int32_t W, int32_t E, lw_stream_t stream) {
+  if (!img || !w || !b || !tokens) return LW_ERR_NULL;
+  if (B <= 0 || H <= 0 || W <= 0 || E % 8 || E > 64 || Cin < 1 || Cin > 4) return LW_ERR_BAD_SHAPE;
+  const long long npix = (long long)B * H * W;
+  const int blocks = (int)((npix + 127) / 128);
+  input_proj_kernel<<<blocks, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(img, w, b, reinterpret_cast<bf16*>(tokens), B, Cin, H, W, E);
+  LW_TRY(cudaGetLastError());
+  return LW_OK;
+}
+
+extern "C" int lw_output_proj_fwd(const void* tokens, const float* w, const float* b, const float* img, float* out, int32_t B,
+                                  int32_t Cin, int32_t H, int32_t W, int32_t Cout, lw_stream_t stream) {
+  if (!tokens || !w || !b || !out) return LW_ERR_NULL;
+  if (B <= 0 || H <= 0 || W <= 0 || Cin % 8 || Cin > 128 || Cout < 1 || Cout > 4) return LW_ERR_BAD_SHAPE;
+  const long long npix = (long long)B * H * W;
+  const int blocks = (int)((npix + 127) / 128);
+  const size_t smem = (size_t)Cout * 9 * Cin * sizeof(float);
+  output_proj_kernel<<<blocks, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const bf16*>(tokens), w, b, img, out, B, Cin, H,
+                                                                                    W, Cout);
+  LW_TRY(cudaGetLastError());
+  return LW_OK;
+}

@@ -1,0 +1,168 @@
+// lewin_common.cuh — CTA organisation shared by the LeWin kernels.
+//
+// Every kernel processes one 128-row tile (128 tokens) per CTA with three roles:
+//   warps 0-3  "workers": 128 threads, thread r owns tile row r == TMEM lane r.  They gather /
+//              normalise the A operand into shared memory and run every epilogue.
+//   warp 4     "producer": lane 0 streams pre-swizzled weight chunk images global -> shared with
+//              cp.async.bulk (UBLKCP) into a ring of 16 KB stages guarded by full/empty mbarriers.
+//              The warp also owns the TMEM allocation.
+//   warp 5     "issuer": lane 0 issues every tcgen05.mma and commits completion to mbarriers.
+#pragma once
+#include "umma.cuh"
+
+namespace lw {
+
+constexpr int kWorkers = 128;
+constexpr int kThreads = 192;
+constexpr int kStageBytes = 16384;
+constexpr float kLog2e = 1.4426950408889634f;
+
+__device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes,
+                                         uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(dst_smem), "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+
+// Weight-chunk ring shared by producer and issuer.  Both walk the same static chunk schedule.
+struct Ring {
+  uint32_t base;       // smem address of stage 0
+  uint32_t full0;      // smem address of full[0]; full[s] = full0 + 8*s
+  uint32_t empty0;
+  int stages;
+  int idx;             // running chunk counter
+  __device__ __forceinline__ uint32_t stage_addr() const { return base + (idx % stages) * kStageBytes; }
+  __device__ __forceinline__ uint32_t full() const { return full0 + 8 * (idx % stages); }
+  __device__ __forceinline__ uint32_t empty() const { return empty0 + 8 * (idx % stages); }
+  __device__ __forceinline__ uint32_t phase() const { return (idx / stages) & 1; }
+  // producer side
+  __device__ __forceinline__ void load(const void* src, uint32_t bytes) {
+    mbar_wait(empty(), phase() ^ 1);
+    mbar_expect_tx(full(), bytes);
+    bulk_g2s(stage_addr(), src, bytes, full());
+    ++idx;
+  }
+  // issuer side: wait for the chunk, returns its smem address; call release() after the MMAs
+  __device__ __forceinline__ uint32_t acquire() {
+    mbar_wait(full(), phase());
+    tc_fence_after();
+    return stage_addr();
+  }
+  __device__ __forceinline__ void release() {
+    umma_commit(empty());
+    ++idx;
+  }
+};
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+}
+
+__device__ __forceinline__ void unpack8(const uint4& v, float* f) {
+  const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(p[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 v;
+  v.x = pack_bf16(f[0], f[1]);
+  v.y = pack_bf16(f[2], f[3]);
+  v.z = pack_bf16(f[4], f[5]);
+  v.w = pack_bf16(f[6], f[7]);
+  return v;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Stage a 128 x C bf16 A operand into shared memory in the K-major SWIZZLE_128B layout
+// ([C/64 k-blocks][128 rows][128 B]), optionally applying LayerNorm (fp32 statistics, biased
+// variance, eps inside the sqrt — nn.LayerNorm as at model.py:881,888) and adding a per-row
+// fp32 table (the window modulator, model.py:966-969).  row_tok[r] is the source token index of
+// tile row r (-1: row is padding -> zeros).  Executed by the 4 worker warps; warp w stages rows
+// [32w, 32w+32).  Lanes run along channels, so global reads are coalesced 16 B vectors.
+// ----------------------------------------------------------------------------------------------
+template <int C>
+__device__ __forceinline__ void stage_rows_ln(uint8_t* sX, const bf16* __restrict__ x,
+                                              const int* row_tok, const float* __restrict__ ln_w,
+                                              const float* __restrict__ ln_b, float eps,
+                                              const float* __restrict__ addtab /* [64][C] or null */) {
+  constexpr int VPL = (C >= 256) ? C / 256 : 1;   // 16-byte vectors per lane
+  constexpr int LPT = (C >= 256) ? 32 : C / 8;    // lanes per token
+  constexpr int TPP = 32 / LPT;                   // tokens per pass
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = lane % LPT;
+  for (int t0 = 0; t0 < 32; t0 += TPP) {
+    const int r = warp * 32 + t0 + lane / LPT;
+    const int tok = row_tok[r];
+    float v[VPL][8];
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      const int c0 = j * 256 + sub * 8;
+      if (tok >= 0) {
+        uint4 raw = __ldg(reinterpret_cast<const uint4*>(x + (size_t)tok * C + c0));
+        unpack8(raw, v[j]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[j][i] = 0.f;
+      }
+    }
+    if (ln_w != nullptr) {
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < VPL; ++j)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += v[j][i];
+#pragma unroll
+      for (int o = 1; o < LPT; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mean = s * (1.0f / C);
+      float q = 0.f;
+#pragma unroll
+      for (int j = 0; j < VPL; ++j)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float d = v[j][i] - mean;
+          q += d * d;
+        }
+#pragma unroll
+      for (int o = 1; o < LPT; o <<= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      const float rstd = rsqrtf(q * (1.0f / C) + eps);
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) {
+        const int c0 = j * 256 + sub * 8;
+        float4 g0 = __ldg(reinterpret_cast<const float4*>(ln_w + c0));
+        float4 g1 = __ldg(reinterpret_cast<const float4*>(ln_w + c0 + 4));
+        float4 b0 = __ldg(reinterpret_cast<const float4*>(ln_b + c0));
+        float4 b1 = __ldg(reinterpret_cast<const float4*>(ln_b + c0 + 4));
+        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[j][i] = (v[j][i] - mean) * rstd * g[i] + b[i];
+      }
+    }
+    if (addtab != nullptr && tok >= 0) {
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) {
+        const int c0 = j * 256 + sub * 8;
+        const float* t = addtab + (size_t)(r & 63) * C + c0;
+        float4 a0 = __ldg(reinterpret_cast<const float4*>(t));
+        float4 a1 = __ldg(reinterpret_cast<const float4*>(t + 4));
+        v[j][0] += a0.x; v[j][1] += a0.y; v[j][2] += a0.z; v[j][3] += a0.w;
+        v[j][4] += a1.x; v[j][5] += a1.y; v[j][6] += a1.z; v[j][7] += a1.w;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      const int c0 = j * 256 + sub * 8;
+      const uint32_t off = (c0 >> 6) * (128 * 128) + swz<128>(r, (c0 & 63) * 2);
+      *reinterpret_cast<uint4*>(sX + off) = pack8(v[j]);
+    }
+  }
+}
+
+}  // namespace lw

@@ -1,0 +1,346 @@
+"""Drop-in nn.Module surface of the reference's LeWin block engine (model.py, L0 in SURVEY §1).
+
+Each class keeps the reference's constructor signature, attributes, ``flops()`` and — crucially —
+the exact child-module tree, so ``state_dict()`` keys/shapes are identical (strict checkpoint
+loading, utils/model_utils.py:23-33) and ``Uformer._init_weights`` (model.py:1249-1256) still finds
+real nn.Linear / nn.LayerNorm children.  Only ``forward`` differs: it packs the parameters once
+(cached, invalidated on in-place updates) and calls the native sm_100a kernels.  Forward is
+inference-only this round (no autograd graph is built).  There is NO CPU path: calling forward on
+a non-CUDA tensor raises ``EngineUnavailable``.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib, ops, packing
+from ._lib import EngineUnavailable  # noqa: F401  (re-export)
+
+
+def _to_2tuple(v):
+    return tuple(v) if isinstance(v, (tuple, list)) else (v, v)
+
+
+class DropPath(nn.Module):
+    """Stochastic depth (timm semantics).  Identity in eval; the fused kernels do not implement the
+    training-time per-sample mask yet, so training-mode forward with p>0 raises in the block."""
+
+    def __init__(self, drop_prob: float = 0.0):
+        super().__init__()
+        self.drop_prob = drop_prob
+
+    def forward(self, x):
+        if self.drop_prob == 0.0 or not self.training:
+            return x
+        keep = 1.0 - self.drop_prob
+        shape = (x.shape[0],) + (1,) * (x.ndim - 1)
+        return x * x.new_empty(shape).bernoulli_(keep).div_(keep)
+
+
+class _PackCache:
+    """Packed-parameter cache: recomputed when any source tensor is replaced or modified in place."""
+
+    def __init__(self):
+        self._key = None
+        self._val = None
+
+    def get(self, tensors, build):
+        key = tuple((t.data_ptr(), t._version, str(t.device)) for t in tensors if t is not None)
+        if key != self._key:
+            with torch.no_grad():
+                self._val = build()
+            self._key = key
+        return self._val
+
+
+def _as_bf16(x):
+    """Module-boundary dtype policy: compute is bf16 (fp32 accumulate); other float dtypes are cast."""
+    if x.dtype == torch.bfloat16:
+        return x.contiguous(), None
+    if not torch.is_floating_point(x):
+        raise TypeError("expected a floating point tensor")
+    return x.to(torch.bfloat16).contiguous(), x.dtype
+
+
+def _no_grad_guard(*tensors):
+    _lib.require_device(tensors[0].device)      # device check first: no CPU fallback, fail loudly
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
+        raise NotImplementedError("uformer_b200: backward kernels are not implemented yet (inference only); "
+                                  "wrap the call in torch.no_grad()")
+
+
+# -------------------------------------------------------------------------------------------------
+class LinearProjection(nn.Module):
+    """Parameter container with the reference's names (model.py:421-447): to_q (C->C), to_kv (C->2C)."""
+
+    def __init__(self, dim, heads=8, dim_head=64, dropout=0., bias=True):
+        super().__init__()
+        inner_dim = dim_head * heads
+        self.heads = heads
+        self.to_q = nn.Linear(dim, inner_dim, bias=bias)
+        self.to_kv = nn.Linear(dim, inner_dim * 2, bias=bias)
+        self.dim = dim
+        self.inner_dim = inner_dim
+
+    def flops(self, q_L, kv_L=None):
+        kv_L = kv_L or q_L
+        return q_L * self.dim * self.inner_dim + kv_L * self.dim * self.inner_dim * 2
+
+
+class WindowAttention(nn.Module):
+    """model.py:452-546.  forward(x (B_, N, C), attn_kv=None, mask=None (nW, N, N)) -> (B_, N, C)."""
+
+    def __init__(self, dim, win_size, num_heads, token_projection='linear', qkv_bias=True, qk_scale=None,
+                 attn_drop=0., proj_drop=0.):
+        super().__init__()
+        if token_projection != 'linear':
+            raise NotImplementedError("uformer_b200 implements token_projection='linear' (every get_arch config)")
+        self.dim = dim
+        self.win_size = win_size
+        self.num_heads = num_heads
+        head_dim = dim // num_heads
+        self.scale = qk_scale or head_dim ** -0.5
+        n_rel = (2 * win_size[0] - 1) * (2 * win_size[1] - 1)
+        self.relative_position_bias_table = nn.Parameter(torch.zeros(n_rel, num_heads))
+        t = torch.arange(win_size[0] * win_size[1])
+        ty, tx = t // win_size[1], t % win_size[1]
+        idx = (ty[:, None] - ty[None, :] + win_size[0] - 1) * (2 * win_size[1] - 1) + (tx[:, None] - tx[None, :] + win_size[1] - 1)
+        self.register_buffer("relative_position_index", idx)
+        nn.init.trunc_normal_(self.relative_position_bias_table, std=.02)
+        self.qkv = LinearProjection(dim, num_heads, dim // num_heads, bias=qkv_bias)
+        self.token_projection = token_projection
+        self.attn_drop = nn.Dropout(attn_drop)
+        self.proj = nn.Linear(dim, dim)
+        self.proj_drop = nn.Dropout(proj_drop)
+        self.softmax = nn.Softmax(dim=-1)
+        self._cache = _PackCache()
+
+    # ---- packing -------------------------------------------------------------------------------
+    def packed(self):
+        q, kv, pr = self.qkv.to_q, self.qkv.to_kv, self.proj
+        srcs = [q.weight, q.bias, kv.weight, kv.bias, pr.weight, pr.bias, self.relative_position_bias_table]
+
+        def build():
+            C = self.dim
+            dev = q.weight.device
+            bq = q.bias if q.bias is not None else torch.zeros(C, device=dev)
+            bkv = kv.bias if kv.bias is not None else torch.zeros(2 * C, device=dev)
+            wimg, bqkv = packing.pack_qkv(q.weight, bq, kv.weight, bkv, self.num_heads, float(self.scale))
+            return dict(wqkv_img=wimg, bqkv=bqkv, wproj_img=packing.pack_kmajor(pr.weight, min(C, 128), "nk"),
+                        bproj=pr.bias.float().contiguous(), relpos=packing.pack_relpos(self.relative_position_bias_table),
+                        head_dim=C // self.num_heads)
+        return self._cache.get(srcs, build)
+
+    def _check_supported(self):
+        if tuple(self.win_size) != (8, 8):
+            raise NotImplementedError(f"uformer_b200 kernels are specialised for 8x8 windows (got {self.win_size})")
+        hd = self.dim // self.num_heads
+        if hd not in (16, 32) or self.dim % hd or self.dim > 512 or (hd == 16 and self.dim > 256):
+            raise NotImplementedError(f"unsupported (dim={self.dim}, heads={self.num_heads})")
+        if self.attn_drop.p > 0 and self.training or self.proj_drop.p > 0 and self.training:
+            raise NotImplementedError("attention/projection dropout is not implemented (p=0 in every Uformer config)")
+
+    def forward(self, x, attn_kv=None, mask=None):
+        if attn_kv is not None:
+            raise NotImplementedError("cross-attention keys (attn_kv) are never used by Uformer configs")
+        self._check_supported()
+        _no_grad_guard(x, self.proj.weight)
+        xb, back = _as_bf16(x)
+        out = ops.wmsa(xb, self.packed(), H=0, W=0, shift=0, windowed=True, resid=None, mask=mask)
+        return out if back is None else out.to(back)
+
+    def extra_repr(self) -> str:
+        return f'dim={self.dim}, win_size={self.win_size}, num_heads={self.num_heads}'
+
+    def flops(self, H, W):
+        N = self.win_size[0] * self.win_size[1]
+        nW = H * W / N
+        hd = self.dim // self.num_heads
+        return (self.qkv.flops(H * W, H * W) + nW * self.num_heads * N * hd * N + nW * self.num_heads * N * N * hd
+                + nW * N * self.dim * self.dim)
+
+
+# -------------------------------------------------------------------------------------------------
+class LeFF(nn.Module):
+    """model.py:654-699.  forward(x (B, HW, C)) -> (B, HW, C)."""
+
+    def __init__(self, dim=32, hidden_dim=128, act_layer=nn.GELU, drop=0., use_eca=False):
+        super().__init__()
+        if act_layer is not nn.GELU or use_eca:
+            raise NotImplementedError("uformer_b200 LeFF: exact GELU, no ECA (as in every Uformer config)")
+        self.linear1 = nn.Sequential(nn.Linear(dim, hidden_dim), act_layer())
+        self.dwconv = nn.Sequential(nn.Conv2d(hidden_dim, hidden_dim, groups=hidden_dim, kernel_size=3, stride=1, padding=1),
+                                    act_layer())
+        self.linear2 = nn.Sequential(nn.Linear(hidden_dim, dim))
+        self.dim = dim
+        self.hidden_dim = hidden_dim
+        self.eca = nn.Identity()
+        self._cache = _PackCache()
+
+    def packed(self):
+        l1, dw, l2 = self.linear1[0], self.dwconv[0], self.linear2[0]
+        srcs = [l1.weight, l1.bias, dw.weight, dw.bias, l2.weight, l2.bias]
+
+        def build():
+            wd, bd = packing.pack_dwconv(dw.weight, dw.bias)
+            return dict(w1_img=packing.pack_kmajor(l1.weight, min(self.hidden_dim, 128), "nk"), b1=l1.bias.float().contiguous(),
+                        wd=wd, bd=bd, w2_img=packing.pack_kmajor(l2.weight, min(self.dim, 128), "kn"),
+                        b2=l2.bias.float().contiguous(), hidden=self.hidden_dim)
+        return self._cache.get(srcs, build)
+
+    def _check_supported(self):
+        if self.dim % 16 or self.dim > 512 or self.hidden_dim % 64 or self.dim not in (16, 32, 64, 128, 256, 512):
+            raise NotImplementedError(f"unsupported LeFF dims ({self.dim}, {self.hidden_dim})")
+
+    def forward(self, x):
+        self._check_supported()
+        _no_grad_guard(x, self.linear1[0].weight)
+        B, L, _ = x.shape
+        H = int(math.sqrt(L))
+        xb, back = _as_bf16(x)
+        out = ops.leff(xb, self.packed(), B=B, H=H, W=H, resid=None)
+        return out if back is None else out.to(back)
+
+    def flops(self, H, W):
+        return H * W * self.dim * self.hidden_dim + H * W * self.hidden_dim * 3 * 3 + H * W * self.hidden_dim * self.dim
+
+
+# -------------------------------------------------------------------------------------------------
+class Downsample(nn.Module):
+    """model.py:730-753: tokens -> Conv2d(k4,s2,p1) -> tokens."""
+
+    def __init__(self, in_channel, out_channel):
+        super().__init__()
+        self.conv = nn.Sequential(nn.Conv2d(in_channel, out_channel, kernel_size=4, stride=2, padding=1))
+        self.in_channel = in_channel
+        self.out_channel = out_channel
+        self._cache = _PackCache()
+
+    def packed(self):
+        cv = self.conv[0]
+        return self._cache.get([cv.weight, cv.bias], lambda: dict(
+            w_img=packing.pack_downsample(cv.weight, min(self.out_channel, 128)), bias=cv.bias.float().contiguous(),
+            cout=self.out_channel))
+
+    def forward(self, x):
+        _no_grad_guard(x, self.conv[0].weight)
+        B, L, _ = x.shape
+        H = int(math.sqrt(L))
+        xb, back = _as_bf16(x)
+        out = ops.downsample(xb, self.packed(), B=B, H=H, W=H)
+        return out if back is None else out.to(back)
+
+    def flops(self, H, W):
+        return H / 2 * W / 2 * self.in_channel * self.out_channel * 4 * 4
+
+
+class Upsample(nn.Module):
+    """model.py:756-778: tokens -> ConvTranspose2d(k2,s2) -> tokens."""
+
+    def __init__(self, in_channel, out_channel):
+        super().__init__()
+        self.deconv = nn.Sequential(nn.ConvTranspose2d(in_channel, out_channel, kernel_size=2, stride=2))
+        self.in_channel = in_channel
+        self.out_channel = out_channel
+        self._cache = _PackCache()
+
+    def packed(self):
+        dc = self.deconv[0]
+        return self._cache.get([dc.weight, dc.bias], lambda: dict(
+            w_img=packing.pack_upsample(dc.weight, min(4 * self.out_channel, 128)), bias=dc.bias.float().contiguous(),
+            cout=self.out_channel))
+
+    def forward(self, x, out=None):
+        _no_grad_guard(x, self.deconv[0].weight)
+        B, L, _ = x.shape
+        H = int(math.sqrt(L))
+        xb, back = _as_bf16(x)
+        res = ops.upsample(xb, self.packed(), B=B, H=H, W=H, out=out)
+        return res if back is None else res.to(back)
+
+    def flops(self, H, W):
+        # same expression as the reference (model.py:773-778), which over-counts 4x
+        return H * 2 * W * 2 * self.in_channel * self.out_channel * 2 * 2
+
+
+# -------------------------------------------------------------------------------------------------
+class LeWinTransformerBlock(nn.Module):
+    """model.py:850-1008.  forward(x (B, HW, C), mask=None) -> (B, HW, C), three kernel launches:
+    fused W-MSA (LN1..first residual), LeFF part 1 (LN2+Linear1+GELU), LeFF part 2 (dwconv..second residual)."""
+
+    def __init__(self, dim, input_resolution, num_heads, win_size=8, shift_size=0, mlp_ratio=4., qkv_bias=True,
+                 qk_scale=None, drop=0., attn_drop=0., drop_path=0., act_layer=nn.GELU, norm_layer=nn.LayerNorm,
+                 token_projection='linear', token_mlp='leff', modulator=False, cross_modulator=False):
+        super().__init__()
+        if token_mlp != 'leff' or cross_modulator or norm_layer is not nn.LayerNorm:
+            raise NotImplementedError("uformer_b200 block: token_mlp='leff', LayerNorm, no cross-modulator "
+                                      "(every get_arch config, utils/model_utils.py:56-81)")
+        self.dim = dim
+        self.input_resolution = input_resolution
+        self.num_heads = num_heads
+        self.win_size = win_size
+        self.shift_size = shift_size
+        self.mlp_ratio = mlp_ratio
+        self.token_mlp = token_mlp
+        if min(self.input_resolution) <= self.win_size:          # construction-time clamp, model.py:863-865
+            self.shift_size = 0
+            self.win_size = min(self.input_resolution)
+        assert 0 <= self.shift_size < self.win_size, "shift_size must in 0-win_size"
+        self.modulator = nn.Embedding(win_size * win_size, dim) if modulator else None
+        self.cross_modulator = None
+        self.norm1 = norm_layer(dim)
+        self.attn = WindowAttention(dim, win_size=_to_2tuple(self.win_size), num_heads=num_heads, qkv_bias=qkv_bias,
+                                    qk_scale=qk_scale, attn_drop=attn_drop, proj_drop=drop, token_projection=token_projection)
+        self.drop_path = DropPath(drop_path) if drop_path > 0. else nn.Identity()
+        self.norm2 = norm_layer(dim)
+        self.mlp = LeFF(dim, int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
+        self._cache = _PackCache()
+
+    def extra_repr(self) -> str:
+        return (f"dim={self.dim}, input_resolution={self.input_resolution}, num_heads={self.num_heads}, "
+                f"win_size={self.win_size}, shift_size={self.shift_size}, mlp_ratio={self.mlp_ratio},modulator={self.modulator}")
+
+    def packed(self):
+        srcs = [self.norm1.weight, self.norm1.bias, self.norm2.weight, self.norm2.bias,
+                self.modulator.weight if self.modulator is not None else None]
+
+        def build():
+            return dict(ln1_w=self.norm1.weight.float().contiguous(), ln1_b=self.norm1.bias.float().contiguous(),
+                        ln2_w=self.norm2.weight.float().contiguous(), ln2_b=self.norm2.bias.float().contiguous(),
+                        modulator=None if self.modulator is None else self.modulator.weight.float().contiguous())
+        return self._cache.get(srcs, build)
+
+    @staticmethod
+    def input_mask_to_attn_mask(mask, H, W, ws):
+        """(B,1,h,w) input mask -> additive (B*nW, N, N) mask, model.py:914-921 (host side, rarely used)."""
+        m = torch.nn.functional.interpolate(mask.float(), size=(H, W)).permute(0, 2, 3, 1)
+        B = m.shape[0]
+        m = m.view(B, H // ws, ws, W // ws, ws, 1).permute(0, 1, 3, 2, 4, 5).reshape(-1, ws * ws)
+        am = m.unsqueeze(2) * m.unsqueeze(1)
+        return torch.where(am != 0, torch.full_like(am, -100.0), torch.zeros_like(am))
+
+    def forward(self, x, mask=None):
+        B, L, C = x.shape
+        H = W = int(math.sqrt(L))
+        if H * W != L or H % 8 or self.win_size != 8:
+            raise NotImplementedError(f"uformer_b200 block needs a square token map with side % 8 == 0 and 8x8 windows "
+                                      f"(L={L}, win_size={self.win_size})")
+        if self.training and isinstance(self.drop_path, DropPath) and self.drop_path.drop_prob > 0:
+            raise NotImplementedError("stochastic depth in training mode is not fused yet; call .eval()")
+        self.attn._check_supported()
+        self.mlp._check_supported()
+        _no_grad_guard(x, self.norm1.weight)
+        xb, back = _as_bf16(x)
+        pk = self.packed()
+        pa = dict(self.attn.packed(), ln_w=pk["ln1_w"], ln_b=pk["ln1_b"], modulator=pk["modulator"], ln_eps=self.norm1.eps)
+        amask = None if mask is None else self.input_mask_to_attn_mask(mask.to(x.device), H, W, 8)
+        x1 = ops.wmsa(xb, pa, H=H, W=W, shift=self.shift_size, windowed=False, resid=xb, mask=amask)
+        pm = dict(self.mlp.packed(), ln_w=pk["ln2_w"], ln_b=pk["ln2_b"], ln_eps=self.norm2.eps)
+        out = ops.leff(x1, pm, B=B, H=H, W=W, resid=x1)
+        return out if back is None else out.to(back)
+
+    def flops(self):
+        H, W = self.input_resolution
+        return self.dim * H * W + self.attn.flops(H, W) + self.dim * H * W + self.mlp.flops(H, W)

@@ -1,0 +1,179 @@
+"""Caller side of the engine: the U-shaped stage wiring (reference L1: BasicUformerLayer
+model.py:1013-1066 and Uformer model.py:1069-1328), re-expressed as a data-driven stage table so the
+engine can be driven where the reference's model.py is not importable (the GPU box).  Attribute /
+state-dict names match the reference exactly, so its checkpoints load with strict=True.
+
+Everything runs in this library's kernels: input projection (fp32 NCHW -> bf16 tokens), 9 LeWin
+stages, 4 Downsample / 4 Upsample, output projection (+ global residual, -> fp32 NCHW).  The
+skip-concat (model.py:1288-1300) is folded: Upsample writes straight into the left half of the
+decoder input buffer, the skip is copied once into the right half.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .modules import Downsample, LeWinTransformerBlock, Upsample, _no_grad_guard
+
+_STAGE_NAMES = ["encoderlayer_0", "encoderlayer_1", "encoderlayer_2", "encoderlayer_3", "conv",
+                "decoderlayer_0", "decoderlayer_1", "decoderlayer_2", "decoderlayer_3"]
+
+
+class LeWinStage(nn.Module):
+    """`depth` LeWin blocks at one resolution; odd blocks are shifted by win_size//2 (model.py:1030)."""
+
+    def __init__(self, dim, output_dim, input_resolution, depth, num_heads, win_size, mlp_ratio=4., qkv_bias=True,
+                 qk_scale=None, drop=0., attn_drop=0., drop_path=0., norm_layer=nn.LayerNorm, use_checkpoint=False,
+                 token_projection='linear', token_mlp='leff', shift_flag=True, modulator=False, cross_modulator=False):
+        super().__init__()
+        self.dim, self.input_resolution, self.depth, self.use_checkpoint = dim, input_resolution, depth, use_checkpoint
+        self.blocks = nn.ModuleList([
+            LeWinTransformerBlock(dim=dim, input_resolution=input_resolution, num_heads=num_heads, win_size=win_size,
+                                  shift_size=win_size // 2 if (shift_flag and i % 2 == 1) else 0, mlp_ratio=mlp_ratio,
+                                  qkv_bias=qkv_bias, qk_scale=qk_scale, drop=drop, attn_drop=attn_drop,
+                                  drop_path=drop_path[i] if isinstance(drop_path, list) else drop_path,
+                                  norm_layer=norm_layer, token_projection=token_projection, token_mlp=token_mlp,
+                                  modulator=modulator, cross_modulator=cross_modulator)
+            for i in range(depth)])
+
+    def extra_repr(self):
+        return f"dim={self.dim}, input_resolution={self.input_resolution}, depth={self.depth}"
+
+    def forward(self, x, mask=None):
+        for blk in self.blocks:
+            x = blk(x, mask)
+        return x
+
+    def flops(self):
+        return sum(b.flops() for b in self.blocks)
+
+
+class InputProj(nn.Module):
+    """model.py:781-812 parameter container; arithmetic in ops.input_proj."""
+
+    def __init__(self, in_channel=3, out_channel=64, kernel_size=3, stride=1, norm_layer=None, act_layer=nn.LeakyReLU):
+        super().__init__()
+        self.proj = nn.Sequential(nn.Conv2d(in_channel, out_channel, kernel_size=3, stride=stride, padding=kernel_size // 2),
+                                  act_layer(inplace=True))
+        self.norm = None
+        self.in_channel, self.out_channel = in_channel, out_channel
+
+    def forward(self, x):
+        cv = self.proj[0]
+        return ops.input_proj(x, cv.weight.detach().float().contiguous(), cv.bias.detach().float().contiguous())
+
+    def flops(self, H, W):
+        return H * W * self.in_channel * self.out_channel * 3 * 3
+
+
+class OutputProj(nn.Module):
+    """model.py:815-846 parameter container; arithmetic (+ global residual) in ops.output_proj."""
+
+    def __init__(self, in_channel=64, out_channel=3, kernel_size=3, stride=1, norm_layer=None, act_layer=None):
+        super().__init__()
+        self.proj = nn.Sequential(nn.Conv2d(in_channel, out_channel, kernel_size=3, stride=stride, padding=kernel_size // 2))
+        self.norm = None
+        self.in_channel, self.out_channel = in_channel, out_channel
+
+    def forward(self, x, residual=None):
+        B, L, C = x.shape
+        H = int(math.sqrt(L))
+        cv = self.proj[0]
+        xb = x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16)
+        return ops.output_proj(xb.contiguous(), cv.weight.detach().float().contiguous(), cv.bias.detach().float().contiguous(),
+                               residual, H, H)
+
+    def flops(self, H, W):
+        return H * W * self.in_channel * self.out_channel * 3 * 3
+
+
+class Uformer(nn.Module):
+    """Same constructor keywords and state-dict as the reference's Uformer (model.py:1069-1247)."""
+
+    def __init__(self, img_size=256, in_chans=3, dd_in=3, embed_dim=32, depths=(2, 2, 2, 2, 2, 2, 2, 2, 2),
+                 num_heads=(1, 2, 4, 8, 16, 16, 8, 4, 2), win_size=8, mlp_ratio=4., qkv_bias=True, qk_scale=None,
+                 drop_rate=0., attn_drop_rate=0., drop_path_rate=0.1, norm_layer=nn.LayerNorm, patch_norm=True,
+                 use_checkpoint=False, token_projection='linear', token_mlp='leff', dowsample=Downsample, upsample=Upsample,
+                 shift_flag=True, modulator=False, cross_modulator=False, **kwargs):
+        super().__init__()
+        depths = list(depths)
+        self.num_enc_layers = self.num_dec_layers = len(depths) // 2
+        self.embed_dim, self.patch_norm, self.mlp_ratio = embed_dim, patch_norm, mlp_ratio
+        self.token_projection, self.mlp, self.win_size, self.reso, self.dd_in = token_projection, token_mlp, win_size, img_size, dd_in
+        self.pos_drop = nn.Dropout(p=drop_rate)
+        E = embed_dim
+        # stochastic-depth schedule (model.py:1093-1095)
+        enc_dpr = [v.item() for v in torch.linspace(0, drop_path_rate, sum(depths[:4]))]
+        dec_dpr = enc_dpr[::-1]
+        dpr = []
+        for i in range(4):
+            dpr.append(enc_dpr[sum(depths[:i]):sum(depths[:i + 1])])
+        dpr.append([drop_path_rate] * depths[4])
+        dpr.append(dec_dpr[:depths[5]])
+        for j in range(1, 4):
+            dpr.append(dec_dpr[sum(depths[5:5 + j]):sum(depths[5:6 + j])])
+
+        self.input_proj = InputProj(in_channel=dd_in, out_channel=E, kernel_size=3, stride=1, act_layer=nn.LeakyReLU)
+        self.output_proj = OutputProj(in_channel=2 * E, out_channel=in_chans, kernel_size=3, stride=1)
+        dims = [E, 2 * E, 4 * E, 8 * E, 16 * E, 16 * E, 8 * E, 4 * E, 2 * E]
+        reso = [img_size // (2 ** s) for s in (0, 1, 2, 3, 4, 3, 2, 1, 0)]
+        for i, name in enumerate(_STAGE_NAMES):
+            decoder = i >= 5
+            stage = LeWinStage(dim=dims[i], output_dim=dims[i], input_resolution=(reso[i], reso[i]), depth=depths[i],
+                               num_heads=num_heads[i], win_size=win_size, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias,
+                               qk_scale=qk_scale, drop=drop_rate, attn_drop=attn_drop_rate, drop_path=dpr[i],
+                               norm_layer=norm_layer, use_checkpoint=use_checkpoint, token_projection=token_projection,
+                               token_mlp=token_mlp, shift_flag=shift_flag,
+                               modulator=modulator if decoder else False, cross_modulator=cross_modulator if decoder else False)
+            setattr(self, name, stage)
+            if i < 4:
+                setattr(self, f"dowsample_{i}", dowsample(dims[i], dims[i + 1]))
+        up_io = [(16 * E, 8 * E), (16 * E, 4 * E), (8 * E, 2 * E), (4 * E, E)]
+        for j, (ci, co) in enumerate(up_io):
+            setattr(self, f"upsample_{j}", upsample(ci, co))
+        self.apply(self._init_weights)
+
+    def _init_weights(self, m):
+        if isinstance(m, nn.Linear):
+            nn.init.trunc_normal_(m.weight, std=.02)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.constant_(m.bias, 0)
+            nn.init.constant_(m.weight, 1.0)
+
+    def extra_repr(self):
+        return f"embed_dim={self.embed_dim}, token_projection={self.token_projection}, token_mlp={self.mlp},win_size={self.win_size}"
+
+    @torch.no_grad()
+    def forward(self, x, mask=None):
+        """x: (B, dd_in, H, W) float image on a B200; returns fp32 (B, in_chans, H, W)."""
+        _no_grad_guard(x)
+        B = x.shape[0]
+        y = self.input_proj(x)
+        skips = []
+        for i in range(4):
+            y = getattr(self, f"encoderlayer_{i}")(y, mask)
+            skips.append(y)
+            y = getattr(self, f"dowsample_{i}")(y)
+        y = self.conv(y, mask)
+        for j in range(4):
+            up = getattr(self, f"upsample_{j}")
+            skip = skips[3 - j]
+            co = up.out_channel
+            cat = torch.empty((B, skip.shape[1], co + skip.shape[2]), dtype=torch.bfloat16, device=y.device)
+            up(y, out=cat)                      # left half: transposed-conv output, written in place
+            cat[:, :, co:].copy_(skip)          # right half: encoder skip
+            y = getattr(self, f"decoderlayer_{j}")(cat, mask)
+        return self.output_proj(y, x if self.dd_in == 3 else None)
+
+    def flops(self):
+        r = self.reso
+        f = self.input_proj.flops(r, r) + self.output_proj.flops(r, r) + self.conv.flops()
+        for i in range(4):
+            f += getattr(self, f"encoderlayer_{i}").flops() + getattr(self, f"dowsample_{i}").flops(r // 2 ** i, r // 2 ** i)
+            f += getattr(self, f"upsample_{i}").flops(r // 2 ** (4 - i), r // 2 ** (4 - i)) + getattr(self, f"decoderlayer_{i}").flops()
+        return f

@@ -1,0 +1,129 @@
+"""Functional layer: torch tensors in, native sm_100a kernels (C ABI via ctypes) out.
+
+All activations are bf16 CUDA tensors in the reference's token layout (B, H*W, C).  Launches go on
+torch's current stream, never synchronise and never allocate inside the library (outputs are
+torch.empty'd here), so a whole forward is CUDA-graph capturable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+Tensor = torch.Tensor
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _check_act(x: Tensor, name: str):
+    if x.dtype != torch.bfloat16:
+        raise TypeError(f"{name} must be bfloat16 (got {x.dtype}); use the module wrappers for dtype conversion")
+    if not x.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    _lib.require_device(x.device)
+
+
+def wmsa(x: Tensor, p: dict, *, H: int, W: int, shift: int, windowed: bool, resid: Tensor | None,
+         mask: Tensor | None = None, out: Tensor | None = None) -> Tensor:
+    """Fused (LN) + (roll/partition) + W-MSA + proj + (reverse/unroll) + (residual).
+    p: packed parameter dict from modules._pack_attention (+ optional ln_w/ln_b/modulator)."""
+    _check_act(x, "x")
+    Cc = x.shape[-1]
+    if windowed:
+        n_windows = x.shape[0]
+    else:
+        n_windows = x.shape[0] * (H // 8) * (W // 8)
+    if out is None:
+        out = torch.empty_like(x)
+    a = _lib.WmsaArgs()
+    a.x, a.out, a.resid = _ptr(x), _ptr(out), _ptr(resid)
+    a.ln_w, a.ln_b, a.modulator = _ptr(p.get("ln_w")), _ptr(p.get("ln_b")), _ptr(p.get("modulator"))
+    a.wqkv_img, a.bqkv, a.wproj_img, a.bproj, a.relpos = (_ptr(p["wqkv_img"]), _ptr(p["bqkv"]), _ptr(p["wproj_img"]),
+                                                          _ptr(p["bproj"]), _ptr(p["relpos"]))
+    if mask is not None:
+        mask = mask.to(device=x.device, dtype=torch.float32).contiguous()
+        a.mask, a.n_mask_windows = _ptr(mask), mask.shape[0]
+    a.n_windows, a.H, a.W, a.C, a.head_dim = n_windows, H, W, Cc, p["head_dim"]
+    a.shift, a.windowed, a.ln_eps = shift, int(windowed), p.get("ln_eps", 1e-5)
+    _lib.check(_lib.load().lw_wmsa_fwd(C.byref(a), _stream()), "lw_wmsa_fwd")
+    return out
+
+
+def leff(x: Tensor, p: dict, *, B: int, H: int, W: int, resid: Tensor | None, out: Tensor | None = None) -> Tensor:
+    """(LN) + Linear1 + GELU  ->  dwconv3x3 + GELU + Linear2 (+ residual).  Two launches; the hidden map
+    makes one bf16 round trip through HBM/L2 between them."""
+    _check_act(x, "x")
+    Cc, hidden = x.shape[-1], p["hidden"]
+    n_tokens = B * H * W
+    h1 = torch.empty((n_tokens, hidden), dtype=torch.bfloat16, device=x.device)
+    a = _lib.Leff1Args()
+    a.x, a.h1, a.ln_w, a.ln_b = _ptr(x), _ptr(h1), _ptr(p.get("ln_w")), _ptr(p.get("ln_b"))
+    a.w1_img, a.b1 = _ptr(p["w1_img"]), _ptr(p["b1"])
+    a.n_tokens, a.C, a.hidden, a.ln_eps = n_tokens, Cc, hidden, p.get("ln_eps", 1e-5)
+    lib = _lib.load()
+    _lib.check(lib.lw_leff1_fwd(C.byref(a), _stream()), "lw_leff1_fwd")
+    if out is None:
+        out = torch.empty_like(x)
+    b = _lib.Leff2Args()
+    b.h1, b.out, b.resid = _ptr(h1), _ptr(out), _ptr(resid)
+    b.wd, b.bd, b.w2_img, b.b2 = _ptr(p["wd"]), _ptr(p["bd"]), _ptr(p["w2_img"]), _ptr(p["b2"])
+    b.B, b.H, b.W, b.C, b.hidden = B, H, W, Cc, hidden
+    _lib.check(lib.lw_leff2_fwd(C.byref(b), _stream()), "lw_leff2_fwd")
+    return out
+
+
+def downsample(x: Tensor, p: dict, *, B: int, H: int, W: int) -> Tensor:
+    _check_act(x, "x")
+    Cin, Cout = x.shape[-1], p["cout"]
+    out = torch.empty((B, (H // 2) * (W // 2), Cout), dtype=torch.bfloat16, device=x.device)
+    a = _lib.DownArgs()
+    a.x, a.out, a.w_img, a.bias = _ptr(x), _ptr(out), _ptr(p["w_img"]), _ptr(p["bias"])
+    a.B, a.H, a.W, a.Cin, a.Cout = B, H, W, Cin, Cout
+    _lib.check(_lib.load().lw_downsample_fwd(C.byref(a), _stream()), "lw_downsample_fwd")
+    return out
+
+
+def upsample(x: Tensor, p: dict, *, B: int, H: int, W: int, out: Tensor | None = None) -> Tensor:
+    """out may be a wider (B, 4HW, S) buffer (skip-concat fusion): the first Cout channels are written."""
+    _check_act(x, "x")
+    Cin, Cout = x.shape[-1], p["cout"]
+    if out is None:
+        out = torch.empty((B, 4 * H * W, Cout), dtype=torch.bfloat16, device=x.device)
+    a = _lib.UpArgs()
+    a.x, a.out, a.w_img, a.bias = _ptr(x), _ptr(out), _ptr(p["w_img"]), _ptr(p["bias"])
+    a.B, a.H, a.W, a.Cin, a.Cout, a.out_stride = B, H, W, Cin, Cout, out.shape[-1]
+    _lib.check(_lib.load().lw_upsample_fwd(C.byref(a), _stream()), "lw_upsample_fwd")
+    return out
+
+
+def input_proj(img: Tensor, w: Tensor, b: Tensor) -> Tensor:
+    """NCHW fp32 image -> bf16 tokens (B, H*W, E): conv3x3 + LeakyReLU(0.01)."""
+    _lib.require_device(img.device)
+    img = img.float().contiguous()
+    B, Cin, H, W = img.shape
+    E = w.shape[0]
+    tok = torch.empty((B, H * W, E), dtype=torch.bfloat16, device=img.device)
+    _lib.check(_lib.load().lw_input_proj_fwd(_ptr(img), _ptr(w), _ptr(b), _ptr(tok), B, Cin, H, W, E, _stream()),
+               "lw_input_proj_fwd")
+    return tok
+
+
+def output_proj(tok: Tensor, w: Tensor, b: Tensor, img: Tensor | None, H: int, W: int) -> Tensor:
+    """bf16 tokens (B, H*W, Cin) -> NCHW fp32 conv3x3 output (+ img residual)."""
+    _check_act(tok, "tokens")
+    B, _, Cin = tok.shape
+    Cout = w.shape[0]
+    out = torch.empty((B, Cout, H, W), dtype=torch.float32, device=tok.device)
+    if img is not None:
+        img = img.float().contiguous()
+    _lib.check(_lib.load().lw_output_proj_fwd(_ptr(tok), _ptr(w), _ptr(b), _ptr(img), _ptr(out), B, Cin, H, W, Cout, _stream()),
+               "lw_output_proj_fwd")
+    return out
