@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""bench.py — images/sec of the Uformer-B 256x256 forward (BASELINE.json configs[1]) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+
+A "step" is one forward of a batch of 32 synthetic 256x256x3 images through the native engine
+(bf16 activations, fp32 accumulate).  Weights: Uformer-B architecture, seeded synthetic init
+(tests/paramgen.py).  N>1 (torchrun): independent replicas, one per GPU, no data-path collective
+(inference shards by image); value = images of all ranks / max-over-ranks device time.
+
+Timing: per-step CUDA events on the launching stream; an L2 flush (256 MB memset) runs between
+timed steps outside the event brackets; W>=3 warm-up steps.  `e2e` repeats the measurement through
+the public API with pinned HOST input, H2D copy and D2H of the restored image inside the timed region.
+`roofline` is the dominant kernel class (largest share of step time), timed live with CUDA events
+in an extra instrumented step.  `cpu_baseline` / `--impl reference` time the CPU oracle port of the
+reference forward (oracle/lewin_oracle.py; the reference itself is Python and cannot travel to the
+GPU box) on the host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import torch  # noqa: E402
+
+UFORMER_B = dict(img_size=256, embed_dim=32, win_size=8, token_projection="linear", token_mlp="leff",
+                 depths=[1, 2, 8, 8, 2, 8, 8, 2, 1], modulator=True, dd_in=3)       # utils/model_utils.py:76-78
+GFLOP_PER_IMG = 173.1          # BASELINE.md §2 (2 x 86.57 GMAC)
+
+
+def note(msg):
+    """progress line on stderr (stdout carries only the JSON line)"""
+    print(f"[bench {time.strftime('%X')}] {msg}", file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons of one GPU with nvidia-smi while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons, samples=len(sm))
+
+
+def build_engine(device, seed=1234):
+    import uformer_b200
+    from paramgen import randomize_state
+    net = uformer_b200.Uformer(**UFORMER_B)
+    net.load_state_dict(randomize_state(net.state_dict(), seed), strict=True)
+    return net.to(device).eval()
+
+
+def _cpu_forward_fn(n_images):
+    """Closure running the CPU oracle port (library-op formulation, fp32) of the Uformer-B forward."""
+    from oracle import lewin_oracle as O
+    from paramgen import randomize_state
+    import uformer_b200
+    O.FAST = True
+    st = randomize_state(uformer_b200.Uformer(**UFORMER_B).state_dict(), 1234)
+    torch.manual_seed(1234)
+    x = torch.rand(n_images, 3, 256, 256)
+
+    def fwd():
+        with torch.no_grad():
+            return O.uformer_forward(x, st, 256, 32, UFORMER_B["depths"])
+    return fwd
+
+
+def _pick_threads(fwd):
+    """torch's CPU ops do not scale to 128 threads on these shapes; pick the best of a few counts
+    (one forward each) so the baseline uses the host as well as it can."""
+    best, best_t = None, None
+    ncpu = os.cpu_count() or 8
+    for th in sorted({min(ncpu, c) for c in (16, 32, 64)}):
+        torch.set_num_threads(th)
+        fwd()
+        t0 = time.perf_counter()
+        fwd()
+        dt = time.perf_counter() - t0
+        note(f"cpu port: {th} threads -> {dt:.2f}s per forward")
+        if best is None or dt < best:
+            best, best_t = dt, th
+    torch.set_num_threads(best_t)
+    return best_t
+
+
+def cpu_oracle_rate(n_images, iters=2):
+    """images/sec of the CPU oracle port on `n_images` 256x256 images (bounded sample)."""
+    fwd = _cpu_forward_fn(n_images)
+    threads = _pick_threads(fwd)
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        fwd()
+    dt = (time.perf_counter() - t0) / iters
+    return n_images / dt, threads, dt
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    nimg = 4                         # bounded sample of the batch-32 step
+    fwd = _cpu_forward_fn(nimg)
+    threads = _pick_threads(fwd)     # doubles as warm-up
+    steps, warm = max(1, min(args.steps, 5)), 1
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fwd()
+    dt = (time.perf_counter() - t0) / steps
+    v = nimg / dt
+    sample = (f"{nimg} images of the batch-32 step per timed step (fp32 oracle port of model.py's forward, torch CPU ops, "
+              f"{threads} of {os.cpu_count()} host threads = best of 16/32/64)")
+    print(json.dumps({
+        "impl": "reference", "metric": "images/sec Uformer-B 256x256 fwd", "value": v, "unit": "img/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": "Uformer-B 256x256 inference fwd (BASELINE configs[1]), CPU port of the reference forward",
+                   "global_batch": nimg},
+        "cpu_baseline": {"value": v, "unit": "img/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from uformer_b200 import ops
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    warm = max(args.warmup, 3)
+    B = args.batch
+    net = build_engine(dev)
+    torch.manual_seed(1234 + rank)
+    x_host = torch.rand(B, 3, 256, 256).pin_memory()
+    x_dev = x_host.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    y_host = torch.empty(B, 3, 256, 256).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        for s, e in evs:
+            flush.zero_()                    # L2 flush, outside the event bracket
+            s.record()
+            fn()
+            e.record()
+        barrier()
+        ms = sum(s.elapsed_time(e) for s, e in evs)
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    def step_dev():
+        return net(x_dev)
+
+    def step_e2e():
+        xd = x_host.to(dev, non_blocking=True)
+        y = net(xd)
+        y_host.copy_(y, non_blocking=True)
+
+    note("engine built; warm-up")
+    for _ in range(warm):
+        step_dev()
+    torch.cuda.synchronize()
+    note("timing device-resident steps")
+    ops.LAUNCH_COUNT = 0
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    total_ms = timed(step_dev, args.steps)
+    launches = ops.LAUNCH_COUNT
+    clocks = sampler.stop() if rank == 0 else None
+    note(f"device-resident: {total_ms / args.steps:.2f} ms/step; timing e2e (host buffers)")
+    for _ in range(2):
+        step_e2e()
+    e2e_ms = timed(step_e2e, args.steps)
+
+    # ---- instrumented step: per-kernel-class device time (CUDA events around every launch) ----
+    prof = None
+    if rank == 0:
+        ops.PROFILE = []
+        step_dev()
+        torch.cuda.synchronize()
+        rec, ops.PROFILE = ops.PROFILE, None
+        agg = {}
+        for label, flops, s, e in rec:
+            a = agg.setdefault(label, [0.0, 0, 0.0])
+            a[0] += s.elapsed_time(e); a[1] += 1; a[2] += flops
+        prof = agg
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = measured_peaks()
+    ms_step = total_ms / args.steps
+    value = world * B * args.steps / (total_ms / 1e3)
+    e2e_val = world * B * args.steps / (e2e_ms / 1e3)
+    # dominant kernel class by device time
+    tot_prof = sum(v[0] for v in prof.values())
+    dom = max(prof.items(), key=lambda kv: kv[1][0])
+    dname, (dms, dcount, dflops) = dom
+    ach = dflops / dcount / (dms / dcount * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": dname, "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                "frac": ach / peaks["tf_sustained"], "peak_source": peaks["src"] + " sustained (kernel timed inside a long step)",
+                "traffic": None, "share_of_step": dms / tot_prof, "launches_per_step": dcount,
+                "avg_launch_ms": dms / dcount,
+                "model": {"achieved": GFLOP_PER_IMG * value / world / 1e3, "unit": "TFLOP/s",
+                          "frac": GFLOP_PER_IMG * value / world / 1e3 / peaks["tf_sustained"]},
+                "by_kernel_ms": {k: round(v[0], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}}
+    line = {
+        "metric": "images/sec Uformer-B 256x256 fwd", "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "Uformer-B 256x256 inference fwd, batch 32 per GPU (BASELINE configs[1])", "global_batch": B * world,
+                   "per_gpu_batch": B, "parallelism": f"replicas x{world} (no collective)", "l2": "256MB flush between timed steps",
+                   "weights": "synthetic seeded init of the Uformer-B architecture"},
+        "e2e": {"value": e2e_val, "unit": "img/s", "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": y_host.numel() * 4,
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roofline}
+    if not args.no_cpu_baseline and world == 1:
+        note("cpu baseline (oracle port on host cores)")
+        v, threads, dt = cpu_oracle_rate(4, iters=2)
+        line["cpu_baseline"] = {"value": v, "unit": "img/s", "cores": threads, "kind": "port",
+                                "sample": f"4 images x 2 iterations of the same forward (fp32 oracle port, {dt:.2f}s per iteration, "
+                                          f"best of 16/32/64 threads on {os.cpu_count()} cpus)"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -48,3 +48,17 @@ def test_window_roundtrip():
     assert torch.equal(O.window_reverse(w, 8, 16, 24), x)
     # window order: batch-major, then row-major over (wy, wx)
     assert torch.equal(w[4], x[0, 8:16, 8:16])
+
+
+def test_fast_mode_equals_explicit():
+    """oracle.FAST (library-op formulation used for the timed CPU baseline) == explicit restatement."""
+    from oracle import lewin_oracle as O
+    g = load_golden("uformer_t2_128")
+    _, st = build_module(g)
+    y0 = oracle_run(g, st, g["x"])
+    O.FAST = True
+    try:
+        y1 = oracle_run(g, st, g["x"])
+    finally:
+        O.FAST = False
+    assert rel_l2(y1, y0) < 1e-5

@@ -14,6 +14,24 @@ from . import _lib
 
 Tensor = torch.Tensor
 
+# bench.py instrumentation: number of native kernel launches, and (when PROFILE is a list) one
+# (label, algorithmic flops, start event, end event) record per launch on the launching stream.
+LAUNCH_COUNT = 0
+PROFILE = None
+
+
+def _launch(label: str, flops: float, fn, rc_name: str):
+    global LAUNCH_COUNT
+    LAUNCH_COUNT += 1
+    if PROFILE is None:
+        _lib.check(fn(), rc_name)
+        return
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    _lib.check(fn(), rc_name)
+    e.record()
+    PROFILE.append((label, flops, s, e))
+
 
 def _ptr(t):
     return None if t is None else t.data_ptr()
@@ -53,7 +71,8 @@ def wmsa(x: Tensor, p: dict, *, H: int, W: int, shift: int, windowed: bool, resi
         a.mask, a.n_mask_windows = _ptr(mask), mask.shape[0]
     a.n_windows, a.H, a.W, a.C, a.head_dim = n_windows, H, W, Cc, p["head_dim"]
     a.shift, a.windowed, a.ln_eps = shift, int(windowed), p.get("ln_eps", 1e-5)
-    _lib.check(_lib.load().lw_wmsa_fwd(C.byref(a), _stream()), "lw_wmsa_fwd")
+    ntok = n_windows * 64
+    _launch(f"wmsa_C{Cc}", 2.0 * ntok * (4 * Cc * Cc + 128 * Cc), lambda: _lib.load().lw_wmsa_fwd(C.byref(a), _stream()), "lw_wmsa_fwd")
     return out
 
 
@@ -69,14 +88,14 @@ def leff(x: Tensor, p: dict, *, B: int, H: int, W: int, resid: Tensor | None, ou
     a.w1_img, a.b1 = _ptr(p["w1_img"]), _ptr(p["b1"])
     a.n_tokens, a.C, a.hidden, a.ln_eps = n_tokens, Cc, hidden, p.get("ln_eps", 1e-5)
     lib = _lib.load()
-    _lib.check(lib.lw_leff1_fwd(C.byref(a), _stream()), "lw_leff1_fwd")
+    _launch(f"leff1_C{Cc}", 2.0 * n_tokens * Cc * hidden, lambda: lib.lw_leff1_fwd(C.byref(a), _stream()), "lw_leff1_fwd")
     if out is None:
         out = torch.empty_like(x)
     b = _lib.Leff2Args()
     b.h1, b.out, b.resid = _ptr(h1), _ptr(out), _ptr(resid)
     b.wd, b.bd, b.w2_img, b.b2 = _ptr(p["wd"]), _ptr(p["bd"]), _ptr(p["w2_img"]), _ptr(p["b2"])
     b.B, b.H, b.W, b.C, b.hidden = B, H, W, Cc, hidden
-    _lib.check(lib.lw_leff2_fwd(C.byref(b), _stream()), "lw_leff2_fwd")
+    _launch(f"leff2_C{Cc}", 2.0 * n_tokens * (hidden * Cc + 9 * hidden), lambda: lib.lw_leff2_fwd(C.byref(b), _stream()), "lw_leff2_fwd")
     return out
 
 
@@ -87,7 +106,8 @@ def downsample(x: Tensor, p: dict, *, B: int, H: int, W: int) -> Tensor:
     a = _lib.DownArgs()
     a.x, a.out, a.w_img, a.bias = _ptr(x), _ptr(out), _ptr(p["w_img"]), _ptr(p["bias"])
     a.B, a.H, a.W, a.Cin, a.Cout = B, H, W, Cin, Cout
-    _lib.check(_lib.load().lw_downsample_fwd(C.byref(a), _stream()), "lw_downsample_fwd")
+    _launch(f"down_C{Cin}", 2.0 * B * (H // 2) * (W // 2) * 16 * Cin * Cout, lambda: _lib.load().lw_downsample_fwd(C.byref(a), _stream()),
+            "lw_downsample_fwd")
     return out
 
 
@@ -100,7 +120,7 @@ def upsample(x: Tensor, p: dict, *, B: int, H: int, W: int, out: Tensor | None =
     a = _lib.UpArgs()
     a.x, a.out, a.w_img, a.bias = _ptr(x), _ptr(out), _ptr(p["w_img"]), _ptr(p["bias"])
     a.B, a.H, a.W, a.Cin, a.Cout, a.out_stride = B, H, W, Cin, Cout, out.shape[-1]
-    _lib.check(_lib.load().lw_upsample_fwd(C.byref(a), _stream()), "lw_upsample_fwd")
+    _launch(f"up_C{Cin}", 2.0 * B * H * W * Cin * 4 * Cout, lambda: _lib.load().lw_upsample_fwd(C.byref(a), _stream()), "lw_upsample_fwd")
     return out
 
 
@@ -111,8 +131,8 @@ def input_proj(img: Tensor, w: Tensor, b: Tensor) -> Tensor:
     B, Cin, H, W = img.shape
     E = w.shape[0]
     tok = torch.empty((B, H * W, E), dtype=torch.bfloat16, device=img.device)
-    _lib.check(_lib.load().lw_input_proj_fwd(_ptr(img), _ptr(w), _ptr(b), _ptr(tok), B, Cin, H, W, E, _stream()),
-               "lw_input_proj_fwd")
+    _launch("input_proj", 2.0 * B * H * W * 9 * Cin * E,
+            lambda: _lib.load().lw_input_proj_fwd(_ptr(img), _ptr(w), _ptr(b), _ptr(tok), B, Cin, H, W, E, _stream()), "lw_input_proj_fwd")
     return tok
 
 
@@ -124,6 +144,7 @@ def output_proj(tok: Tensor, w: Tensor, b: Tensor, img: Tensor | None, H: int, W
     out = torch.empty((B, Cout, H, W), dtype=torch.float32, device=tok.device)
     if img is not None:
         img = img.float().contiguous()
-    _lib.check(_lib.load().lw_output_proj_fwd(_ptr(tok), _ptr(w), _ptr(b), _ptr(img), _ptr(out), B, Cin, H, W, Cout, _stream()),
-               "lw_output_proj_fwd")
+    _launch("output_proj", 2.0 * B * H * W * 9 * Cin * Cout,
+            lambda: _lib.load().lw_output_proj_fwd(_ptr(tok), _ptr(w), _ptr(b), _ptr(img), _ptr(out), B, Cin, H, W, Cout, _stream()),
+            "lw_output_proj_fwd")
     return out
