@@ -50,7 +50,7 @@ struct AResCfg {
 static_assert(sizeof(GemmMisc) <= 1024, "misc too large");
 
 template <int K, int EPI>
-__global__ void __launch_bounds__(kThreads, 1) ares_kernel(const AResArgs a) {
+__global__ void __launch_bounds__(kThreads8, (K <= 128) ? 2 : 1) ares_kernel(const AResArgs a) {
   using Cfg = AResCfg<K>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -61,11 +61,11 @@ __global__ void __launch_bounds__(kThreads, 1) ares_kernel(const AResArgs a) {
 
   if (tid == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(smem_u32(&ms.bar_full[s]), 1); mbar_init(smem_u32(&ms.bar_empty[s]), 1); }
-    mbar_init(smem_u32(&ms.bar_a_ready), kWorkers);
-    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&ms.bar_d_full[i]), 1); mbar_init(smem_u32(&ms.bar_d_empty[i]), kWorkers); }
+    mbar_init(smem_u32(&ms.bar_a_ready), kWorkers8);
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&ms.bar_d_full[i]), 1); mbar_init(smem_u32(&ms.bar_d_empty[i]), kWorkers8); }
     fence_mbar_init();
   }
-  if (warp == 4) tmem_alloc(smem_u32(&ms.tmem_base), Cfg::T_ALLOC);
+  if (warp == 8) tmem_alloc(smem_u32(&ms.tmem_base), Cfg::T_ALLOC);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -73,14 +73,14 @@ __global__ void __launch_bounds__(kThreads, 1) ares_kernel(const AResArgs a) {
   const uint32_t sX = smem_u32(smem + Cfg::S_X);
   const uint32_t chunk_bytes = a.nch * 128;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       Ring ring{smem_u32(smem + Cfg::S_RING), smem_u32(&ms.bar_full[0]), smem_u32(&ms.bar_empty[0]), Cfg::STAGES, 0};
       for (int nc = 0; nc < NC; ++nc)
         for (int kb = 0; kb < Cfg::KB; ++kb)
           ring.load(a.w_img + (size_t)(nc * Cfg::KB + kb) * chunk_bytes, chunk_bytes);
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     if (lane == 0) {
       Ring ring{smem_u32(smem + Cfg::S_RING), smem_u32(&ms.bar_full[0]), smem_u32(&ms.bar_empty[0]), Cfg::STAGES, 0};
       const uint32_t idesc = make_idesc_bf16(128, a.nch);
@@ -103,40 +103,59 @@ __global__ void __launch_bounds__(kThreads, 1) ares_kernel(const AResArgs a) {
       }
     }
   } else {
-    const int r = tid;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    const int row = tile * 128 + r;
-    ms.row_tok[r] = (row < a.n_rows) ? row : -1;
-    worker_bar();
-    stage_rows_ln<K>(smem + Cfg::S_X, a.x, ms.row_tok, a.ln_w, a.ln_b, a.ln_eps, nullptr);
+    // 8 worker warps: stage 16 rows each; epilogue: lane quadrant warp&3, column half warp>>2
+    if (tid < 128) {
+      const int row0 = tile * 128 + tid;
+      ms.row_tok[tid] = (row0 < a.n_rows) ? row0 : -1;
+    }
+    worker_bar8();
+    stage_rows_ln<K, 8>(smem + Cfg::S_X, a.x, ms.row_tok, a.ln_w, a.ln_b, a.ln_eps, nullptr);
     fence_async_smem();
     mbar_arrive(smem_u32(&ms.bar_a_ready));
+    const int r = (warp & 3) * 32 + lane;
+    const int half = warp >> 2;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const int row = tile * 128 + r;
     const bool valid = row < a.n_rows;
-    // upsample geometry of this input token
-    int ub = 0, uy = 0, ux = 0;
+    int ub = 0, uy = 0, ux = 0;      // upsample geometry of this input token
     if (EPI == 1 && valid) { ub = row / (a.H * a.W); int t = row % (a.H * a.W); uy = t / a.W; ux = t % a.W; }
     for (int nc = 0; nc < NC; ++nc) {
       const int buf = nc & 1;
       mbar_wait(smem_u32(&ms.bar_d_full[buf]), (nc >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < a.nch; c0 += 16) {
+      for (int c0 = half * 16; c0 < a.nch; c0 += 32) {
         uint32_t v[16];
         tmem_ld16(tb + lane_base + buf * 128 + c0, v);
         tmem_wait_ld();
         if (valid) {
           const int n0 = nc * a.nch + c0;
-          float f[16];
+          uint4 o0, o1;
           if (EPI == 0) {
+            const float4* bp = reinterpret_cast<const float4*>(a.bias + n0);
+            uint32_t pk[8];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = gelu_erf(__uint_as_float(v[j]) + __ldg(a.bias + n0 + j));
+            for (int j = 0; j < 4; ++j) {
+              const float4 b4 = __ldg(bp + j);
+              const f2 x0 = f2_add(f2_pack(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])), f2_pack(b4.x, b4.y));
+              const f2 x1 = f2_add(f2_pack(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), f2_pack(b4.z, b4.w));
+              pk[2 * j] = f2_to_bf2(gelu2(x0));
+              pk[2 * j + 1] = f2_to_bf2(gelu2(x1));
+            }
+            o0 = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            o1 = make_uint4(pk[4], pk[5], pk[6], pk[7]);
             uint4* op = reinterpret_cast<uint4*>(a.out + (size_t)row * a.n_total + n0);
-            op[0] = pack8(f);
-            op[1] = pack8(f + 8);
+            op[0] = o0;
+            op[1] = o1;
           } else {
             const int q = n0 / a.Cout, co = n0 % a.Cout;
+            float f[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + __ldg(a.bias + co + j);
+            for (int j = 0; j < 16; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + co + j));
+              f[j] = __uint_as_float(v[j]) + b4.x; f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+              f[j + 2] = __uint_as_float(v[j + 2]) + b4.z; f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+            }
             const size_t orow = ((size_t)ub * (2 * a.H) + (2 * uy + (q >> 1))) * (2 * a.W) + (2 * ux + (q & 1));
             uint4* op = reinterpret_cast<uint4*>(a.out + orow * a.out_stride + co);
             op[0] = pack8(f);
@@ -150,7 +169,7 @@ __global__ void __launch_bounds__(kThreads, 1) ares_kernel(const AResArgs a) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tb, Cfg::T_ALLOC);
+  if (warp == 8) tmem_dealloc(tb, Cfg::T_ALLOC);
 }
 
 // =================================================================================================

@@ -4,6 +4,7 @@
 #include <cstring>
 #include "wmsa.cuh"
 #include "leff.cuh"
+#include "leff2.cuh"
 #include "proj.cuh"
 
 using namespace lw;
@@ -42,7 +43,7 @@ static int launch_wmsa(const lw_wmsa_args* a, cudaStream_t st) {
   static_assert(Cfg::SMEM_BYTES <= 232448, "smem budget");
   LW_TRY(cudaFuncSetAttribute(wmsa_kernel<C, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   const int tiles = (a->n_windows + 1) / 2;
-  wmsa_kernel<C, HD><<<tiles, kThreads, Cfg::SMEM_BYTES, st>>>(*a);
+  wmsa_kernel<C, HD><<<tiles, kThreads8, Cfg::SMEM_BYTES, st>>>(*a);
   LW_TRY(cudaGetLastError());
   return LW_OK;
 }
@@ -75,7 +76,7 @@ static int launch_ares(const AResArgs& a, cudaStream_t st) {
   static_assert(Cfg::SMEM_BYTES <= 232448, "smem budget");
   LW_TRY(cudaFuncSetAttribute(ares_kernel<K, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
   const int tiles = (a.n_rows + 127) / 128;
-  ares_kernel<K, EPI><<<tiles, kThreads, Cfg::SMEM_BYTES, st>>>(a);
+  ares_kernel<K, EPI><<<tiles, kThreads8, Cfg::SMEM_BYTES, st>>>(a);
   LW_TRY(cudaGetLastError());
   return LW_OK;
 }
@@ -133,10 +134,15 @@ extern "C" int lw_leff2_fwd(const lw_leff2_args* p, lw_stream_t stream) {
   a.wd = p->wd; a.bd = p->bd; a.w_img = reinterpret_cast<const uint8_t*>(p->w2_img);
   a.N = p->C; a.nch = p->C < 128 ? p->C : 128; a.bias = p->b2;
   a.resid = reinterpret_cast<const bf16*>(p->resid); a.out = reinterpret_cast<bf16*>(p->out);
-  a.TW = p->W >= 16 ? 16 : 8; a.TH = 128 / a.TW;
-  a.tiles_x = (p->W + a.TW - 1) / a.TW;
-  const int tiles_y = (p->B * p->H + a.TH - 1) / a.TH;
-  return launch_astream<0>(a, a.tiles_x * tiles_y, reinterpret_cast<cudaStream_t>(stream));
+  if (p->H % 8) return LW_ERR_BAD_SHAPE;
+  a.TW = 16; a.TH = 8;
+  a.tiles_x = (p->W + 15) / 16;
+  const int tiles = a.tiles_x * (p->H / 8) * p->B;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  LW_TRY(cudaFuncSetAttribute(leff2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Leff2Cfg::SMEM_BYTES));
+  leff2_kernel<<<tiles, kL2Threads, Leff2Cfg::SMEM_BYTES, st>>>(a, pow2_cols(a.N));
+  LW_TRY(cudaGetLastError());
+  return LW_OK;
 }
 
 extern "C" int lw_downsample_fwd(const lw_down_args* p, lw_stream_t stream) {

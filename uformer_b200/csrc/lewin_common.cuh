@@ -12,12 +12,15 @@
 
 namespace lw {
 
-constexpr int kWorkers = 128;
+constexpr int kWorkers = 128;     // legacy 4-worker-warp skeleton (downsample)
 constexpr int kThreads = 192;
+constexpr int kWorkers8 = 256;    // 8 worker warps: warp w -> TMEM lane quadrant w & 3, column half w >> 2
+constexpr int kThreads8 = 320;    // + producer warp 8 + issuer warp 9
 constexpr int kStageBytes = 16384;
 constexpr float kLog2e = 1.4426950408889634f;
 
 __device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void worker_bar8() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes,
                                          uint32_t bar) {
@@ -61,6 +64,75 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
 }
 
+// ---- packed fp32 pairs (FFMA2 / FMUL2 on sm_100: two fp32 lanes per instruction) ----
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 f2_pack(float lo, float hi) {
+  f2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(f2 r, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(r));
+}
+__device__ __forceinline__ f2 f2_fma(f2 a, f2 b, f2 c) {
+  f2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f2 f2_add(f2 a, f2 b) {
+  f2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f2 f2_mul(f2 a, f2 b) {
+  f2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// two bf16 packed in a 32-bit word -> two fp32 (exact): lo = u << 16, hi = u & 0xffff0000
+__device__ __forceinline__ f2 bf2_to_f2(uint32_t u) {
+  return f2_pack(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// GELU(x) = x * Phi(x) with Phi(x) = 0.5 (1 + tanh(x (c0 + c1 x^2 + c2 x^4))): a least-squares fit of
+// the EXACT erf form (nn.GELU default, model.py:658), |error| <= 4.2e-5 for exact tanh (the common
+// "tanh approximation" with 0.044715 is 10x worse); MUFU.TANH adds <= 2^-11 relative on tanh.
+// The polynomial argument is clamped to |x| <= 8 where tanh has saturated (keeps it monotone).
+__device__ __forceinline__ f2 gelu2(f2 x) {
+  float a, b;
+  f2_unpack(x, a, b);
+  const f2 xc = f2_pack(fminf(fmaxf(a, -8.f), 8.f), fminf(fmaxf(b, -8.f), 8.f));
+  const f2 x2 = f2_mul(xc, xc);
+  f2 p = f2_fma(x2, f2_pack(-3.72804244e-4f, -3.72804244e-4f), f2_pack(3.71494616e-2f, 3.71494616e-2f));
+  p = f2_fma(x2, p, f2_pack(0.797344279f, 0.797344279f));
+  float qa, qb;
+  f2_unpack(f2_mul(xc, p), qa, qb);
+  const f2 t = f2_pack(tanh_approx(qa), tanh_approx(qb));
+  const f2 hx = f2_mul(x, f2_pack(0.5f, 0.5f));
+  return f2_fma(hx, t, hx);
+}
+__device__ __forceinline__ float gelu1(float x) {
+  const float xc = fminf(fmaxf(x, -8.f), 8.f);
+  const float x2 = xc * xc;
+  const float q = xc * fmaf(x2, fmaf(x2, -3.72804244e-4f, 3.71494616e-2f), 0.797344279f);
+  const float hx = 0.5f * x;
+  return fmaf(hx, tanh_approx(q), hx);
+}
+__device__ __forceinline__ uint32_t f2_to_bf2(f2 v) {
+  float a, b;
+  f2_unpack(v, a, b);
+  return pack_bf16(a, b);
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 __device__ __forceinline__ void unpack8(const uint4& v, float* f) {
   const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&v);
 #pragma unroll
@@ -87,7 +159,7 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 // tile row r (-1: row is padding -> zeros).  Executed by the 4 worker warps; warp w stages rows
 // [32w, 32w+32).  Lanes run along channels, so global reads are coalesced 16 B vectors.
 // ----------------------------------------------------------------------------------------------
-template <int C>
+template <int C, int NW = 4>
 __device__ __forceinline__ void stage_rows_ln(uint8_t* sX, const bf16* __restrict__ x,
                                               const int* row_tok, const float* __restrict__ ln_w,
                                               const float* __restrict__ ln_b, float eps,
@@ -97,8 +169,9 @@ __device__ __forceinline__ void stage_rows_ln(uint8_t* sX, const bf16* __restric
   constexpr int TPP = 32 / LPT;                   // tokens per pass
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sub = lane % LPT;
-  for (int t0 = 0; t0 < 32; t0 += TPP) {
-    const int r = warp * 32 + t0 + lane / LPT;
+  constexpr int RPW = 128 / NW;                   // rows per worker warp
+  for (int t0 = 0; t0 < RPW; t0 += TPP) {
+    const int r = warp * RPW + t0 + lane / LPT;
     const int tok = row_tok[r];
     float v[VPL][8];
 #pragma unroll

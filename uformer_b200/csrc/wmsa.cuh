@@ -29,7 +29,7 @@ struct WmsaCfg {
   static constexpr int NCH = C < 128 ? C : 128;            // proj N chunk
   static constexpr int NC = C / NCH;
   static constexpr int PROJ_CHUNK_BYTES = NCH * 128;
-  static constexpr int STAGES = (C >= 512) ? 3 : 4;
+  static constexpr int STAGES = (C >= 512) ? 3 : (C == 128 ? 2 : 4);   // C=128: 2 stages so two CTAs fit per SM
   // TMEM columns
   static constexpr int T_OALL = 0;                         // O for all heads, bf16 packed: C/2 cols
   static constexpr int T_WORK = (C / 2 < 32) ? 32 : C / 2; // S / D_qkv (aliased), 128 cols
@@ -44,7 +44,7 @@ struct WmsaCfg {
   static constexpr int S_V = S_K + TILE_B;
   static constexpr int S_RING = S_V + TILE_B;
   static constexpr int S_MISC = S_RING + STAGES * kStageBytes;
-  static constexpr int SMEM_BYTES = S_MISC + 2048 + 1024;  // + slack for 1024 B alignment
+  static constexpr int SMEM_BYTES = S_MISC + 4096 + 1024;  // + slack for 1024 B alignment
 };
 
 struct WmsaMisc {
@@ -52,15 +52,17 @@ struct WmsaMisc {
   int row_tok[128];
   uint8_t region[128];
   int win_mixed[2];
+  float xmax[2][128];      // softmax row max / sum halves exchanged between the two column-half threads
+  float xsum[2][128];
   uint64_t bar_full[4], bar_empty[4];
   uint64_t bar_xn, bar_qkv_full, bar_qkv_staged, bar_s_full, bar_p_ready, bar_o_full, bar_oall;
   uint64_t bar_d_full[2], bar_d_empty[2];
   uint32_t tmem_base;
 };
-static_assert(sizeof(WmsaMisc) <= 2048, "misc too large");
+static_assert(sizeof(WmsaMisc) <= 4096, "misc too large");
 
 template <int C, int HD>
-__global__ void __launch_bounds__(kThreads, 1) wmsa_kernel(const lw_wmsa_args a) {
+__global__ void __launch_bounds__(kThreads8, (C <= 128) ? 2 : 1) wmsa_kernel(const lw_wmsa_args a) {
   using Cfg = WmsaCfg<C, HD>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -72,17 +74,17 @@ __global__ void __launch_bounds__(kThreads, 1) wmsa_kernel(const lw_wmsa_args a)
   // ---------------- setup ----------------
   if (tid == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(smem_u32(&ms.bar_full[s]), 1); mbar_init(smem_u32(&ms.bar_empty[s]), 1); }
-    mbar_init(smem_u32(&ms.bar_xn), kWorkers);
+    mbar_init(smem_u32(&ms.bar_xn), kWorkers8);
     mbar_init(smem_u32(&ms.bar_qkv_full), 1);
-    mbar_init(smem_u32(&ms.bar_qkv_staged), kWorkers);
+    mbar_init(smem_u32(&ms.bar_qkv_staged), kWorkers8);
     mbar_init(smem_u32(&ms.bar_s_full), 1);
-    mbar_init(smem_u32(&ms.bar_p_ready), kWorkers);
+    mbar_init(smem_u32(&ms.bar_p_ready), kWorkers8);
     mbar_init(smem_u32(&ms.bar_o_full), 1);
-    mbar_init(smem_u32(&ms.bar_oall), kWorkers);
-    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&ms.bar_d_full[i]), 1); mbar_init(smem_u32(&ms.bar_d_empty[i]), kWorkers); }
+    mbar_init(smem_u32(&ms.bar_oall), kWorkers8);
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&ms.bar_d_full[i]), 1); mbar_init(smem_u32(&ms.bar_d_empty[i]), kWorkers8); }
     fence_mbar_init();
   }
-  if (warp == 4) tmem_alloc(smem_u32(&ms.tmem_base), Cfg::T_ALLOC);
+  if (warp == 8) tmem_alloc(smem_u32(&ms.tmem_base), Cfg::T_ALLOC);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -91,7 +93,7 @@ __global__ void __launch_bounds__(kThreads, 1) wmsa_kernel(const lw_wmsa_args a)
   const uint32_t sX = smem_u32(smem + Cfg::S_X), sQ = smem_u32(smem + Cfg::S_Q), sK = smem_u32(smem + Cfg::S_K),
                  sV = smem_u32(smem + Cfg::S_V);
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ======================= producer: weight chunk images =======================
     if (lane == 0) {
       Ring ring{smem_u32(smem + Cfg::S_RING), smem_u32(&ms.bar_full[0]), smem_u32(&ms.bar_empty[0]), Cfg::STAGES, 0};
@@ -104,7 +106,7 @@ __global__ void __launch_bounds__(kThreads, 1) wmsa_kernel(const lw_wmsa_args a)
         for (int kb = 0; kb < Cfg::KB; ++kb)
           ring.load(wp + (size_t)(nc * Cfg::KB + kb) * Cfg::PROJ_CHUNK_BYTES, Cfg::PROJ_CHUNK_BYTES);
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ======================= issuer: all tcgen05.mma =======================
     if (lane == 0) {
       Ring ring{smem_u32(smem + Cfg::S_RING), smem_u32(&ms.bar_full[0]), smem_u32(&ms.bar_empty[0]), Cfg::STAGES, 0};
@@ -171,12 +173,14 @@ __global__ void __launch_bounds__(kThreads, 1) wmsa_kernel(const lw_wmsa_args a)
       }
     }
   } else {
-    // ======================= workers =======================
-    const int r = tid;                   // tile row == TMEM lane
+    // ======================= workers (8 warps) =======================
+    // thread -> tile row r = (warp&3)*32 + lane (== TMEM lane), column half hf = warp>>2
+    const int r = (warp & 3) * 32 + lane;
+    const int hf = warp >> 2;
     const int wl = r >> 6, i = r & 63;   // window within the tile, token within the window
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    // ---- source token of every row + region id for the shift mask ----
-    {
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    // ---- source token of every row + region id for the shift mask (one thread per row) ----
+    if (hf == 0) {
       const int w = tile * 2 + wl;
       int tok = -1;
       uint8_t reg = 0;
@@ -202,124 +206,128 @@ __global__ void __launch_bounds__(kThreads, 1) wmsa_kernel(const lw_wmsa_args a)
       ms.region[r] = reg;
       if (i == 0) ms.win_mixed[wl] = 0;
     }
-    worker_bar();
-    if (a.shift > 0 && !a.windowed && ms.region[r] != ms.region[wl * 64]) ms.win_mixed[wl] = 1;
+    worker_bar8();
+    if (hf == 0 && a.shift > 0 && !a.windowed && ms.region[r] != ms.region[wl * 64]) ms.win_mixed[wl] = 1;
     // ---- A operand: LN(x) + modulator ----
-    stage_rows_ln<C>(smem + Cfg::S_X, xin, ms.row_tok, a.ln_w, a.ln_b, a.ln_eps, a.modulator);
+    stage_rows_ln<C, 8>(smem + Cfg::S_X, xin, ms.row_tok, a.ln_w, a.ln_b, a.ln_eps, a.modulator);
     fence_async_smem();
     mbar_arrive(smem_u32(&ms.bar_xn));
 
     const int tok = ms.row_tok[r];
     const int yi = i >> 3, xi = i & 7;
     const int rp_base = (yi + 7) * 15 + xi + 7;
+    const uint32_t relpos_s = smem_u32(&ms.relpos[0]);
+    const uint32_t region_s = smem_u32(&ms.region[0]);
+    (void)region_s;
 
     for (int h = 0; h < Cfg::NH; ++h) {
       const uint32_t ph = h & 1;
-      // relative-position bias row of this head -> smem (previous head's readers are past softmax)
-      for (int t = tid; t < 225; t += kWorkers) ms.relpos[t] = __ldg(a.relpos + h * 225 + t);
-      // ---- QKV epilogue: + bias, -> bf16 tiles Q,K (K-major) and V (row-major = MN-major B) ----
+      // relative-position bias row of this head -> smem (readers of the previous head are past their softmax barrier)
+      if (tid < 225) ms.relpos[tid] = __ldg(a.relpos + h * 225 + tid);
+      // ---- QKV epilogue: + bias -> bf16 tiles Q,K (K-major) and V (row-major = MN-major B); 16-col groups alternate halves ----
       mbar_wait(smem_u32(&ms.bar_qkv_full), ph);
       tc_fence_after();
       {
         const float* bq = a.bqkv + h * Cfg::QKV_N;
+        constexpr int NG = Cfg::QKV_N / 16;
 #pragma unroll
-        for (int part = 0; part < 3; ++part) {
-          uint8_t* tile_ptr = smem + (part == 0 ? Cfg::S_Q : part == 1 ? Cfg::S_K : Cfg::S_V);
+        for (int g = 0; g < NG; ++g) {
+          if ((g & 1) != hf) continue;
+          const int col = g * 16;                      // column inside D_qkv
+          const int part = col / HD, c0 = col % HD;    // 0:q 1:k 2:v, channel inside the head
+          const uint32_t tile_s = (part == 0 ? sQ : part == 1 ? sK : sV);
+          uint32_t v[16];
+          tmem_ld16(tb + lane_base + Cfg::T_WORK + col, v);
+          tmem_wait_ld();
+          float f[16];
 #pragma unroll
-          for (int c0 = 0; c0 < HD; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(tb + lane_base + Cfg::T_WORK + part * HD + c0, v);
-            tmem_wait_ld();
-            float f[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + __ldg(bq + part * HD + c0 + j);
-            *reinterpret_cast<uint4*>(tile_ptr + swz<Cfg::SWH>(r, c0 * 2)) = pack8(f);
-            *reinterpret_cast<uint4*>(tile_ptr + swz<Cfg::SWH>(r, c0 * 2 + 16)) = pack8(f + 8);
+          for (int j = 0; j < 16; j += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bq + col + j));
+            f[j] = __uint_as_float(v[j]) + b4.x; f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
+            f[j + 2] = __uint_as_float(v[j + 2]) + b4.z; f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
           }
+          sts128(tile_s + swz<Cfg::SWH>(r, c0 * 2), pack8(f));
+          sts128(tile_s + swz<Cfg::SWH>(r, c0 * 2 + 16), pack8(f + 8));
         }
       }
       fence_async_smem();
       tc_fence_before();
       mbar_arrive(smem_u32(&ms.bar_qkv_staged));
 
-      // ---- softmax over this row's 64 keys ----
+      // ---- softmax: this thread owns keys [hf*32, hf*32+32) of its row ----
       mbar_wait(smem_u32(&ms.bar_s_full), ph);
       tc_fence_after();
-      float s[64];
+      float s[32];
       {
         uint32_t v[32];
-        tmem_ld32(tb + lane_base + Cfg::T_WORK + wl * 64, v);
+        tmem_ld32(tb + lane_base + Cfg::T_WORK + wl * 64 + hf * 32, v);
         tmem_wait_ld();
 #pragma unroll
         for (int j = 0; j < 32; ++j) s[j] = __uint_as_float(v[j]);
-        tmem_ld32(tb + lane_base + Cfg::T_WORK + wl * 64 + 32, v);
-        tmem_wait_ld();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) s[32 + j] = __uint_as_float(v[j]);
       }
 #pragma unroll
-      for (int j = 0; j < 64; ++j) s[j] += ms.relpos[rp_base - (j >> 3) * 15 - (j & 7)];
+      for (int j = 0; j < 32; ++j) {
+        const int key = hf * 32 + j;                   // hf is warp-uniform
+        s[j] += lds32f(relpos_s + (rp_base - (key >> 3) * 15 - (key & 7)) * 4);
+      }
       if (ms.win_mixed[wl]) {
         const uint8_t myreg = ms.region[r];
 #pragma unroll
-        for (int j = 0; j < 64; ++j) s[j] += (ms.region[wl * 64 + j] != myreg) ? -100.0f : 0.0f;
+        for (int j = 0; j < 32; ++j) s[j] += (ms.region[wl * 64 + hf * 32 + j] != myreg) ? -100.0f : 0.0f;
       }
       if (a.mask != nullptr && tok >= 0) {
         const int w = tile * 2 + wl;
-        const float* mrow = a.mask + ((size_t)(w % a.n_mask_windows) * 64 + i) * 64;
+        const float* mrow = a.mask + ((size_t)(w % a.n_mask_windows) * 64 + i) * 64 + hf * 32;
 #pragma unroll
-        for (int j = 0; j < 64; j += 4) {
+        for (int j = 0; j < 32; j += 4) {
           float4 m4 = __ldg(reinterpret_cast<const float4*>(mrow + j));
           s[j] += m4.x; s[j + 1] += m4.y; s[j + 2] += m4.z; s[j + 3] += m4.w;
         }
       }
       float mx = s[0];
 #pragma unroll
-      for (int j = 1; j < 64; ++j) mx = fmaxf(mx, s[j]);
+      for (int j = 1; j < 32; ++j) mx = fmaxf(mx, s[j]);
+      ms.xmax[hf][r] = mx;
+      worker_bar8();
+      mx = fmaxf(mx, ms.xmax[hf ^ 1][r]);
       float sum = 0.f;
       const float mxs = mx * kLog2e;
 #pragma unroll
-      for (int j = 0; j < 64; ++j) {
-        s[j] = exp2f(s[j] * kLog2e - mxs);
+      for (int j = 0; j < 32; ++j) {
+        s[j] = exp2f(fmaf(s[j], kLog2e, -mxs));
         sum += s[j];
       }
-      // P (unnormalised, bf16) over the S columns: this row's keys at packed cols [wl*32, +32), zeros elsewhere
+      ms.xsum[hf][r] = sum;
+      // P (unnormalised, bf16) over the S columns: this row's keys at packed cols [wl*32 + hf*16, +16), zeros in the other window's cols
       {
         uint32_t pk[16];
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(s[half * 32 + 2 * j], s[half * 32 + 2 * j + 1]);
-          tmem_st16(tb + lane_base + Cfg::T_WORK + wl * 32 + half * 16, pk);
-        }
+        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(s[2 * j], s[2 * j + 1]);
+        tmem_st16(tb + lane_base + Cfg::T_WORK + wl * 32 + hf * 16, pk);
 #pragma unroll
         for (int j = 0; j < 16; ++j) pk[j] = 0u;
-        tmem_st16(tb + lane_base + Cfg::T_WORK + (1 - wl) * 32, pk);
-        tmem_st16(tb + lane_base + Cfg::T_WORK + (1 - wl) * 32 + 16, pk);
+        tmem_st16(tb + lane_base + Cfg::T_WORK + (1 - wl) * 32 + hf * 16, pk);
         tmem_wait_st();
       }
       tc_fence_before();
       mbar_arrive(smem_u32(&ms.bar_p_ready));
 
-      // ---- O epilogue: normalise, park as bf16 A operand of the projection ----
+      // ---- O epilogue: normalise, park as bf16 A operand of the projection (16-col groups alternate halves) ----
       mbar_wait(smem_u32(&ms.bar_o_full), ph);
       tc_fence_after();
-      {
-        const float inv = 1.0f / sum;
+      if (hf * 16 < HD) {
+        const float inv = 1.0f / (ms.xsum[0][r] + ms.xsum[1][r]);
+        const int c0 = hf * 16;
+        uint32_t v[16];
+        tmem_ld16(tb + lane_base + Cfg::T_DO + c0, v);
+        tmem_wait_ld();
+        uint32_t pk[8];
 #pragma unroll
-        for (int c0 = 0; c0 < HD; c0 += 16) {
-          uint32_t v[16];
-          tmem_ld16(tb + lane_base + Cfg::T_DO + c0, v);
-          tmem_wait_ld();
-          uint32_t pk[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) pk[j] = pack_bf16(__uint_as_float(v[2 * j]) * inv, __uint_as_float(v[2 * j + 1]) * inv);
-          tmem_st8(tb + lane_base + Cfg::T_OALL + (h * HD + c0) / 2, pk);
-        }
+        for (int j = 0; j < 8; ++j) pk[j] = pack_bf16(__uint_as_float(v[2 * j]) * inv, __uint_as_float(v[2 * j + 1]) * inv);
+        tmem_st8(tb + lane_base + Cfg::T_OALL + (h * HD + c0) / 2, pk);
         tmem_wait_st();
       }
       tc_fence_before();
-      worker_bar();   // relpos table may be overwritten by the next head only after everyone's softmax
     }
     mbar_arrive(smem_u32(&ms.bar_oall));
 
@@ -331,7 +339,7 @@ __global__ void __launch_bounds__(kThreads, 1) wmsa_kernel(const lw_wmsa_args a)
       mbar_wait(smem_u32(&ms.bar_d_full[buf]), (nc >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < Cfg::NCH; c0 += 16) {
+      for (int c0 = hf * 16; c0 < Cfg::NCH; c0 += 32) {
         uint32_t v[16];
         tmem_ld16(tb + lane_base + Cfg::T_WORK + buf * 128 + c0, v);
         tmem_wait_ld();
@@ -366,7 +374,7 @@ __global__ void __launch_bounds__(kThreads, 1) wmsa_kernel(const lw_wmsa_args a)
   // ---------------- teardown ----------------
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tb, Cfg::T_ALLOC);
+  if (warp == 8) tmem_dealloc(tb, Cfg::T_ALLOC);
 }
 
 }  // namespace lw
