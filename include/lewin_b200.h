@@ -37,6 +37,10 @@ const char* lw_last_cuda_error(void);
 /* 0 if the current device is a B200-class (sm_100) part, LW_ERR_ARCH otherwise. */
 int lw_check_device(void);
 
+/* Rows per weight-image chunk the A-resident GEMM kernels (lw_leff1_fwd, lw_upsample_fwd) expect for
+ * reduction depth K and output width n_total: the host packer must cut w1_img / w_img with this value. */
+int lw_nch_ares(int K, int n_total);
+
 /* ---- fused W-MSA: replaces LeWinTransformerBlock.forward's attention half (model.py:951-986)
  * and, with ln_w=NULL / resid=NULL / windowed=1, WindowAttention.forward (model.py:494-522).
  *   out = resid + reverse( proj( softmax( q k^T * hd^-1/2 + relpos_bias + mask ) v ) )

@@ -48,7 +48,7 @@ class UpArgs(C.Structure):
 
 
 # every symbol include/lewin_b200.h declares
-EXPORTS = ["lw_abi_version", "lw_last_cuda_error", "lw_check_device", "lw_wmsa_fwd", "lw_leff1_fwd", "lw_leff2_fwd",
+EXPORTS = ["lw_abi_version", "lw_last_cuda_error", "lw_check_device", "lw_nch_ares", "lw_wmsa_fwd", "lw_leff1_fwd", "lw_leff2_fwd",
            "lw_downsample_fwd", "lw_upsample_fwd", "lw_input_proj_fwd", "lw_output_proj_fwd"]
 
 _lib = None
@@ -65,6 +65,8 @@ def load():
     lib.lw_abi_version.restype = C.c_int
     lib.lw_last_cuda_error.restype = C.c_char_p
     lib.lw_check_device.restype = C.c_int
+    lib.lw_nch_ares.restype = C.c_int
+    lib.lw_nch_ares.argtypes = [C.c_int, C.c_int]
     for name, argt in [("lw_wmsa_fwd", WmsaArgs), ("lw_leff1_fwd", Leff1Args), ("lw_leff2_fwd", Leff2Args),
                        ("lw_downsample_fwd", DownArgs), ("lw_upsample_fwd", UpArgs)]:
         fn = getattr(lib, name)

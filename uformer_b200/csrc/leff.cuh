@@ -35,19 +35,58 @@ struct AResArgs {
   bf16* out;
   // EPI 0: out row stride = n_total.  EPI 1: upsample geometry
   int H, W, Cout, out_stride;
+  long long* trace;   // dbg&16: CTA 0 writes clock64 timestamps here (profiling aid)
+  int dbg;   // profiling knobs (env LW_DEBUG): 1 skip epilogue stores, 2 skip GELU, 4 skip weight loads, 8 skip A staging loads
 };
 
 template <int K>
 struct AResCfg {
   static constexpr int KB = (K + 63) / 64;
-  static constexpr int STAGES = 4;
+  // N chunk per accumulator buffer: 256-wide UMMAs halve the A re-reads from shared memory (an SS UMMA
+  // re-reads its whole 128 x 16 A slice every instruction); only K == 256 has the capacity for it.
+  static constexpr int NCH_MAX = (K == 256) ? 256 : 128;
+  static constexpr int STAGE_BYTES = NCH_MAX * 128;
+  static constexpr int STAGES = (K <= 128) ? 2 : 3;
   static constexpr int S_X = 0;
   static constexpr int S_RING = KB * 16384;
-  static constexpr int S_MISC = S_RING + STAGES * kStageBytes;
+  static constexpr int S_STAGE = S_RING + STAGES * STAGE_BYTES;      // epilogue staging tile: 128 rows x 272 B
+  static constexpr int STAGE_PITCH = 272;
+  static constexpr int S_BIAS = S_STAGE + 35840;                     // bias of the whole N range (<= 2048 fp32)
+  static constexpr int S_MISC = S_BIAS + 8192;
   static constexpr int SMEM_BYTES = S_MISC + 1024 + 1024;
-  static constexpr int T_ALLOC = 256;      // two 128-column accumulators
+  static constexpr int T_ALLOC = 2 * NCH_MAX;                        // two accumulator buffers
 };
 static_assert(sizeof(GemmMisc) <= 1024, "misc too large");
+
+// Phase A of the A-resident epilogue for one sub-chunk of 16*NB columns: warp (q, half) owns TMEM lanes q*32..+32
+// (two 16-lane fragments) and columns half*8NB .. +8NB.  tcol = TMEM address of the sub-chunk's first column,
+// ncol = its global N index.
+template <int NB, int EPI>
+__device__ __forceinline__ void ares_phase_a(const AResArgs& a, uint32_t tcol, int ncol, uint32_t bias_s, uint32_t stage_s, int pitch) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = warp & 3, half = warp >> 2, tq = lane & 3;
+  constexpr int CPH = 8 * NB;
+  uint32_t v[2][4 * NB];
+#pragma unroll
+  for (int hl = 0; hl < 2; ++hl) {
+    const uint32_t ta = tcol + half * CPH + ((uint32_t)(q * 32 + hl * 16) << 16);
+    if (NB == 8) tmem_ld_16x256b_x8(ta, v[hl]); else tmem_ld_16x256b_x4(ta, v[hl]);
+  }
+  f2 bb[NB];
+#pragma unroll
+  for (int i = 0; i < NB; ++i) {
+    const int n0 = ncol + half * CPH + 8 * i + 2 * tq;
+    const float2 b2 = lds64f(bias_s + ((EPI == 0) ? n0 : (n0 % a.Cout)) * 4);
+    bb[i] = f2_pack(b2.x, b2.y);
+  }
+  tmem_wait_ld();
+#pragma unroll
+  for (int hl = 0; hl < 2; ++hl) {
+    uint32_t pk[2 * NB];
+    frag_bias_act_pack<NB, EPI == 0>(v[hl], bb, pk);
+    stage_frag<NB>(stage_s, pitch, q * 32 + hl * 16, half * CPH, pk);
+  }
+}
 
 template <int K, int EPI>
 __global__ void __launch_bounds__(kThreads8, (K <= 128) ? 2 : 1) ares_kernel(const AResArgs a) {
@@ -75,97 +114,124 @@ __global__ void __launch_bounds__(kThreads8, (K <= 128) ? 2 : 1) ares_kernel(con
 
   if (warp == 8) {
     if (lane == 0) {
-      Ring ring{smem_u32(smem + Cfg::S_RING), smem_u32(&ms.bar_full[0]), smem_u32(&ms.bar_empty[0]), Cfg::STAGES, 0};
+      Ring ring{smem_u32(smem + Cfg::S_RING), smem_u32(&ms.bar_full[0]), smem_u32(&ms.bar_empty[0]), Cfg::STAGES, 0, Cfg::STAGE_BYTES};
       for (int nc = 0; nc < NC; ++nc)
         for (int kb = 0; kb < Cfg::KB; ++kb)
-          ring.load(a.w_img + (size_t)(nc * Cfg::KB + kb) * chunk_bytes, chunk_bytes);
+          if (a.dbg & 4) { mbar_wait(ring.empty(), ring.phase() ^ 1); mbar_arrive(ring.full()); ++ring.idx; }
+          else ring.load(a.w_img + (size_t)(nc * Cfg::KB + kb) * chunk_bytes, chunk_bytes);
     }
   } else if (warp == 9) {
     if (lane == 0) {
-      Ring ring{smem_u32(smem + Cfg::S_RING), smem_u32(&ms.bar_full[0]), smem_u32(&ms.bar_empty[0]), Cfg::STAGES, 0};
+      Ring ring{smem_u32(smem + Cfg::S_RING), smem_u32(&ms.bar_full[0]), smem_u32(&ms.bar_empty[0]), Cfg::STAGES, 0, Cfg::STAGE_BYTES};
       const uint32_t idesc = make_idesc_bf16(128, a.nch);
+      const uint32_t ring_base = smem_u32(smem + Cfg::S_RING);
+      const uint64_t a_desc0 = kmajor_desc<128>(sX), b_desc0 = kmajor_desc<128>(ring_base);   // address field += bytes >> 4
+      const bool tr = (a.dbg & 16) && blockIdx.x == 0 && a.trace != nullptr;
+      int ti = 0;
+      if (tr) a.trace[ti++] = clock64();
       mbar_wait(smem_u32(&ms.bar_a_ready), 0);
       tc_fence_after();
+      if (tr) a.trace[ti++] = clock64();
       for (int nc = 0; nc < NC; ++nc) {
         const int buf = nc & 1;
         mbar_wait(smem_u32(&ms.bar_d_empty[buf]), ((nc >> 1) & 1) ^ 1);
         tc_fence_after();
+        if (tr) a.trace[ti++] = clock64();
         for (int kb = 0; kb < Cfg::KB; ++kb) {
           const uint32_t wst = ring.acquire();
+          if (tr) a.trace[ti++] = clock64();
           constexpr int KS = (K >= 64) ? 4 : K / 16;
+          const uint64_t ad = a_desc0 + (uint64_t)(kb * 1024), bd = b_desc0 + (uint64_t)((wst - ring_base) >> 4);
 #pragma unroll
           for (int ks = 0; ks < KS; ++ks)
-            umma_ss(tb + buf * 128, kmajor_desc<128>(sX + kb * 16384 + ks * 32), kmajor_desc<128>(wst + ks * 32), idesc,
-                    (kb | ks) != 0);
+            umma_ss(tb + buf * Cfg::NCH_MAX, ad + 2 * ks, bd + 2 * ks, idesc, (kb | ks) != 0);
           ring.release();
+          if (tr) a.trace[ti++] = clock64();
         }
         umma_commit(smem_u32(&ms.bar_d_full[buf]));
       }
+      if (tr) a.trace[ti++] = -1;
     }
   } else {
-    // 8 worker warps: stage 16 rows each; epilogue: lane quadrant warp&3, column half warp>>2
+    // 8 worker warps: stage 16 A rows each; epilogue: lane quadrant warp&3, column half warp>>2
     if (tid < 128) {
       const int row0 = tile * 128 + tid;
       ms.row_tok[tid] = (row0 < a.n_rows) ? row0 : -1;
     }
+    const uint32_t bias_s = smem_u32(smem + Cfg::S_BIAS);
+    {
+      const int nb = (EPI == 0) ? a.n_total : a.Cout;      // bias entries
+      for (int i4 = tid * 4; i4 < nb; i4 += kWorkers8 * 4) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + i4));
+        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(bias_s + i4 * 4), "f"(b4.x), "f"(b4.y), "f"(b4.z), "f"(b4.w) : "memory");
+      }
+    }
     worker_bar8();
-    stage_rows_ln<K, 8>(smem + Cfg::S_X, a.x, ms.row_tok, a.ln_w, a.ln_b, a.ln_eps, nullptr);
+    if (!(a.dbg & 8)) stage_rows_ln<K, 8>(smem + Cfg::S_X, a.x, ms.row_tok, a.ln_w, a.ln_b, a.ln_eps, nullptr);
     fence_async_smem();
     mbar_arrive(smem_u32(&ms.bar_a_ready));
-    const int r = (warp & 3) * 32 + lane;
     const int half = warp >> 2;
-    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    const int row = tile * 128 + r;
-    const bool valid = row < a.n_rows;
-    int ub = 0, uy = 0, ux = 0;      // upsample geometry of this input token
-    if (EPI == 1 && valid) { ub = row / (a.H * a.W); int t = row % (a.H * a.W); uy = t / a.W; ux = t % a.W; }
+    const uint32_t stage_s = smem_u32(smem + Cfg::S_STAGE);
+    if (EPI == 1) {
+      // destination base row of every input token: (b, 2y, 2x) in the (B, 2H, 2W) output map
+      worker_bar8();
+      if (tid < 128) {
+        const int row0 = ms.row_tok[tid];
+        if (row0 >= 0) {
+          const int ub = row0 / (a.H * a.W), t = row0 % (a.H * a.W), uy = t / a.W, ux = t % a.W;
+          ms.row_tok[tid] = (ub * 2 * a.H + 2 * uy) * (2 * a.W) + 2 * ux;
+        }
+      }
+      worker_bar8();
+    }
+    const int sub_cols = a.nch < 128 ? a.nch : 128;          // staged 128 columns at a time
+    int sub_log2 = 4;
+    while ((1 << sub_log2) < sub_cols) ++sub_log2;
+    const bool trw = (a.dbg & 16) && blockIdx.x == 0 && tid == 0 && a.trace != nullptr;
+    int tw = 512, tw2 = 1024;
+    if (trw) a.trace[tw++] = clock64();
     for (int nc = 0; nc < NC; ++nc) {
       const int buf = nc & 1;
       mbar_wait(smem_u32(&ms.bar_d_full[buf]), (nc >> 1) & 1);
       tc_fence_after();
-#pragma unroll 1
-      for (int c0 = half * 16; c0 < a.nch; c0 += 32) {
-        uint32_t v[16];
-        tmem_ld16(tb + lane_base + buf * 128 + c0, v);
-        tmem_wait_ld();
-        if (valid) {
-          const int n0 = nc * a.nch + c0;
-          uint4 o0, o1;
+      if (trw) a.trace[tw++] = clock64();
+      for (int sc = 0; sc < a.nch; sc += 128) {
+        // ---- phase A: TMEM (16x256b fragments) -> (+bias, GELU) -> bf16 -> stmatrix into the staging tile.
+        // warp (q, half): lanes q*32..+32 as two 16-lane groups, columns half*cph .. +cph of the sub-chunk ----
+        if (sub_cols == 128) ares_phase_a<8, EPI>(a, tb + buf * Cfg::NCH_MAX + sc, nc * a.nch + sc, bias_s, stage_s, Cfg::STAGE_PITCH);
+        else ares_phase_a<4, EPI>(a, tb + buf * Cfg::NCH_MAX + sc, nc * a.nch + sc, bias_s, stage_s, Cfg::STAGE_PITCH);
+        if (trw && nc == 1) a.trace[tw2++] = clock64();
+        if (sc + 128 >= a.nch) {            // accumulator fully read: hand the buffer back to the issuer
+          tc_fence_before();
+          mbar_arrive(smem_u32(&ms.bar_d_empty[buf]));
+        }
+        worker_bar8();
+        if (trw && nc == 1) a.trace[tw2++] = clock64();
+        // ---- phase B: coalesced copy-out ----
+        if (!(a.dbg & 1)) {
           if (EPI == 0) {
-            const float4* bp = reinterpret_cast<const float4*>(a.bias + n0);
-            uint32_t pk[8];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float4 b4 = __ldg(bp + j);
-              const f2 x0 = f2_add(f2_pack(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])), f2_pack(b4.x, b4.y));
-              const f2 x1 = f2_add(f2_pack(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), f2_pack(b4.z, b4.w));
-              pk[2 * j] = f2_to_bf2(gelu2(x0));
-              pk[2 * j + 1] = f2_to_bf2(gelu2(x1));
-            }
-            o0 = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            o1 = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-            uint4* op = reinterpret_cast<uint4*>(a.out + (size_t)row * a.n_total + n0);
-            op[0] = o0;
-            op[1] = o1;
+            store_staged_rows(stage_s, Cfg::STAGE_PITCH, sub_log2, ms.row_tok, a.out, nullptr, (size_t)a.n_total,
+                              nc * a.nch + sc, tid, kWorkers8);
           } else {
-            const int q = n0 / a.Cout, co = n0 % a.Cout;
-            float f[16];
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + co + j));
-              f[j] = __uint_as_float(v[j]) + b4.x; f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
-              f[j + 2] = __uint_as_float(v[j + 2]) + b4.z; f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+            const int vshift = sub_log2 - 3;
+            const int total = 128 << vshift;
+            for (int i2 = tid; i2 < total; i2 += kWorkers8) {
+              const int row = i2 >> vshift, vec = i2 & ((1 << vshift) - 1);
+              const int obase = ms.row_tok[row];
+              if (obase < 0) continue;
+              const int n0 = nc * a.nch + sc + vec * 8;
+              const int q = n0 / a.Cout, co = n0 % a.Cout;
+              const size_t orow = (size_t)obase + (q >> 1) * (2 * a.W) + (q & 1);
+              *reinterpret_cast<uint4*>(a.out + orow * a.out_stride + co) = lds128(stage_s + row * Cfg::STAGE_PITCH + vec * 16);
             }
-            const size_t orow = ((size_t)ub * (2 * a.H) + (2 * uy + (q >> 1))) * (2 * a.W) + (2 * ux + (q & 1));
-            uint4* op = reinterpret_cast<uint4*>(a.out + orow * a.out_stride + co);
-            op[0] = pack8(f);
-            op[1] = pack8(f + 8);
           }
         }
+        if (trw && nc == 1) a.trace[tw2++] = clock64();
+        worker_bar8();                      // staging tile free for the next phase A
+        if (trw) a.trace[tw++] = clock64();
       }
-      tc_fence_before();
-      mbar_arrive(smem_u32(&ms.bar_d_empty[buf]));
     }
+    if (trw) { a.trace[tw++] = -1; a.trace[tw2++] = -1; }
   }
   tc_fence_before();
   __syncthreads();

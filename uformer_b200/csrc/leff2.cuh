@@ -33,6 +33,24 @@ static_assert(Leff2Cfg::S_RING % 1024 == 0, "ring alignment");
 
 __device__ __forceinline__ void l2_worker_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
+// accumulator columns [tcol, +8*NB) of 16 TMEM lanes -> + bias -> bf16 -> staging tile rows row16..+16, columns col0..
+template <int NB>
+__device__ __forceinline__ void epi_cols(uint32_t tcol, const float* __restrict__ bias, uint32_t stage_s, int pitch, int row16, int col0) {
+  const int tq = threadIdx.x & 3;
+  uint32_t v[4 * NB];
+  if (NB == 8) tmem_ld_16x256b_x8(tcol, v); else if (NB == 4) tmem_ld_16x256b_x4(tcol, v); else tmem_ld_16x256b_x2(tcol, v);
+  f2 bb[NB];
+#pragma unroll
+  for (int i = 0; i < NB; ++i) {
+    const float2 b2 = __ldg(reinterpret_cast<const float2*>(bias + 8 * i + 2 * tq));
+    bb[i] = f2_pack(b2.x, b2.y);
+  }
+  tmem_wait_ld();
+  uint32_t pk[2 * NB];
+  frag_bias_act_pack<NB, false>(v, bb, pk);
+  stage_frag<NB>(stage_s, pitch, row16, col0, pk);
+}
+
 __global__ void __launch_bounds__(kL2Threads, 1) leff2_kernel(const AStreamArgs a, const int t_alloc) {
   using Cfg = Leff2Cfg;
   extern __shared__ uint8_t smem_raw[];
@@ -190,41 +208,30 @@ __global__ void __launch_bounds__(kL2Threads, 1) leff2_kernel(const AStreamArgs 
       mbar_arrive(smem_u32(&ms.bar_a_full[ab]));
     }
 
-    // ---------------- epilogue: + bias (+ residual); warp w: lane quadrant w&3, column group w>>2 ----------------
+    // ---------------- epilogue: + bias -> bf16 -> staging tile (the halo buffers are free now) ->
+    // coalesced copy-out with the residual added on the way (warp w: lane quadrant w&3, column half w>>2)
     const int r = (warp & 3) * 32 + lane;
-    const int y = y0 + (r >> 4), x = x0 + (r & 15);
-    const bool valid = (x < a.W);
-    const size_t out_row = ((size_t)b * a.H + y) * a.W + x;
-    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    if (warp < 4) {
+      const int y = y0 + (r >> 4), x = x0 + (r & 15);
+      ms.row_tok[r] = (x < a.W) ? (int)(((size_t)b * a.H + y) * a.W + x) : -1;
+    }
+    const uint32_t stage_s = halo0;
+    const int sub_cols = a.N < 128 ? a.N : 128;
+    const int pitch = sub_cols * 2 + 16;
+    int sub_log2 = 4;
+    while ((1 << sub_log2) < sub_cols) ++sub_log2;
     mbar_wait(smem_u32(&ms.bar_d_full[0]), 0);
     tc_fence_after();
-#pragma unroll 1
-    for (int c0 = (warp >> 2) * 16; c0 < a.N; c0 += 32) {
-      uint32_t vv[16];
-      tmem_ld16(tb + lane_base + c0, vv);
-      tmem_wait_ld();
-      if (valid) {
-        float f[16];
-#pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + c0 + j));
-          f[j] = __uint_as_float(vv[j]) + b4.x; f[j + 1] = __uint_as_float(vv[j + 1]) + b4.y;
-          f[j + 2] = __uint_as_float(vv[j + 2]) + b4.z; f[j + 3] = __uint_as_float(vv[j + 3]) + b4.w;
-        }
-        if (a.resid != nullptr) {
-          const uint4* rp = reinterpret_cast<const uint4*>(a.resid + out_row * a.N + c0);
-          float g[8];
-          unpack8(__ldg(rp), g);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] += g[j];
-          unpack8(__ldg(rp + 1), g);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) f[8 + j] += g[j];
-        }
-        uint4* op = reinterpret_cast<uint4*>(a.out + out_row * a.N + c0);
-        op[0] = pack8(f);
-        op[1] = pack8(f + 8);
-      }
+    const int row16 = (warp & 3) * 32 + (warp >> 2) * 16;     // this warp's 16 TMEM lanes / tile rows
+    for (int sc = 0; sc < a.N; sc += 128) {
+      const uint32_t tcol = tb + ((uint32_t)row16 << 16) + sc;
+      if (sub_cols == 128) { epi_cols<8>(tcol, a.bias + sc, stage_s, pitch, row16, 0); epi_cols<8>(tcol + 64, a.bias + sc + 64, stage_s, pitch, row16, 64); }
+      else if (sub_cols == 64) epi_cols<8>(tcol, a.bias + sc, stage_s, pitch, row16, 0);
+      else if (sub_cols == 32) epi_cols<4>(tcol, a.bias + sc, stage_s, pitch, row16, 0);
+      else epi_cols<2>(tcol, a.bias + sc, stage_s, pitch, row16, 0);
+      l2_worker_bar();
+      store_staged_rows(stage_s, pitch, sub_log2, ms.row_tok, a.out, a.resid, (size_t)a.N, sc, tid, kL2Workers);
+      l2_worker_bar();
     }
   }
   tc_fence_before();

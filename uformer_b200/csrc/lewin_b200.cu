@@ -2,6 +2,7 @@
 // Validation first, then a template dispatch on the channel count; no allocation, no sync.
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include "wmsa.cuh"
 #include "leff.cuh"
 #include "leff2.cuh"
@@ -28,6 +29,17 @@ extern "C" int lw_check_device(void) {
   if (cudaGetDevice(&dev) != cudaSuccess) return LW_ERR_ARCH;
   if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return LW_ERR_ARCH;
   return major == 10 ? LW_OK : LW_ERR_ARCH;
+}
+
+static int debug_flags() {
+  const char* e = getenv("LW_DEBUG");   // profiling knobs, see leff.cuh (never set in production)
+  return e ? atoi(e) : 0;
+}
+
+// N-chunk (rows per weight image chunk) of the A-resident kernels; packing.py mirrors this rule.
+extern "C" int lw_nch_ares(int K, int n_total) {
+  const int cap = (K == 256) ? 256 : 128;
+  return n_total < cap ? n_total : cap;
 }
 
 static int pow2_cols(int n) {
@@ -100,8 +112,13 @@ extern "C" int lw_leff1_fwd(const lw_leff1_args* p, lw_stream_t stream) {
   AResArgs a{};
   a.x = reinterpret_cast<const bf16*>(p->x); a.n_rows = p->n_tokens; a.K = p->C;
   a.ln_w = p->ln_w; a.ln_b = p->ln_b; a.ln_eps = p->ln_eps;
-  a.w_img = reinterpret_cast<const uint8_t*>(p->w1_img); a.n_total = p->hidden; a.nch = p->hidden < 128 ? p->hidden : 128;
+  a.w_img = reinterpret_cast<const uint8_t*>(p->w1_img); a.n_total = p->hidden; a.nch = lw_nch_ares(p->C, p->hidden);
   a.bias = p->b1; a.out = reinterpret_cast<bf16*>(p->h1);
+  a.dbg = debug_flags();
+  if (a.dbg & 16) {   // profiling aid: env LW_TRACE_PTR carries a device buffer address (>= 8 KB) for CTA-0 timestamps
+    const char* e = getenv("LW_TRACE_PTR");
+    a.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr;
+  }
   return dispatch_ares<0>(a, reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -110,7 +127,7 @@ extern "C" int lw_upsample_fwd(const lw_up_args* p, lw_stream_t stream) {
   if (p->B <= 0 || p->H <= 0 || p->W <= 0 || p->Cout % 16 || p->out_stride < p->Cout || p->out_stride % 8) return LW_ERR_BAD_SHAPE;
   AResArgs a{};
   a.x = reinterpret_cast<const bf16*>(p->x); a.n_rows = p->B * p->H * p->W; a.K = p->Cin;
-  a.w_img = reinterpret_cast<const uint8_t*>(p->w_img); a.n_total = 4 * p->Cout; a.nch = a.n_total < 128 ? a.n_total : 128;
+  a.w_img = reinterpret_cast<const uint8_t*>(p->w_img); a.n_total = 4 * p->Cout; a.nch = lw_nch_ares(p->Cin, 4 * p->Cout);
   a.bias = p->bias; a.out = reinterpret_cast<bf16*>(p->out);
   a.H = p->H; a.W = p->W; a.Cout = p->Cout; a.out_stride = p->out_stride;
   return dispatch_ares<1>(a, reinterpret_cast<cudaStream_t>(stream));

@@ -37,7 +37,8 @@ struct Ring {
   uint32_t empty0;
   int stages;
   int idx;             // running chunk counter
-  __device__ __forceinline__ uint32_t stage_addr() const { return base + (idx % stages) * kStageBytes; }
+  int stage_bytes = kStageBytes;
+  __device__ __forceinline__ uint32_t stage_addr() const { return base + (idx % stages) * stage_bytes; }
   __device__ __forceinline__ uint32_t full() const { return full0 + 8 * (idx % stages); }
   __device__ __forceinline__ uint32_t empty() const { return empty0 + 8 * (idx % stages); }
   __device__ __forceinline__ uint32_t phase() const { return (idx / stages) & 1; }
@@ -152,6 +153,94 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// Epilogue staging.  Thread-per-row TMEM reads produce 32 B per thread per 16 columns; writing those
+// straight to global memory touches 32 different 128 B lines per warp instruction.  Instead every
+// epilogue first parks its bf16 results in a shared [128 rows][pitch] tile (pitch = 2*ncols + 16 B, so
+// the per-row 16 B writes of a warp spread over all banks), then all worker threads copy the tile out
+// with lanes running ALONG rows: fully coalesced 16 B stores, and fully coalesced residual loads.
+// ----------------------------------------------------------------------------------------------
+// Park a bf16-packed 16-row x (8*NB)-column accumulator fragment (pk[2i] = row t/4 of column block i,
+// pk[2i+1] = row t/4+8) in a row-major staging tile with stmatrix: NB/2 instructions, conflict-free.
+template <int NB>
+__device__ __forceinline__ void stage_frag(uint32_t stage_s, int pitch, int row16, int col0, const uint32_t* pk) {
+  const int lane = threadIdx.x & 31;
+  const int m = lane >> 3, rr = lane & 7;
+  const uint32_t base = stage_s + (row16 + (m & 1) * 8 + rr) * pitch + (col0 + (m >> 1) * 8) * 2;
+  if (NB == 1) {
+    stsm_x2(stage_s + (row16 + (m & 1) * 8 + rr) * pitch + col0 * 2, pk[0], pk[1]);
+  } else {
+#pragma unroll
+    for (int i2 = 0; i2 < NB / 2; ++i2) stsm_x4(base + i2 * 32, pk[4 * i2], pk[4 * i2 + 1], pk[4 * i2 + 2], pk[4 * i2 + 3]);
+  }
+}
+
+// Branch-free epilogue body for one 16-lane x (8*NB)-column fp32 fragment: + bias (per column pair, fp32 pairs
+// preloaded in bb[NB]) -> optional GELU -> bf16 pack.  Fully unrolled straight-line code so the scheduler can
+// interleave the NB*2 independent dependency chains.
+template <int NB, bool GELU>
+__device__ __forceinline__ void frag_bias_act_pack(const uint32_t* v, const f2* bb, uint32_t* pk) {
+#pragma unroll
+  for (int i = 0; i < NB; ++i) {
+    const f2 x0 = f2_add(f2_pack(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1])), bb[i]);
+    const f2 x1 = f2_add(f2_pack(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])), bb[i]);
+    pk[2 * i] = f2_to_bf2(GELU ? gelu2(x0) : x0);
+    pk[2 * i + 1] = f2_to_bf2(GELU ? gelu2(x1) : x1);
+  }
+}
+
+__device__ __forceinline__ uint4 add_bf16x8(const uint4& a, const uint4& b) {
+  float fa[8], fb[8];
+  unpack8(a, fa);
+  unpack8(b, fb);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) fa[i] += fb[i];
+  return pack8(fa);
+}
+// copy a staged tile to global rows with 256 threads.  row_tok (smem) gives the destination row of each tile
+// row (-1: skip).  All shared/global loads of a thread are issued before its first store (latency overlap).
+template <int VSHIFT>   // log2(16-byte vectors per row) = log2(ncols) - 3
+__device__ __forceinline__ void store_staged_rows_t(uint32_t stage_s, int pitch, uint32_t row_tok_s,
+                                                    bf16* __restrict__ out, const bf16* __restrict__ resid,
+                                                    size_t row_stride, int col0, int tid) {
+  constexpr int ITER = ((128 << VSHIFT) + 255) / 256;
+  uint4 v[ITER], rv[ITER];
+  size_t g[ITER];
+  int tok[ITER];
+#pragma unroll
+  for (int k = 0; k < ITER; ++k) {
+    const int i = tid + k * 256;
+    const int row = i >> VSHIFT, vec = i & ((1 << VSHIFT) - 1);
+    const bool in = (128 << VSHIFT) >= 256 || i < (128 << VSHIFT);
+    int t;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(t) : "r"(row_tok_s + (in ? row : 0) * 4));
+    tok[k] = in ? t : -1;
+    v[k] = lds128(stage_s + (in ? row : 0) * pitch + vec * 16);
+    g[k] = (size_t)(tok[k] < 0 ? 0 : tok[k]) * row_stride + col0 + vec * 8;
+  }
+  if (resid != nullptr) {
+#pragma unroll
+    for (int k = 0; k < ITER; ++k) rv[k] = (tok[k] >= 0) ? __ldg(reinterpret_cast<const uint4*>(resid + g[k])) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int k = 0; k < ITER; ++k) v[k] = add_bf16x8(v[k], rv[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < ITER; ++k)
+    if (tok[k] >= 0) *reinterpret_cast<uint4*>(out + g[k]) = v[k];
+}
+__device__ __forceinline__ void store_staged_rows(uint32_t stage_s, int pitch, int ncols_log2, const int* row_tok,
+                                                  bf16* __restrict__ out, const bf16* __restrict__ resid,
+                                                  size_t row_stride, int col0, int tid, int nthreads) {
+  const uint32_t rts = smem_u32(row_tok);
+  (void)nthreads;   // 256 worker threads
+  switch (ncols_log2) {
+    case 7: store_staged_rows_t<4>(stage_s, pitch, rts, out, resid, row_stride, col0, tid); break;
+    case 6: store_staged_rows_t<3>(stage_s, pitch, rts, out, resid, row_stride, col0, tid); break;
+    case 5: store_staged_rows_t<2>(stage_s, pitch, rts, out, resid, row_stride, col0, tid); break;
+    default: store_staged_rows_t<1>(stage_s, pitch, rts, out, resid, row_stride, col0, tid); break;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
 // Stage a 128 x C bf16 A operand into shared memory in the K-major SWIZZLE_128B layout
 // ([C/64 k-blocks][128 rows][128 B]), optionally applying LayerNorm (fp32 statistics, biased
 // variance, eps inside the sqrt — nn.LayerNorm as at model.py:881,888) and adding a per-row
@@ -167,73 +256,82 @@ __device__ __forceinline__ void stage_rows_ln(uint8_t* sX, const bf16* __restric
   constexpr int VPL = (C >= 256) ? C / 256 : 1;   // 16-byte vectors per lane
   constexpr int LPT = (C >= 256) ? 32 : C / 8;    // lanes per token
   constexpr int TPP = 32 / LPT;                   // tokens per pass
+  constexpr int RPW = 128 / NW;                   // rows per worker warp
+  constexpr int PASSES = RPW / TPP;
+  constexpr int BATCH = (PASSES * VPL > 8) ? (8 / VPL) : PASSES;   // passes whose loads are in flight together
+  static_assert(PASSES % BATCH == 0, "batching");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sub = lane % LPT;
-  constexpr int RPW = 128 / NW;                   // rows per worker warp
-  for (int t0 = 0; t0 < RPW; t0 += TPP) {
-    const int r = warp * RPW + t0 + lane / LPT;
-    const int tok = row_tok[r];
-    float v[VPL][8];
+  const uint32_t sX_s = smem_u32(sX);
+  for (int p0 = 0; p0 < PASSES; p0 += BATCH) {
+    // ---- issue every global load of the batch before touching any (memory-level parallelism) ----
+    uint4 raw[BATCH][VPL];
+    int toks[BATCH];
 #pragma unroll
-    for (int j = 0; j < VPL; ++j) {
-      const int c0 = j * 256 + sub * 8;
-      if (tok >= 0) {
-        uint4 raw = __ldg(reinterpret_cast<const uint4*>(x + (size_t)tok * C + c0));
-        unpack8(raw, v[j]);
-      } else {
+    for (int b = 0; b < BATCH; ++b) {
+      const int r = warp * RPW + (p0 + b) * TPP + lane / LPT;
+      toks[b] = row_tok[r];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[j][i] = 0.f;
+      for (int j = 0; j < VPL; ++j) {
+        const int c0 = j * 256 + sub * 8;
+        raw[b][j] = (toks[b] >= 0) ? __ldg(reinterpret_cast<const uint4*>(x + (size_t)toks[b] * C + c0)) : make_uint4(0, 0, 0, 0);
       }
     }
-    if (ln_w != nullptr) {
-      float s = 0.f;
 #pragma unroll
-      for (int j = 0; j < VPL; ++j)
+    for (int b = 0; b < BATCH; ++b) {
+      const int r = warp * RPW + (p0 + b) * TPP + lane / LPT;
+      float v[VPL][8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) s += v[j][i];
+      for (int j = 0; j < VPL; ++j) unpack8(raw[b][j], v[j]);
+      if (ln_w != nullptr) {
+        float s = 0.f;
 #pragma unroll
-      for (int o = 1; o < LPT; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      const float mean = s * (1.0f / C);
-      float q = 0.f;
+        for (int j = 0; j < VPL; ++j)
 #pragma unroll
-      for (int j = 0; j < VPL; ++j)
+          for (int i = 0; i < 8; ++i) s += v[j][i];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float d = v[j][i] - mean;
-          q += d * d;
+        for (int o = 1; o < LPT; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float mean = s * (1.0f / C);
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < VPL; ++j)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float d = v[j][i] - mean;
+            q += d * d;
+          }
+#pragma unroll
+        for (int o = 1; o < LPT; o <<= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        const float rstd = rsqrtf(q * (1.0f / C) + eps);
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) {
+          const int c0 = j * 256 + sub * 8;
+          float4 g0 = __ldg(reinterpret_cast<const float4*>(ln_w + c0));
+          float4 g1 = __ldg(reinterpret_cast<const float4*>(ln_w + c0 + 4));
+          float4 b0 = __ldg(reinterpret_cast<const float4*>(ln_b + c0));
+          float4 b1 = __ldg(reinterpret_cast<const float4*>(ln_b + c0 + 4));
+          const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[j][i] = (v[j][i] - mean) * rstd * g[i] + bb[i];
         }
+      }
+      if (addtab != nullptr && toks[b] >= 0) {
 #pragma unroll
-      for (int o = 1; o < LPT; o <<= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-      const float rstd = rsqrtf(q * (1.0f / C) + eps);
+        for (int j = 0; j < VPL; ++j) {
+          const int c0 = j * 256 + sub * 8;
+          const float* t = addtab + (size_t)(r & 63) * C + c0;
+          float4 a0 = __ldg(reinterpret_cast<const float4*>(t));
+          float4 a1 = __ldg(reinterpret_cast<const float4*>(t + 4));
+          v[j][0] += a0.x; v[j][1] += a0.y; v[j][2] += a0.z; v[j][3] += a0.w;
+          v[j][4] += a1.x; v[j][5] += a1.y; v[j][6] += a1.z; v[j][7] += a1.w;
+        }
+      }
 #pragma unroll
       for (int j = 0; j < VPL; ++j) {
         const int c0 = j * 256 + sub * 8;
-        float4 g0 = __ldg(reinterpret_cast<const float4*>(ln_w + c0));
-        float4 g1 = __ldg(reinterpret_cast<const float4*>(ln_w + c0 + 4));
-        float4 b0 = __ldg(reinterpret_cast<const float4*>(ln_b + c0));
-        float4 b1 = __ldg(reinterpret_cast<const float4*>(ln_b + c0 + 4));
-        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-        const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[j][i] = (v[j][i] - mean) * rstd * g[i] + b[i];
+        sts128(sX_s + (c0 >> 6) * (128 * 128) + swz<128>(r, (c0 & 63) * 2), pack8(v[j]));
       }
-    }
-    if (addtab != nullptr && tok >= 0) {
-#pragma unroll
-      for (int j = 0; j < VPL; ++j) {
-        const int c0 = j * 256 + sub * 8;
-        const float* t = addtab + (size_t)(r & 63) * C + c0;
-        float4 a0 = __ldg(reinterpret_cast<const float4*>(t));
-        float4 a1 = __ldg(reinterpret_cast<const float4*>(t + 4));
-        v[j][0] += a0.x; v[j][1] += a0.y; v[j][2] += a0.z; v[j][3] += a0.w;
-        v[j][4] += a1.x; v[j][5] += a1.y; v[j][6] += a1.z; v[j][7] += a1.w;
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < VPL; ++j) {
-      const int c0 = j * 256 + sub * 8;
-      const uint32_t off = (c0 >> 6) * (128 * 128) + swz<128>(r, (c0 & 63) * 2);
-      *reinterpret_cast<uint4*>(sX + off) = pack8(v[j]);
     }
   }
 }

@@ -52,8 +52,7 @@ struct WmsaMisc {
   int row_tok[128];
   uint8_t region[128];
   int win_mixed[2];
-  float xmax[2][128];      // softmax row max / sum halves exchanged between the two column-half threads
-  float xsum[2][128];
+  float bqkv[2][96];       // q|k|v bias of the current / next head (written one head ahead)
   uint64_t bar_full[4], bar_empty[4];
   uint64_t bar_xn, bar_qkv_full, bar_qkv_staged, bar_s_full, bar_p_ready, bar_o_full, bar_oall;
   uint64_t bar_d_full[2], bar_d_empty[2];
@@ -174,14 +173,17 @@ __global__ void __launch_bounds__(kThreads8, (C <= 128) ? 2 : 1) wmsa_kernel(con
     }
   } else {
     // ======================= workers (8 warps) =======================
-    // thread -> tile row r = (warp&3)*32 + lane (== TMEM lane), column half hf = warp>>2
-    const int r = (warp & 3) * 32 + lane;
-    const int hf = warp >> 2;
-    const int wl = r >> 6, i = r & 63;   // window within the tile, token within the window
-    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    // warp w owns the 16 tile rows row16 = (w&3)*32 + (w>>2)*16 .. +16 (TMEM lanes) for every per-head step.
+    // TMEM is read with the 16x256b shape: thread t holds rows row16 + t/4 (+8) and column pairs 8i + 2(t%4).
+    const int row16 = (warp & 3) * 32 + (warp >> 2) * 16;
+    const int wl = row16 >> 6;                       // window of this warp's rows (warp-uniform)
+    const int t4 = lane >> 2, tq = lane & 3;
+    const int r0 = row16 + t4, r1 = r0 + 8;          // this thread's two rows
+    const uint32_t tl = (uint32_t)row16 << 16;       // TMEM lane field
     // ---- source token of every row + region id for the shift mask (one thread per row) ----
-    if (hf == 0) {
-      const int w = tile * 2 + wl;
+    if (tid < 128) {
+      const int r = tid, wlr = r >> 6, i = r & 63;
+      const int w = tile * 2 + wlr;
       int tok = -1;
       uint8_t reg = 0;
       if (w < a.n_windows) {
@@ -204,171 +206,193 @@ __global__ void __launch_bounds__(kThreads8, (C <= 128) ? 2 : 1) wmsa_kernel(con
       }
       ms.row_tok[r] = tok;
       ms.region[r] = reg;
-      if (i == 0) ms.win_mixed[wl] = 0;
+      if (i == 0) ms.win_mixed[wlr] = 0;
     }
     worker_bar8();
-    if (hf == 0 && a.shift > 0 && !a.windowed && ms.region[r] != ms.region[wl * 64]) ms.win_mixed[wl] = 1;
+    if (tid < 128 && a.shift > 0 && !a.windowed && ms.region[tid] != ms.region[(tid >> 6) * 64]) ms.win_mixed[tid >> 6] = 1;
     // ---- A operand: LN(x) + modulator ----
     stage_rows_ln<C, 8>(smem + Cfg::S_X, xin, ms.row_tok, a.ln_w, a.ln_b, a.ln_eps, a.modulator);
     fence_async_smem();
     mbar_arrive(smem_u32(&ms.bar_xn));
 
-    const int tok = ms.row_tok[r];
-    const int yi = i >> 3, xi = i & 7;
-    const int rp_base = (yi + 7) * 15 + xi + 7;
     const uint32_t relpos_s = smem_u32(&ms.relpos[0]);
-    const uint32_t region_s = smem_u32(&ms.region[0]);
-    (void)region_s;
+    // q|k|v bias of head 0 (later heads are written one head ahead, ordered by the p_ready / o_full chain)
+    if (tid < Cfg::QKV_N) ms.bqkv[0][tid] = __ldg(a.bqkv + tid);
+    worker_bar8();
+    // relative-position index base of this thread's two rows (token i = row & 63: yi = i>>3, xi = i&7)
+    const int rp0 = (((r0 & 63) >> 3) + 7) * 15 + (r0 & 7) + 7;
+    const int rp1 = (((r1 & 63) >> 3) + 7) * 15 + (r1 & 7) + 7;
+    constexpr int NBH = HD / 8;                      // 8-column blocks per head slice (4 or 2)
 
     for (int h = 0; h < Cfg::NH; ++h) {
       const uint32_t ph = h & 1;
-      // relative-position bias row of this head -> smem (readers of the previous head are past their softmax barrier)
+      // per-head tables -> smem (readers of the previous head are done: they arrived on p_ready / qkv_staged)
       if (tid < 225) ms.relpos[tid] = __ldg(a.relpos + h * 225 + tid);
-      // ---- QKV epilogue: + bias -> bf16 tiles Q,K (K-major) and V (row-major = MN-major B); 16-col groups alternate halves ----
+      if (h + 1 < Cfg::NH && tid < Cfg::QKV_N) ms.bqkv[(h + 1) & 1][tid] = __ldg(a.bqkv + (h + 1) * Cfg::QKV_N + tid);
+      const uint32_t bqkv_s = smem_u32(&ms.bqkv[h & 1][0]);
+      // ---- QKV epilogue: + bias -> bf16 -> stmatrix into the Q,K (K-major) and V (row-major = MN-major B) tiles ----
       mbar_wait(smem_u32(&ms.bar_qkv_full), ph);
       tc_fence_after();
       {
-        const float* bq = a.bqkv + h * Cfg::QKV_N;
-        constexpr int NG = Cfg::QKV_N / 16;
+        uint32_t v[3][4 * NBH];
 #pragma unroll
-        for (int g = 0; g < NG; ++g) {
-          if ((g & 1) != hf) continue;
-          const int col = g * 16;                      // column inside D_qkv
-          const int part = col / HD, c0 = col % HD;    // 0:q 1:k 2:v, channel inside the head
-          const uint32_t tile_s = (part == 0 ? sQ : part == 1 ? sK : sV);
-          uint32_t v[16];
-          tmem_ld16(tb + lane_base + Cfg::T_WORK + col, v);
-          tmem_wait_ld();
-          float f[16];
+        for (int part = 0; part < 3; ++part) {
+          if (NBH == 4) tmem_ld_16x256b_x4(tb + tl + Cfg::T_WORK + part * HD, v[part]);
+          else tmem_ld_16x256b_x2(tb + tl + Cfg::T_WORK + part * HD, v[part]);
+        }
+        tmem_wait_ld();
+        const int m = lane >> 3, rr = lane & 7;
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bq + col + j));
-            f[j] = __uint_as_float(v[j]) + b4.x; f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
-            f[j + 2] = __uint_as_float(v[j + 2]) + b4.z; f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
+        for (int part = 0; part < 3; ++part) {
+          f2 bb[NBH];
+#pragma unroll
+          for (int i = 0; i < NBH; ++i) {
+            const float2 b2 = lds64f(bqkv_s + (part * HD + 8 * i + 2 * tq) * 4);
+            bb[i] = f2_pack(b2.x, b2.y);
           }
-          sts128(tile_s + swz<Cfg::SWH>(r, c0 * 2), pack8(f));
-          sts128(tile_s + swz<Cfg::SWH>(r, c0 * 2 + 16), pack8(f + 8));
+          uint32_t pk[2 * NBH];
+          frag_bias_act_pack<NBH, false>(v[part], bb, pk);
+          const uint32_t tile_s = (part == 0 ? sQ : part == 1 ? sK : sV);
+          const int row = row16 + (m & 1) * 8 + rr;
+#pragma unroll
+          for (int i2 = 0; i2 < NBH / 2; ++i2)
+            stsm_x4(tile_s + swz<Cfg::SWH>(row, (2 * i2 + (m >> 1)) * 16), pk[4 * i2], pk[4 * i2 + 1], pk[4 * i2 + 2], pk[4 * i2 + 3]);
         }
       }
       fence_async_smem();
       tc_fence_before();
       mbar_arrive(smem_u32(&ms.bar_qkv_staged));
 
-      // ---- softmax: this thread owns keys [hf*32, hf*32+32) of its row ----
+      // ---- softmax over the 64 keys of this warp's 16 rows; a row lives in the 4 threads of a quad ----
       mbar_wait(smem_u32(&ms.bar_s_full), ph);
       tc_fence_after();
-      float s[32];
+      float sum0, sum1;
       {
         uint32_t v[32];
-        tmem_ld32(tb + lane_base + Cfg::T_WORK + wl * 64 + hf * 32, v);
+        tmem_ld_16x256b_x8(tb + tl + Cfg::T_WORK + wl * 64, v);
         tmem_wait_ld();
+        float s0[16], s1[16];                        // row r0 / r1, keys 8b + 2tq + e  (index 2b + e)
 #pragma unroll
-        for (int j = 0; j < 32; ++j) s[j] = __uint_as_float(v[j]);
-      }
+        for (int b = 0; b < 8; ++b) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int key = hf * 32 + j;                   // hf is warp-uniform
-        s[j] += lds32f(relpos_s + (rp_base - (key >> 3) * 15 - (key & 7)) * 4);
-      }
-      if (ms.win_mixed[wl]) {
-        const uint8_t myreg = ms.region[r];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) s[j] += (ms.region[wl * 64 + hf * 32 + j] != myreg) ? -100.0f : 0.0f;
-      }
-      if (a.mask != nullptr && tok >= 0) {
-        const int w = tile * 2 + wl;
-        const float* mrow = a.mask + ((size_t)(w % a.n_mask_windows) * 64 + i) * 64 + hf * 32;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 m4 = __ldg(reinterpret_cast<const float4*>(mrow + j));
-          s[j] += m4.x; s[j + 1] += m4.y; s[j + 2] += m4.z; s[j + 3] += m4.w;
+          for (int e = 0; e < 2; ++e) {
+            const int koff = b * 15 + 2 * tq + e;    // (key>>3)*15 + (key&7)
+            s0[2 * b + e] = __uint_as_float(v[4 * b + e]) + lds32f(relpos_s + (rp0 - koff) * 4);
+            s1[2 * b + e] = __uint_as_float(v[4 * b + 2 + e]) + lds32f(relpos_s + (rp1 - koff) * 4);
+          }
         }
-      }
-      float mx = s[0];
+        if (ms.win_mixed[wl]) {
+          const uint8_t g0 = ms.region[r0], g1 = ms.region[r1];
 #pragma unroll
-      for (int j = 1; j < 32; ++j) mx = fmaxf(mx, s[j]);
-      ms.xmax[hf][r] = mx;
-      worker_bar8();
-      mx = fmaxf(mx, ms.xmax[hf ^ 1][r]);
-      float sum = 0.f;
-      const float mxs = mx * kLog2e;
+          for (int b = 0; b < 8; ++b)
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        s[j] = exp2f(fmaf(s[j], kLog2e, -mxs));
-        sum += s[j];
-      }
-      ms.xsum[hf][r] = sum;
-      // P (unnormalised, bf16) over the S columns: this row's keys at packed cols [wl*32 + hf*16, +16), zeros in the other window's cols
-      {
+            for (int e = 0; e < 2; ++e) {
+              const uint8_t gk = ms.region[wl * 64 + 8 * b + 2 * tq + e];
+              s0[2 * b + e] += (gk != g0) ? -100.0f : 0.0f;
+              s1[2 * b + e] += (gk != g1) ? -100.0f : 0.0f;
+            }
+        }
+        if (a.mask != nullptr) {
+          const int w = tile * 2 + wl;
+          if (w < a.n_windows) {
+            const float* m0 = a.mask + ((size_t)(w % a.n_mask_windows) * 64 + (r0 & 63)) * 64;
+            const float* m1 = a.mask + ((size_t)(w % a.n_mask_windows) * 64 + (r1 & 63)) * 64;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+              const float2 a0 = __ldg(reinterpret_cast<const float2*>(m0 + 8 * b + 2 * tq));
+              const float2 a1 = __ldg(reinterpret_cast<const float2*>(m1 + 8 * b + 2 * tq));
+              s0[2 * b] += a0.x; s0[2 * b + 1] += a0.y;
+              s1[2 * b] += a1.x; s1[2 * b + 1] += a1.y;
+            }
+          }
+        }
+        float mx0 = s0[0], mx1 = s1[0];
+#pragma unroll
+        for (int j = 1; j < 16; ++j) { mx0 = fmaxf(mx0, s0[j]); mx1 = fmaxf(mx1, s1[j]); }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float ms0 = mx0 * kLog2e, ms1 = mx1 * kLog2e;
+        sum0 = 0.f; sum1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          s0[j] = exp2f(fmaf(s0[j], kLog2e, -ms0)); sum0 += s0[j];
+          s1[j] = exp2f(fmaf(s1[j], kLog2e, -ms1)); sum1 += s1[j];
+        }
+        sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+        sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+        // P (unnormalised bf16) as the A operand of P·V: packed key pairs -> 16x128b fragments.  This window's
+        // keys go to packed columns [wl*32, +32); the other window's columns are zero (block-diagonal P).
         uint32_t pk[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(s[2 * j], s[2 * j + 1]);
-        tmem_st16(tb + lane_base + Cfg::T_WORK + wl * 32 + hf * 16, pk);
+        for (int b = 0; b < 8; ++b) {
+          pk[2 * b] = pack_bf16(s0[2 * b], s0[2 * b + 1]);
+          pk[2 * b + 1] = pack_bf16(s1[2 * b], s1[2 * b + 1]);
+        }
+        tmem_st_16x128b_x8(tb + tl + Cfg::T_WORK + wl * 32, pk);
 #pragma unroll
         for (int j = 0; j < 16; ++j) pk[j] = 0u;
-        tmem_st16(tb + lane_base + Cfg::T_WORK + (1 - wl) * 32 + hf * 16, pk);
+        tmem_st_16x128b_x8(tb + tl + Cfg::T_WORK + (1 - wl) * 32, pk);
         tmem_wait_st();
       }
       tc_fence_before();
       mbar_arrive(smem_u32(&ms.bar_p_ready));
 
-      // ---- O epilogue: normalise, park as bf16 A operand of the projection (16-col groups alternate halves) ----
+      // ---- O epilogue: normalise, park as bf16 A operand of the projection ----
       mbar_wait(smem_u32(&ms.bar_o_full), ph);
       tc_fence_after();
-      if (hf * 16 < HD) {
-        const float inv = 1.0f / (ms.xsum[0][r] + ms.xsum[1][r]);
-        const int c0 = hf * 16;
-        uint32_t v[16];
-        tmem_ld16(tb + lane_base + Cfg::T_DO + c0, v);
+      {
+        uint32_t v[4 * NBH];
+        if (NBH == 4) tmem_ld_16x256b_x4(tb + tl + Cfg::T_DO, v); else tmem_ld_16x256b_x2(tb + tl + Cfg::T_DO, v);
         tmem_wait_ld();
-        uint32_t pk[8];
+        const float i0 = 1.0f / sum0, i1 = 1.0f / sum1;
+        uint32_t pk[2 * NBH];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) pk[j] = pack_bf16(__uint_as_float(v[2 * j]) * inv, __uint_as_float(v[2 * j + 1]) * inv);
-        tmem_st8(tb + lane_base + Cfg::T_OALL + (h * HD + c0) / 2, pk);
+        for (int i = 0; i < NBH; ++i) {
+          pk[2 * i] = pack_bf16(__uint_as_float(v[4 * i]) * i0, __uint_as_float(v[4 * i + 1]) * i0);
+          pk[2 * i + 1] = pack_bf16(__uint_as_float(v[4 * i + 2]) * i1, __uint_as_float(v[4 * i + 3]) * i1);
+        }
+        if (NBH == 4) tmem_st_16x128b_x4(tb + tl + Cfg::T_OALL + (h * HD) / 2, pk);
+        else tmem_st_16x128b_x2(tb + tl + Cfg::T_OALL + (h * HD) / 2, pk);
         tmem_wait_st();
       }
       tc_fence_before();
     }
     mbar_arrive(smem_u32(&ms.bar_oall));
 
-    // ---- projection epilogue: + bias + shortcut, scatter to the (un-rolled) token positions ----
+    // ---- projection epilogue: + bias -> bf16 -> staging tile (the A operand / Q,K,V tiles are dead now) ->
+    // coalesced scatter to the (un-rolled) token positions with the shortcut added on the way ----
     bf16* __restrict__ outp = reinterpret_cast<bf16*>(a.out);
     const bf16* __restrict__ resid = reinterpret_cast<const bf16*>(a.resid);
+    constexpr int PITCH = Cfg::NCH * 2 + 16;
+    static_assert(128 * PITCH <= Cfg::S_RING, "staging tile must fit in the dead A/QKV region");
+    constexpr int NCH_LOG2 = Cfg::NCH == 128 ? 7 : Cfg::NCH == 64 ? 6 : Cfg::NCH == 32 ? 5 : 4;
+    constexpr int NBP = (Cfg::NCH >= 64) ? 8 : Cfg::NCH / 8;          // column blocks per TMEM load (64 / 32 / 16 columns)
+    const uint32_t stage_s = sX;
     for (int nc = 0; nc < Cfg::NC; ++nc) {
       const int buf = nc & 1;
       mbar_wait(smem_u32(&ms.bar_d_full[buf]), (nc >> 1) & 1);
       tc_fence_after();
-#pragma unroll 1
-      for (int c0 = hf * 16; c0 < Cfg::NCH; c0 += 32) {
-        uint32_t v[16];
-        tmem_ld16(tb + lane_base + Cfg::T_WORK + buf * 128 + c0, v);
-        tmem_wait_ld();
-        if (tok >= 0) {
-          const int col = nc * Cfg::NCH + c0;
-          float f[16];
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bproj + col + j));
-            f[j] = __uint_as_float(v[j]) + b4.x; f[j + 1] = __uint_as_float(v[j + 1]) + b4.y;
-            f[j + 2] = __uint_as_float(v[j + 2]) + b4.z; f[j + 3] = __uint_as_float(v[j + 3]) + b4.w;
-          }
-          if (resid != nullptr) {
-            const uint4* rp = reinterpret_cast<const uint4*>(resid + (size_t)tok * C + col);
-            float g[8];
-            unpack8(__ldg(rp), g);
+      for (int c0 = 0; c0 < Cfg::NCH; c0 += 8 * NBP) {
+        uint32_t v[4 * NBP];
+        const uint32_t ta = tb + tl + Cfg::T_WORK + buf * 128 + c0;
+        if (NBP == 8) tmem_ld_16x256b_x8(ta, v); else if (NBP == 4) tmem_ld_16x256b_x4(ta, v); else tmem_ld_16x256b_x2(ta, v);
+        f2 bb[NBP];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] += g[j];
-            unpack8(__ldg(rp + 1), g);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[8 + j] += g[j];
-          }
-          uint4* op = reinterpret_cast<uint4*>(outp + (size_t)tok * C + col);
-          op[0] = pack8(f);
-          op[1] = pack8(f + 8);
+        for (int i = 0; i < NBP; ++i) {
+          const float2 b2 = __ldg(reinterpret_cast<const float2*>(a.bproj + nc * Cfg::NCH + c0 + 8 * i + 2 * tq));
+          bb[i] = f2_pack(b2.x, b2.y);
         }
+        tmem_wait_ld();
+        uint32_t pk[2 * NBP];
+        frag_bias_act_pack<NBP, false>(v, bb, pk);
+        stage_frag<NBP>(stage_s, PITCH, row16, c0, pk);
       }
       tc_fence_before();
       mbar_arrive(smem_u32(&ms.bar_d_empty[buf]));
+      worker_bar8();
+      store_staged_rows(stage_s, PITCH, NCH_LOG2, ms.row_tok, outp, resid, (size_t)C, nc * Cfg::NCH, tid, kWorkers8);
+      worker_bar8();
     }
   }
   // ---------------- teardown ----------------

@@ -185,7 +185,7 @@ class LeFF(nn.Module):
 
         def build():
             wd, bd = packing.pack_dwconv(dw.weight, dw.bias)
-            return dict(w1_img=packing.pack_kmajor(l1.weight, min(self.hidden_dim, 128), "nk"), b1=l1.bias.float().contiguous(),
+            return dict(w1_img=packing.pack_kmajor(l1.weight, _lib.load().lw_nch_ares(self.dim, self.hidden_dim), "nk"), b1=l1.bias.float().contiguous(),
                         wd=wd, bd=bd, w2_img=packing.pack_kmajor(l2.weight, min(self.dim, 128), "kn"),
                         b2=l2.bias.float().contiguous(), hidden=self.hidden_dim)
         return self._cache.get(srcs, build)
@@ -249,7 +249,7 @@ class Upsample(nn.Module):
     def packed(self):
         dc = self.deconv[0]
         return self._cache.get([dc.weight, dc.bias], lambda: dict(
-            w_img=packing.pack_upsample(dc.weight, min(4 * self.out_channel, 128)), bias=dc.bias.float().contiguous(),
+            w_img=packing.pack_upsample(dc.weight, _lib.load().lw_nch_ares(self.in_channel, 4 * self.out_channel)), bias=dc.bias.float().contiguous(),
             cout=self.out_channel))
 
     def forward(self, x, out=None):
