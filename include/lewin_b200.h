@@ -66,6 +66,8 @@ typedef struct lw_wmsa_args {
   int32_t shift;           /* cyclic shift (0 or 4); the {0,-100} region mask is computed in-kernel */
   int32_t windowed;        /* 1: x/out are already window-major (WindowAttention standalone) */
   float ln_eps;
+  int32_t dbg;             /* profiling aid (env LW_DEBUG & 16): CTA 0 writes clock64 timestamps to `trace` */
+  long long* trace;
 } lw_wmsa_args;
 int lw_wmsa_fwd(const lw_wmsa_args* a, lw_stream_t stream);
 

@@ -23,7 +23,7 @@ class WmsaArgs(C.Structure):
                 ("modulator", C.c_void_p), ("wqkv_img", C.c_void_p), ("bqkv", C.c_void_p), ("wproj_img", C.c_void_p),
                 ("bproj", C.c_void_p), ("relpos", C.c_void_p), ("mask", C.c_void_p), ("n_mask_windows", C.c_int32),
                 ("n_windows", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32), ("head_dim", C.c_int32),
-                ("shift", C.c_int32), ("windowed", C.c_int32), ("ln_eps", C.c_float)]
+                ("shift", C.c_int32), ("windowed", C.c_int32), ("ln_eps", C.c_float), ("dbg", C.c_int32), ("trace", C.c_void_p)]
 
 
 class Leff1Args(C.Structure):

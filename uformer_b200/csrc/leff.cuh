@@ -117,40 +117,43 @@ __global__ void __launch_bounds__(kThreads8, (K <= 128) ? 2 : 1) ares_kernel(con
       Ring ring{smem_u32(smem + Cfg::S_RING), smem_u32(&ms.bar_full[0]), smem_u32(&ms.bar_empty[0]), Cfg::STAGES, 0, Cfg::STAGE_BYTES};
       for (int nc = 0; nc < NC; ++nc)
         for (int kb = 0; kb < Cfg::KB; ++kb)
-          if (a.dbg & 4) { mbar_wait(ring.empty(), ring.phase() ^ 1); mbar_arrive(ring.full()); ++ring.idx; }
+          if (LW_DBG(a, 4)) { mbar_wait(ring.empty(), ring.phase() ^ 1); mbar_arrive(ring.full()); ++ring.idx; }
           else ring.load(a.w_img + (size_t)(nc * Cfg::KB + kb) * chunk_bytes, chunk_bytes);
     }
   } else if (warp == 9) {
-    if (lane == 0) {
+    {   // issuer warp: warp-uniform control flow, one elected lane issues (operands stay in uniform registers)
       Ring ring{smem_u32(smem + Cfg::S_RING), smem_u32(&ms.bar_full[0]), smem_u32(&ms.bar_empty[0]), Cfg::STAGES, 0, Cfg::STAGE_BYTES};
       const uint32_t idesc = make_idesc_bf16(128, a.nch);
       const uint32_t ring_base = smem_u32(smem + Cfg::S_RING);
       const uint64_t a_desc0 = kmajor_desc<128>(sX), b_desc0 = kmajor_desc<128>(ring_base);   // address field += bytes >> 4
-      const bool tr = (a.dbg & 16) && blockIdx.x == 0 && a.trace != nullptr;
-      int ti = 0;
-      if (tr) a.trace[ti++] = clock64();
+      LW_TRACE_STMT(const bool tr = (a.dbg & 16) && blockIdx.x == 0 && a.trace != nullptr; int ti = 0;)
+      LW_TRACE_STMT(if (tr) a.trace[ti++] = clock64();)
       mbar_wait(smem_u32(&ms.bar_a_ready), 0);
       tc_fence_after();
-      if (tr) a.trace[ti++] = clock64();
+      LW_TRACE_STMT(if (tr) a.trace[ti++] = clock64();)
       for (int nc = 0; nc < NC; ++nc) {
         const int buf = nc & 1;
         mbar_wait(smem_u32(&ms.bar_d_empty[buf]), ((nc >> 1) & 1) ^ 1);
         tc_fence_after();
-        if (tr) a.trace[ti++] = clock64();
+        LW_TRACE_STMT(if (tr) a.trace[ti++] = clock64();)
         for (int kb = 0; kb < Cfg::KB; ++kb) {
           const uint32_t wst = ring.acquire();
-          if (tr) a.trace[ti++] = clock64();
+          LW_TRACE_STMT(if (tr) a.trace[ti++] = clock64();)
           constexpr int KS = (K >= 64) ? 4 : K / 16;
           const uint64_t ad = a_desc0 + (uint64_t)(kb * 1024), bd = b_desc0 + (uint64_t)((wst - ring_base) >> 4);
+          if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < KS; ++ks)
-            umma_ss(tb + buf * Cfg::NCH_MAX, ad + 2 * ks, bd + 2 * ks, idesc, (kb | ks) != 0);
+            for (int ks = 0; ks < KS; ++ks)
+              umma_ss(tb + buf * Cfg::NCH_MAX, ad + 2 * ks, bd + 2 * ks, idesc, (kb | ks) != 0);
+          }
+          __syncwarp();
           ring.release();
-          if (tr) a.trace[ti++] = clock64();
+          LW_TRACE_STMT(if (tr) a.trace[ti++] = clock64();)
         }
-        umma_commit(smem_u32(&ms.bar_d_full[buf]));
+        if (elect_one()) umma_commit(smem_u32(&ms.bar_d_full[buf]));
+        __syncwarp();
       }
-      if (tr) a.trace[ti++] = -1;
+      LW_TRACE_STMT(if (tr) a.trace[ti++] = -1;)
     }
   } else {
     // 8 worker warps: stage 16 A rows each; epilogue: lane quadrant warp&3, column half warp>>2
@@ -167,7 +170,7 @@ __global__ void __launch_bounds__(kThreads8, (K <= 128) ? 2 : 1) ares_kernel(con
       }
     }
     worker_bar8();
-    if (!(a.dbg & 8)) stage_rows_ln<K, 8>(smem + Cfg::S_X, a.x, ms.row_tok, a.ln_w, a.ln_b, a.ln_eps, nullptr);
+    if (!LW_DBG(a, 8)) stage_rows_ln<K, 8>(smem + Cfg::S_X, a.x, ms.row_tok, a.ln_w, a.ln_b, a.ln_eps, nullptr);
     fence_async_smem();
     mbar_arrive(smem_u32(&ms.bar_a_ready));
     const int half = warp >> 2;
@@ -187,28 +190,27 @@ __global__ void __launch_bounds__(kThreads8, (K <= 128) ? 2 : 1) ares_kernel(con
     const int sub_cols = a.nch < 128 ? a.nch : 128;          // staged 128 columns at a time
     int sub_log2 = 4;
     while ((1 << sub_log2) < sub_cols) ++sub_log2;
-    const bool trw = (a.dbg & 16) && blockIdx.x == 0 && tid == 0 && a.trace != nullptr;
-    int tw = 512, tw2 = 1024;
-    if (trw) a.trace[tw++] = clock64();
+    LW_TRACE_STMT(const bool trw = (a.dbg & 16) && blockIdx.x == 0 && tid == 0 && a.trace != nullptr; int tw = 512, tw2 = 1024;)
+    LW_TRACE_STMT(if (trw) a.trace[tw++] = clock64();)
     for (int nc = 0; nc < NC; ++nc) {
       const int buf = nc & 1;
       mbar_wait(smem_u32(&ms.bar_d_full[buf]), (nc >> 1) & 1);
       tc_fence_after();
-      if (trw) a.trace[tw++] = clock64();
+      LW_TRACE_STMT(if (trw) a.trace[tw++] = clock64();)
       for (int sc = 0; sc < a.nch; sc += 128) {
         // ---- phase A: TMEM (16x256b fragments) -> (+bias, GELU) -> bf16 -> stmatrix into the staging tile.
         // warp (q, half): lanes q*32..+32 as two 16-lane groups, columns half*cph .. +cph of the sub-chunk ----
         if (sub_cols == 128) ares_phase_a<8, EPI>(a, tb + buf * Cfg::NCH_MAX + sc, nc * a.nch + sc, bias_s, stage_s, Cfg::STAGE_PITCH);
         else ares_phase_a<4, EPI>(a, tb + buf * Cfg::NCH_MAX + sc, nc * a.nch + sc, bias_s, stage_s, Cfg::STAGE_PITCH);
-        if (trw && nc == 1) a.trace[tw2++] = clock64();
+        LW_TRACE_STMT(if (trw && nc == 1) a.trace[tw2++] = clock64();)
         if (sc + 128 >= a.nch) {            // accumulator fully read: hand the buffer back to the issuer
           tc_fence_before();
           mbar_arrive(smem_u32(&ms.bar_d_empty[buf]));
         }
         worker_bar8();
-        if (trw && nc == 1) a.trace[tw2++] = clock64();
+        LW_TRACE_STMT(if (trw && nc == 1) a.trace[tw2++] = clock64();)
         // ---- phase B: coalesced copy-out ----
-        if (!(a.dbg & 1)) {
+        if (!LW_DBG(a, 1)) {
           if (EPI == 0) {
             store_staged_rows(stage_s, Cfg::STAGE_PITCH, sub_log2, ms.row_tok, a.out, nullptr, (size_t)a.n_total,
                               nc * a.nch + sc, tid, kWorkers8);
@@ -226,12 +228,12 @@ __global__ void __launch_bounds__(kThreads8, (K <= 128) ? 2 : 1) ares_kernel(con
             }
           }
         }
-        if (trw && nc == 1) a.trace[tw2++] = clock64();
+        LW_TRACE_STMT(if (trw && nc == 1) a.trace[tw2++] = clock64();)
         worker_bar8();                      // staging tile free for the next phase A
-        if (trw) a.trace[tw++] = clock64();
+        LW_TRACE_STMT(if (trw) a.trace[tw++] = clock64();)
       }
     }
-    if (trw) { a.trace[tw++] = -1; a.trace[tw2++] = -1; }
+    LW_TRACE_STMT(if (trw) { a.trace[tw++] = -1; a.trace[tw2++] = -1; })
   }
   tc_fence_before();
   __syncthreads();
@@ -256,6 +258,8 @@ struct AStreamArgs {
   bf16* out;              // (rows, N)
   int TW, TH;             // PROD 0 tile shape (TW*TH == 128)
   int tiles_x;
+  long long* trace;       // profiling aid (LW_DEBUG & 16)
+  int dbg;
 };
 
 constexpr int kHaloMaxTok = 18 * 10;   // (TW+2)*(TH+2) upper bound for TW in {8,16}: 10*18 = 180
@@ -302,7 +306,7 @@ __global__ void __launch_bounds__(kThreads, 1) astream_kernel(const AStreamArgs 
           ring.load(a.w_img + (size_t)(kb * NC + nc) * chunk_bytes, chunk_bytes);
     }
   } else if (warp == 5) {
-    if (lane == 0) {
+    {   // issuer warp (warp-uniform; one elected lane issues)
       Ring ring{smem_u32(smem + Cfg::S_RING), smem_u32(&ms.bar_full[0]), smem_u32(&ms.bar_empty[0]), Cfg::STAGES, 0};
       const uint32_t idesc = make_idesc_bf16(128, a.nch);
       for (int kb = 0; kb < KB; ++kb) {
@@ -312,14 +316,19 @@ __global__ void __launch_bounds__(kThreads, 1) astream_kernel(const AStreamArgs 
         const uint32_t sA = smem_u32(smem + Cfg::S_A + ab * 16384);
         for (int nc = 0; nc < NC; ++nc) {
           const uint32_t wst = ring.acquire();
+          if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            umma_ss(tb + nc * a.nch, kmajor_desc<128>(sA + ks * 32), kmajor_desc<128>(wst + ks * 32), idesc, (kb | ks) != 0);
+            for (int ks = 0; ks < 4; ++ks)
+              umma_ss(tb + nc * a.nch, kmajor_desc<128>(sA + ks * 32), kmajor_desc<128>(wst + ks * 32), idesc, (kb | ks) != 0);
+          }
+          __syncwarp();
           ring.release();
         }
-        umma_commit(smem_u32(&ms.bar_a_empty[ab]));
+        if (elect_one()) umma_commit(smem_u32(&ms.bar_a_empty[ab]));
+        __syncwarp();
       }
-      umma_commit(smem_u32(&ms.bar_d_full[0]));
+      if (elect_one()) umma_commit(smem_u32(&ms.bar_d_full[0]));
+      __syncwarp();
     }
   } else {
     const int r = tid;

@@ -87,24 +87,31 @@ __global__ void __launch_bounds__(kL2Threads, 1) leff2_kernel(const AStreamArgs 
           ring.load(a.w_img + (size_t)(kb * NC + nc) * chunk_bytes, chunk_bytes);
     }
   } else if (warp == 9) {
-    if (lane == 0) {
+    {   // issuer warp (warp-uniform; one elected lane issues so descriptors stay in uniform registers)
       Ring ring{smem_u32(smem + Cfg::S_RING), smem_u32(&ms.bar_full[0]), smem_u32(&ms.bar_empty[0]), Cfg::STAGES, 0};
       const uint32_t idesc = make_idesc_bf16(128, a.nch);
+      const uint32_t ring_base = smem_u32(smem + Cfg::S_RING);
+      const uint64_t b_desc0 = kmajor_desc<128>(ring_base);
       for (int kb = 0; kb < KB; ++kb) {
         const int ab = kb & 1;
         mbar_wait(smem_u32(&ms.bar_a_full[ab]), (kb >> 1) & 1);
         tc_fence_after();
-        const uint32_t sA = smem_u32(smem + Cfg::S_A + ab * 16384);
+        const uint64_t ad = kmajor_desc<128>(smem_u32(smem + Cfg::S_A + ab * 16384));
         for (int nc = 0; nc < NC; ++nc) {
           const uint32_t wst = ring.acquire();
+          const uint64_t bd = b_desc0 + (uint64_t)((wst - ring_base) >> 4);
+          if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            umma_ss(tb + nc * a.nch, kmajor_desc<128>(sA + ks * 32), kmajor_desc<128>(wst + ks * 32), idesc, (kb | ks) != 0);
+            for (int ks = 0; ks < 4; ++ks) umma_ss(tb + nc * a.nch, ad + 2 * ks, bd + 2 * ks, idesc, (kb | ks) != 0);
+          }
+          __syncwarp();
           ring.release();
         }
-        umma_commit(smem_u32(&ms.bar_a_empty[ab]));
+        if (elect_one()) umma_commit(smem_u32(&ms.bar_a_empty[ab]));
+        __syncwarp();
       }
-      umma_commit(smem_u32(&ms.bar_d_full[0]));
+      if (elect_one()) umma_commit(smem_u32(&ms.bar_d_full[0]));
+      __syncwarp();
     }
   } else {
     // ============================== workers ==============================
@@ -146,12 +153,16 @@ __global__ void __launch_bounds__(kL2Threads, 1) leff2_kernel(const AStreamArgs 
       cp_async_commit();
     };
 
+    LW_TRACE_STMT(const bool trw = (a.dbg & 16) && blockIdx.x == 0 && tid == 0 && a.trace != nullptr; int tw = 0;)
+    LW_TRACE_STMT(if (trw) a.trace[tw++] = clock64();)
     prefetch(0);
     for (int kb = 0; kb < KB; ++kb) {
       const int ab = kb & 1;
       cp_async_wait_all();
       l2_worker_bar();                         // slice kb halo + taps visible; buffers of slice kb-1 free
+      LW_TRACE_STMT(if (trw && kb < 6) a.trace[tw++] = clock64();)
       if (kb + 1 < KB) prefetch(kb + 1);
+      LW_TRACE_STMT(if (trw && kb < 6) a.trace[tw++] = clock64();)
       const uint32_t sH = halo0 + ab * 23552;
       const uint32_t sW = wd0 + ab * 2560;
       // taps of this thread's 8 channels -> registers (as fp32 pairs)
@@ -172,6 +183,7 @@ __global__ void __launch_bounds__(kL2Threads, 1) leff2_kernel(const AStreamArgs 
           acc[o][2] = f2_pack(b1.x, b1.y); acc[o][3] = f2_pack(b1.z, b1.w);
         }
       }
+      LW_TRACE_STMT(if (trw && kb < 6) a.trace[tw++] = clock64();)
       // slide down the column: halo rows hf*4 + r, r = 0..5 ; halo row r feeds output row o = r - ky
 #pragma unroll
       for (int r = 0; r < 6; ++r) {
@@ -191,8 +203,10 @@ __global__ void __launch_bounds__(kL2Threads, 1) leff2_kernel(const AStreamArgs 
           }
         }
       }
+      LW_TRACE_STMT(if (trw && kb < 6) a.trace[tw++] = clock64();)
       // A buffer ab must have been consumed by the MMAs of slice kb-2
       mbar_wait(smem_u32(&ms.bar_a_empty[ab]), ((kb >> 1) & 1) ^ 1);
+      LW_TRACE_STMT(if (trw && kb < 6) a.trace[tw++] = clock64();)
       const uint32_t sA = smem_u32(smem + Cfg::S_A + ab * 16384);
 #pragma unroll
       for (int o = 0; o < 4; ++o) {
@@ -206,7 +220,9 @@ __global__ void __launch_bounds__(kL2Threads, 1) leff2_kernel(const AStreamArgs 
       }
       fence_async_smem();
       mbar_arrive(smem_u32(&ms.bar_a_full[ab]));
+      LW_TRACE_STMT(if (trw && kb < 6) a.trace[tw++] = clock64();)
     }
+    LW_TRACE_STMT(if (trw) a.trace[tw++] = clock64();)
 
     // ---------------- epilogue: + bias -> bf16 -> staging tile (the halo buffers are free now) ->
     // coalesced copy-out with the residual added on the way (warp w: lane quadrant w&3, column half w>>2)
@@ -232,7 +248,9 @@ __global__ void __launch_bounds__(kL2Threads, 1) leff2_kernel(const AStreamArgs 
       l2_worker_bar();
       store_staged_rows(stage_s, pitch, sub_log2, ms.row_tok, a.out, a.resid, (size_t)a.N, sc, tid, kL2Workers);
       l2_worker_bar();
+      LW_TRACE_STMT(if (trw) a.trace[tw++] = clock64();)
     }
+    LW_TRACE_STMT(if (trw) a.trace[tw++] = -1;)
   }
   tc_fence_before();
   __syncthreads();

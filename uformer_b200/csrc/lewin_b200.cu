@@ -73,6 +73,14 @@ extern "C" int lw_wmsa_fwd(const lw_wmsa_args* a, lw_stream_t stream) {
   }
   if (a->mask && a->n_mask_windows <= 0) return LW_ERR_BAD_SHAPE;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  lw_wmsa_args aa = *a;
+  aa.dbg = debug_flags();
+  aa.trace = nullptr;
+  if (aa.dbg & 16) {
+    const char* e = getenv("LW_TRACE_PTR");
+    aa.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr;
+  }
+  a = &aa;
 #define WMSA_CASE(c, hd) \
   if (a->C == c && a->head_dim == hd) return launch_wmsa<c, hd>(a, st);
   WMSA_CASE(32, 32) WMSA_CASE(64, 32) WMSA_CASE(128, 32) WMSA_CASE(256, 32) WMSA_CASE(512, 32)
@@ -152,6 +160,11 @@ extern "C" int lw_leff2_fwd(const lw_leff2_args* p, lw_stream_t stream) {
   a.N = p->C; a.nch = p->C < 128 ? p->C : 128; a.bias = p->b2;
   a.resid = reinterpret_cast<const bf16*>(p->resid); a.out = reinterpret_cast<bf16*>(p->out);
   if (p->H % 8) return LW_ERR_BAD_SHAPE;
+  a.dbg = debug_flags();
+  if (a.dbg & 16) {
+    const char* e = getenv("LW_TRACE_PTR");
+    a.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr;
+  }
   a.TW = 16; a.TH = 8;
   a.tiles_x = (p->W + 15) / 16;
   const int tiles = a.tiles_x * (p->H / 8) * p->B;

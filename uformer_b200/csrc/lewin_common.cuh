@@ -10,7 +10,23 @@
 #pragma once
 #include "umma.cuh"
 
+// Profiling aids (per-CTA clock64 timelines, LW_DEBUG knobs) are compiled in only with -DLW_TRACE: their
+// branches split the hot loops into small basic blocks and cost real time in production builds.
+#ifdef LW_TRACE
+#define LW_TRACE_STMT(...) __VA_ARGS__
+#define LW_DBG(a, bit) ((a).dbg & (bit))
+#else
+#define LW_TRACE_STMT(...)
+#define LW_DBG(a, bit) 0
+#endif
+
 namespace lw {
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 
 constexpr int kWorkers = 128;     // legacy 4-worker-warp skeleton (downsample)
 constexpr int kThreads = 192;
@@ -55,8 +71,10 @@ struct Ring {
     tc_fence_after();
     return stage_addr();
   }
+  // issuer side is warp-uniform: every lane tracks the ring, one elected lane commits
   __device__ __forceinline__ void release() {
-    umma_commit(empty());
+    if (elect_one()) umma_commit(empty());
+    __syncwarp();
     ++idx;
   }
 };

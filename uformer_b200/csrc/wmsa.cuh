@@ -32,9 +32,13 @@ struct WmsaCfg {
   static constexpr int STAGES = (C >= 512) ? 3 : (C == 128 ? 2 : 4);   // C=128: 2 stages so two CTAs fit per SM
   // TMEM columns
   static constexpr int T_OALL = 0;                         // O for all heads, bf16 packed: C/2 cols
-  static constexpr int T_WORK = (C / 2 < 32) ? 32 : C / 2; // S / D_qkv (aliased), 128 cols
+  static constexpr int T_WORK = (C / 2 < 32) ? 32 : C / 2; // S / P (128 cols); also D_out buffer 0
   static constexpr int T_DO = T_WORK + 128;                // D_o, HD cols (<= 32)
-  static constexpr int T_NEED = T_WORK + ((NC > 1) ? 256 : 160);
+  // C >= 256 (1 CTA/SM anyway): D_qkv gets its own 96 columns so the issuer can run the QKV GEMM of head h+1
+  // underneath the softmax of head h.  C <= 128: D_qkv aliases S so that two CTAs fit in TMEM.
+  static constexpr bool PIPE = (C >= 256);
+  static constexpr int T_QKV = PIPE ? T_DO + 32 : T_WORK;
+  static constexpr int T_NEED = T_WORK + ((NC > 1 || PIPE) ? 256 : 160);
   static constexpr int T_ALLOC = T_NEED <= 256 ? 256 : 512;
   // shared memory map (bytes)
   static constexpr int S_X = 0;
@@ -106,50 +110,66 @@ __global__ void __launch_bounds__(kThreads8, (C <= 128) ? 2 : 1) wmsa_kernel(con
           ring.load(wp + (size_t)(nc * Cfg::KB + kb) * Cfg::PROJ_CHUNK_BYTES, Cfg::PROJ_CHUNK_BYTES);
     }
   } else if (warp == 9) {
-    // ======================= issuer: all tcgen05.mma =======================
-    if (lane == 0) {
+    // ======================= issuer: all tcgen05.mma (warp-uniform; one elected lane issues) =======================
+    {
       Ring ring{smem_u32(smem + Cfg::S_RING), smem_u32(&ms.bar_full[0]), smem_u32(&ms.bar_empty[0]), Cfg::STAGES, 0};
       constexpr uint32_t idesc_qkv = make_idesc_bf16(128, Cfg::QKV_N);
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128);
       constexpr uint32_t idesc_pv = make_idesc_bf16(128, HD, false, true);
       constexpr uint32_t idesc_proj = make_idesc_bf16(128, Cfg::NCH);
-      mbar_wait(smem_u32(&ms.bar_xn), 0);
-      tc_fence_after();
-      for (int h = 0; h < Cfg::NH; ++h) {
-        const uint32_t ph = h & 1;
-        if (h > 0) { mbar_wait(smem_u32(&ms.bar_o_full), ph ^ 1); tc_fence_after(); }  // PV(h-1) done: S/P columns reusable
-        // --- D_qkv[128 x 3HD] = Xn * Wqkv_h^T ---
+      const uint32_t ring_base = smem_u32(smem + Cfg::S_RING);
+      const uint64_t a_desc0 = kmajor_desc<128>(sX), b_desc0 = kmajor_desc<128>(ring_base);   // address field += bytes >> 4
+      auto issue_qkv = [&]() {      // D_qkv[128 x 3HD] = Xn * Wqkv_h^T for the next head in the weight stream
         for (int kb = 0; kb < Cfg::KB; ++kb) {
           const uint32_t wst = ring.acquire();
           constexpr int KS = (C >= 64) ? 4 : C / 16;
+          const uint64_t ad = a_desc0 + (uint64_t)(kb * 1024), bd = b_desc0 + (uint64_t)((wst - ring_base) >> 4);
+          if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < KS; ++ks) {
-            const uint64_t ad = kmajor_desc<128>(sX + kb * 16384 + ks * 32);
-            const uint64_t bd = kmajor_desc<128>(wst + ks * 32);
-            umma_ss(tb + Cfg::T_WORK, ad, bd, idesc_qkv, (kb | ks) != 0);
+            for (int ks = 0; ks < KS; ++ks) umma_ss(tb + Cfg::T_QKV, ad + 2 * ks, bd + 2 * ks, idesc_qkv, (kb | ks) != 0);
           }
+          __syncwarp();
           ring.release();
         }
-        umma_commit(smem_u32(&ms.bar_qkv_full));
+        if (elect_one()) umma_commit(smem_u32(&ms.bar_qkv_full));
+        __syncwarp();
+      };
+      mbar_wait(smem_u32(&ms.bar_xn), 0);
+      tc_fence_after();
+      if (Cfg::PIPE) issue_qkv();
+      for (int h = 0; h < Cfg::NH; ++h) {
+        const uint32_t ph = h & 1;
+        if (!Cfg::PIPE) {
+          if (h > 0) { mbar_wait(smem_u32(&ms.bar_o_full), ph ^ 1); tc_fence_after(); }  // PV(h-1) done: S/P columns reusable
+          issue_qkv();
+        }
         // --- S[128 x 128] = Q_h K_h^T (block-diagonal 64x64 halves are the two windows) ---
         mbar_wait(smem_u32(&ms.bar_qkv_staged), ph);
         tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < HD / 16; ++ks) {
-          const uint64_t ad = kmajor_desc<Cfg::SWH>(sQ + ks * 32);
-          const uint64_t bd = kmajor_desc<Cfg::SWH>(sK + ks * 32);
-          umma_ss(tb + Cfg::T_WORK, ad, bd, idesc_s, ks != 0);
+          for (int ks = 0; ks < HD / 16; ++ks) {
+            const uint64_t ad = kmajor_desc<Cfg::SWH>(sQ + ks * 32);
+            const uint64_t bd = kmajor_desc<Cfg::SWH>(sK + ks * 32);
+            umma_ss(tb + Cfg::T_WORK, ad, bd, idesc_s, ks != 0);
+          }
+          umma_commit(smem_u32(&ms.bar_s_full));
         }
-        umma_commit(smem_u32(&ms.bar_s_full));
+        __syncwarp();
+        // QKV GEMM of the next head runs while the workers do this head's softmax (D_qkv(h) was drained before qkv_staged)
+        if (Cfg::PIPE && h + 1 < Cfg::NH) issue_qkv();
         // --- D_o[128 x HD] = P[128 x 128 keys] (TMEM, bf16) * V_h (MN-major tile) ---
         mbar_wait(smem_u32(&ms.bar_p_ready), ph);
         tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t bd = mnmajor_desc<Cfg::SWH>(sV + ks * 16 * Cfg::SWH, 8 * Cfg::SWH);
-          umma_ts(tb + Cfg::T_DO, tb + Cfg::T_WORK + ks * 8, bd, idesc_pv, ks != 0);
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t bd = mnmajor_desc<Cfg::SWH>(sV + ks * 16 * Cfg::SWH, 8 * Cfg::SWH);
+            umma_ts(tb + Cfg::T_DO, tb + Cfg::T_WORK + ks * 8, bd, idesc_pv, ks != 0);
+          }
+          umma_commit(smem_u32(&ms.bar_o_full));
         }
-        umma_commit(smem_u32(&ms.bar_o_full));
+        __syncwarp();
       }
       // --- output projection: D_out[128 x C] = O_all (TMEM) * Wp^T, N chunks of NCH ---
       mbar_wait(smem_u32(&ms.bar_oall), 0);
@@ -161,14 +181,17 @@ __global__ void __launch_bounds__(kThreads8, (C <= 128) ? 2 : 1) wmsa_kernel(con
         for (int kb = 0; kb < Cfg::KB; ++kb) {
           const uint32_t wst = ring.acquire();
           constexpr int KS = (C >= 64) ? 4 : C / 16;
+          const uint64_t bd = b_desc0 + (uint64_t)((wst - ring_base) >> 4);
+          if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < KS; ++ks) {
-            const uint64_t bd = kmajor_desc<128>(wst + ks * 32);
-            umma_ts(tb + Cfg::T_WORK + buf * 128, tb + Cfg::T_OALL + kb * 32 + ks * 8, bd, idesc_proj, (kb | ks) != 0);
+            for (int ks = 0; ks < KS; ++ks)
+              umma_ts(tb + Cfg::T_WORK + buf * 128, tb + Cfg::T_OALL + kb * 32 + ks * 8, bd + 2 * ks, idesc_proj, (kb | ks) != 0);
           }
+          __syncwarp();
           ring.release();
         }
-        umma_commit(smem_u32(&ms.bar_d_full[buf]));
+        if (elect_one()) umma_commit(smem_u32(&ms.bar_d_full[buf]));
+        __syncwarp();
       }
     }
   } else {
@@ -224,6 +247,8 @@ __global__ void __launch_bounds__(kThreads8, (C <= 128) ? 2 : 1) wmsa_kernel(con
     const int rp1 = (((r1 & 63) >> 3) + 7) * 15 + (r1 & 7) + 7;
     constexpr int NBH = HD / 8;                      // 8-column blocks per head slice (4 or 2)
 
+    LW_TRACE_STMT(const bool trw = (a.dbg & 16) && blockIdx.x == 0 && tid == 0 && a.trace != nullptr; int tw = 0;)
+    LW_TRACE_STMT(if (trw) a.trace[tw++] = clock64();)
     for (int h = 0; h < Cfg::NH; ++h) {
       const uint32_t ph = h & 1;
       // per-head tables -> smem (readers of the previous head are done: they arrived on p_ready / qkv_staged)
@@ -233,12 +258,13 @@ __global__ void __launch_bounds__(kThreads8, (C <= 128) ? 2 : 1) wmsa_kernel(con
       // ---- QKV epilogue: + bias -> bf16 -> stmatrix into the Q,K (K-major) and V (row-major = MN-major B) tiles ----
       mbar_wait(smem_u32(&ms.bar_qkv_full), ph);
       tc_fence_after();
+      LW_TRACE_STMT(if (trw && h < 4) a.trace[tw++] = clock64();)
       {
         uint32_t v[3][4 * NBH];
 #pragma unroll
         for (int part = 0; part < 3; ++part) {
-          if (NBH == 4) tmem_ld_16x256b_x4(tb + tl + Cfg::T_WORK + part * HD, v[part]);
-          else tmem_ld_16x256b_x2(tb + tl + Cfg::T_WORK + part * HD, v[part]);
+          if (NBH == 4) tmem_ld_16x256b_x4(tb + tl + Cfg::T_QKV + part * HD, v[part]);
+          else tmem_ld_16x256b_x2(tb + tl + Cfg::T_QKV + part * HD, v[part]);
         }
         tmem_wait_ld();
         const int m = lane >> 3, rr = lane & 7;
@@ -262,10 +288,12 @@ __global__ void __launch_bounds__(kThreads8, (C <= 128) ? 2 : 1) wmsa_kernel(con
       fence_async_smem();
       tc_fence_before();
       mbar_arrive(smem_u32(&ms.bar_qkv_staged));
+      LW_TRACE_STMT(if (trw && h < 4) a.trace[tw++] = clock64();)
 
       // ---- softmax over the 64 keys of this warp's 16 rows; a row lives in the 4 threads of a quad ----
       mbar_wait(smem_u32(&ms.bar_s_full), ph);
       tc_fence_after();
+      LW_TRACE_STMT(if (trw && h < 4) a.trace[tw++] = clock64();)
       float sum0, sum1;
       {
         uint32_t v[32];
@@ -336,10 +364,12 @@ __global__ void __launch_bounds__(kThreads8, (C <= 128) ? 2 : 1) wmsa_kernel(con
       }
       tc_fence_before();
       mbar_arrive(smem_u32(&ms.bar_p_ready));
+      LW_TRACE_STMT(if (trw && h < 4) a.trace[tw++] = clock64();)
 
       // ---- O epilogue: normalise, park as bf16 A operand of the projection ----
       mbar_wait(smem_u32(&ms.bar_o_full), ph);
       tc_fence_after();
+      LW_TRACE_STMT(if (trw && h < 4) a.trace[tw++] = clock64();)
       {
         uint32_t v[4 * NBH];
         if (NBH == 4) tmem_ld_16x256b_x4(tb + tl + Cfg::T_DO, v); else tmem_ld_16x256b_x2(tb + tl + Cfg::T_DO, v);
@@ -356,8 +386,10 @@ __global__ void __launch_bounds__(kThreads8, (C <= 128) ? 2 : 1) wmsa_kernel(con
         tmem_wait_st();
       }
       tc_fence_before();
+      LW_TRACE_STMT(if (trw && h < 4) a.trace[tw++] = clock64();)
     }
     mbar_arrive(smem_u32(&ms.bar_oall));
+    LW_TRACE_STMT(if (trw) a.trace[tw++] = clock64();)
 
     // ---- projection epilogue: + bias -> bf16 -> staging tile (the A operand / Q,K,V tiles are dead now) ->
     // coalesced scatter to the (un-rolled) token positions with the shortcut added on the way ----
@@ -393,7 +425,9 @@ __global__ void __launch_bounds__(kThreads8, (C <= 128) ? 2 : 1) wmsa_kernel(con
       worker_bar8();
       store_staged_rows(stage_s, PITCH, NCH_LOG2, ms.row_tok, outp, resid, (size_t)C, nc * Cfg::NCH, tid, kWorkers8);
       worker_bar8();
+      LW_TRACE_STMT(if (trw) a.trace[tw++] = clock64();)
     }
+    LW_TRACE_STMT(if (trw) a.trace[tw++] = -1;)
   }
   // ---------------- teardown ----------------
   tc_fence_before();
