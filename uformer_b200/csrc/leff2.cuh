@@ -115,9 +115,11 @@ __global__ void __launch_bounds__(kL2Threads, 1) leff2_kernel(const AStreamArgs 
     }
   } else {
     // ============================== workers ==============================
-    const int v = tid & 7;               // channel octet inside the 64-channel slice
-    const int cx = (tid >> 3) & 15;      // tile column
-    const int hf = tid >> 7;             // row half: output rows hf*4 .. hf*4+3
+    // one warp per channel octet: the 3x3 taps of the octet are warp-uniform (broadcast LDS at the point of
+    // use, no tap registers); the 32 lanes are 16 tile columns x 2 row halves.
+    const int v = warp;                  // channel octet inside the 64-channel slice
+    const int cx = lane & 15;            // tile column
+    const int hf = lane >> 4;            // row half: output rows hf*4 .. hf*4+3
     const bf16* __restrict__ src = a.src + (size_t)b * a.H * a.W * a.K;
 
     // Per-thread prefetch descriptors (independent of the slice): up to 6 halo vectors + 1 tap vector.
@@ -132,7 +134,7 @@ __global__ void __launch_bounds__(kL2Threads, 1) leff2_kernel(const AStreamArgs 
       const int y = y0 - 1 + t / 18, x = x0 - 1 + t % 18;
       const bool in = (idx < Cfg::HALO_TOK * 8);
       const bool ok = in && (y >= 0) && (y < a.H) && (x >= 0) && (x < a.W);
-      pf_soff[i] = in ? (uint32_t)(t * 128 + vv * 16) : 0xffffffffu;
+      pf_soff[i] = in ? (uint32_t)(t * 128 + ((vv ^ (t & 7)) * 16)) : 0xffffffffu;   // 16 B chunk XOR-swizzled by token
       pf_goff[i] = ok ? (uint32_t)((y * a.W + x) * a.K + vv * 8) : 0xffffffffu;
     }
     // taps: 10 rows (9 taps + bias) x 64 fp32 = 160 16-byte vectors, one per thread for tid < 160
@@ -165,15 +167,8 @@ __global__ void __launch_bounds__(kL2Threads, 1) leff2_kernel(const AStreamArgs 
       LW_TRACE_STMT(if (trw && kb < 6) a.trace[tw++] = clock64();)
       const uint32_t sH = halo0 + ab * 23552;
       const uint32_t sW = wd0 + ab * 2560;
-      // taps of this thread's 8 channels -> registers (as fp32 pairs)
-      f2 w[9][4], acc[4][4];
-#pragma unroll
-      for (int tap = 0; tap < 9; ++tap) {
-        const float4 w0 = lds128f(sW + (tap * 64 + v * 8) * 4);
-        const float4 w1 = lds128f(sW + (tap * 64 + v * 8 + 4) * 4);
-        w[tap][0] = f2_pack(w0.x, w0.y); w[tap][1] = f2_pack(w0.z, w0.w);
-        w[tap][2] = f2_pack(w1.x, w1.y); w[tap][3] = f2_pack(w1.z, w1.w);
-      }
+      // accumulators start at the conv bias of this octet
+      f2 acc[4][4];
       {
         const float4 b0 = lds128f(sW + (9 * 64 + v * 8) * 4);
         const float4 b1 = lds128f(sW + (9 * 64 + v * 8 + 4) * 4);
@@ -183,23 +178,28 @@ __global__ void __launch_bounds__(kL2Threads, 1) leff2_kernel(const AStreamArgs 
           acc[o][2] = f2_pack(b1.x, b1.y); acc[o][3] = f2_pack(b1.z, b1.w);
         }
       }
-      LW_TRACE_STMT(if (trw && kb < 6) a.trace[tw++] = clock64();)
-      // slide down the column: halo rows hf*4 + r, r = 0..5 ; halo row r feeds output row o = r - ky
+      // column by column (dx): pull the 6 halo rows of that column into registers once, then apply the three
+      // taps (ky) that touch them; halo row r feeds output row o = r - ky.
 #pragma unroll
-      for (int r = 0; r < 6; ++r) {
+      for (int dx = 0; dx < 3; ++dx) {
+        f2 h[6][4];
 #pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
-          const uint4 raw = lds128(sH + ((hf * 4 + r) * 18 + cx + dx) * 128 + v * 16);
-          const f2 h0 = bf2_to_f2(raw.x), h1 = bf2_to_f2(raw.y), h2 = bf2_to_f2(raw.z), h3 = bf2_to_f2(raw.w);
+        for (int r = 0; r < 6; ++r) {
+          const int t = (hf * 4 + r) * 18 + cx + dx;
+          const uint4 raw = lds128(sH + t * 128 + ((v ^ (t & 7)) * 16));
+          h[r][0] = bf2_to_f2(raw.x); h[r][1] = bf2_to_f2(raw.y); h[r][2] = bf2_to_f2(raw.z); h[r][3] = bf2_to_f2(raw.w);
+        }
 #pragma unroll
-          for (int ky = 0; ky < 3; ++ky) {
-            const int o = r - ky;
-            if (o >= 0 && o < 4) {
-              acc[o][0] = f2_fma(h0, w[ky * 3 + dx][0], acc[o][0]);
-              acc[o][1] = f2_fma(h1, w[ky * 3 + dx][1], acc[o][1]);
-              acc[o][2] = f2_fma(h2, w[ky * 3 + dx][2], acc[o][2]);
-              acc[o][3] = f2_fma(h3, w[ky * 3 + dx][3], acc[o][3]);
-            }
+        for (int ky = 0; ky < 3; ++ky) {
+          const float4 w0 = lds128f(sW + ((ky * 3 + dx) * 64 + v * 8) * 4);        // warp-uniform address: broadcast
+          const float4 w1 = lds128f(sW + ((ky * 3 + dx) * 64 + v * 8 + 4) * 4);
+          const f2 wa = f2_pack(w0.x, w0.y), wb = f2_pack(w0.z, w0.w), wc = f2_pack(w1.x, w1.y), wd = f2_pack(w1.z, w1.w);
+#pragma unroll
+          for (int o = 0; o < 4; ++o) {
+            acc[o][0] = f2_fma(h[o + ky][0], wa, acc[o][0]);
+            acc[o][1] = f2_fma(h[o + ky][1], wb, acc[o][1]);
+            acc[o][2] = f2_fma(h[o + ky][2], wc, acc[o][2]);
+            acc[o][3] = f2_fma(h[o + ky][3], wd, acc[o][3]);
           }
         }
       }
@@ -211,10 +211,10 @@ __global__ void __launch_bounds__(kL2Threads, 1) leff2_kernel(const AStreamArgs 
 #pragma unroll
       for (int o = 0; o < 4; ++o) {
         uint4 pk;
-        pk.x = f2_to_bf2(gelu2(acc[o][0]));
-        pk.y = f2_to_bf2(gelu2(acc[o][1]));
-        pk.z = f2_to_bf2(gelu2(acc[o][2]));
-        pk.w = f2_to_bf2(gelu2(acc[o][3]));
+        pk.x = f2_to_bf2(gelu2h(acc[o][0]));
+        pk.y = f2_to_bf2(gelu2h(acc[o][1]));
+        pk.z = f2_to_bf2(gelu2h(acc[o][2]));
+        pk.w = f2_to_bf2(gelu2h(acc[o][3]));
         const int rr = (hf * 4 + o) * 16 + cx;
         sts128(sA + swz<128>(rr, v * 16), pk);
       }
