@@ -6,6 +6,7 @@
 #include "wmsa.cuh"
 #include "leff.cuh"
 #include "leff2.cuh"
+#include "down.cuh"
 #include "proj.cuh"
 
 using namespace lw;
@@ -142,15 +143,6 @@ extern "C" int lw_upsample_fwd(const lw_up_args* p, lw_stream_t stream) {
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int PROD>
-static int launch_astream(const AStreamArgs& a, int tiles, cudaStream_t st) {
-  static_assert(AStreamCfg::SMEM_BYTES <= 232448, "smem budget");
-  LW_TRY(cudaFuncSetAttribute(astream_kernel<PROD>, cudaFuncAttributeMaxDynamicSharedMemorySize, AStreamCfg::SMEM_BYTES));
-  astream_kernel<PROD><<<tiles, kThreads, AStreamCfg::SMEM_BYTES, st>>>(a, pow2_cols(a.N));
-  LW_TRY(cudaGetLastError());
-  return LW_OK;
-}
-
 extern "C" int lw_leff2_fwd(const lw_leff2_args* p, lw_stream_t stream) {
   if (!p || !p->h1 || !p->out || !p->wd || !p->bd || !p->w2_img || !p->b2) return LW_ERR_NULL;
   if (p->B <= 0 || p->H <= 0 || p->W < 8 || p->hidden % 64 || p->C % 16 || p->C > 512) return LW_ERR_BAD_SHAPE;
@@ -184,15 +176,19 @@ extern "C" int lw_downsample_fwd(const lw_down_args* p, lw_stream_t stream) {
   a.w_img = reinterpret_cast<const uint8_t*>(p->w_img); a.N = p->Cout; a.nch = p->Cout < 128 ? p->Cout : 128;
   a.bias = p->bias; a.out = reinterpret_cast<bf16*>(p->out);
   const int rows = p->B * (p->H / 2) * (p->W / 2);
-  return launch_astream<1>(a, (rows + 127) / 128, reinterpret_cast<cudaStream_t>(stream));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  LW_TRY(cudaFuncSetAttribute(down_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DownCfg::SMEM_BYTES));
+  down_kernel<<<(rows + 127) / 128, kThreads8, DownCfg::SMEM_BYTES, st>>>(a, pow2_cols(a.N));
+  LW_TRY(cudaGetLastError());
+  return LW_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
 extern "C" int lw_input_proj_fwd(const float* img, const float* w, const float* b, void* tokens, int32_t B, int32_t Cin,
                                  int32_t H, int32_t W, int32_t E, lw_stream_t stream) {
   if (!img || !w || !b || !tokens) return LW_ERR_NULL;
-  if (B <= 0 || H <= 0 || W <= 0 || E % 8 || E > 64 || Cin < 1 || Cin > 4) return LW_ERR_BAD_SHAPE;
-  const long long npix = (long long)B * H * W;
+  if (B <= 0 || H <= 0 || W <= 0 || (W & 1) || E % 8 || E > 64 || Cin < 1 || Cin > 4) return LW_ERR_BAD_SHAPE;
+  const long long npix = (long long)B * H * (W / 2);     // one thread per horizontal pixel pair
   const int blocks = (int)((npix + 127) / 128);
   input_proj_kernel<<<blocks, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(img, w, b, reinterpret_cast<bf16*>(tokens), B, Cin, H, W, E);
   LW_TRY(cudaGetLastError());
@@ -202,10 +198,10 @@ extern "C" int lw_input_proj_fwd(const float* img, const float* w, const float* 
 extern "C" int lw_output_proj_fwd(const void* tokens, const float* w, const float* b, const float* img, float* out, int32_t B,
                                   int32_t Cin, int32_t H, int32_t W, int32_t Cout, lw_stream_t stream) {
   if (!tokens || !w || !b || !out) return LW_ERR_NULL;
-  if (B <= 0 || H <= 0 || W <= 0 || Cin % 8 || Cin > 128 || Cout < 1 || Cout > 4) return LW_ERR_BAD_SHAPE;
-  const long long npix = (long long)B * H * W;
+  if (B <= 0 || H <= 0 || W <= 0 || (W & 1) || Cin % 8 || Cin > 128 || Cout < 1 || Cout > 4) return LW_ERR_BAD_SHAPE;
+  const long long npix = (long long)B * H * (W / 2);     // one thread per horizontal pixel pair
   const int blocks = (int)((npix + 127) / 128);
-  const size_t smem = (size_t)Cout * 9 * Cin * sizeof(float);
+  const size_t smem = (size_t)9 * Cin * 4 * sizeof(float);
   output_proj_kernel<<<blocks, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const bf16*>(tokens), w, b, img, out, B, Cin, H,
                                                                                     W, Cout);
   LW_TRY(cudaGetLastError());
