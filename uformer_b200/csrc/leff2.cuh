@@ -211,10 +211,10 @@ __global__ void __launch_bounds__(kL2Threads, 1) leff2_kernel(const AStreamArgs 
 #pragma unroll
       for (int o = 0; o < 4; ++o) {
         uint4 pk;
-        pk.x = f2_to_bf2(gelu2h(acc[o][0]));
-        pk.y = f2_to_bf2(gelu2h(acc[o][1]));
-        pk.z = f2_to_bf2(gelu2h(acc[o][2]));
-        pk.w = f2_to_bf2(gelu2h(acc[o][3]));
+        pk.x = f2_to_bf2(gelu2(acc[o][0]));
+        pk.y = f2_to_bf2(gelu2(acc[o][1]));
+        pk.z = f2_to_bf2(gelu2(acc[o][2]));
+        pk.w = f2_to_bf2(gelu2(acc[o][3]));
         const int rr = (hf * 4 + o) * 16 + cx;
         sts128(sA + swz<128>(rr, v * 16), pk);
       }

@@ -220,8 +220,8 @@ __device__ __forceinline__ void frag_bias_act_pack(const uint32_t* v, const f2* 
   for (int i = 0; i < NB; ++i) {
     const f2 x0 = f2_add(f2_pack(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1])), bb[i]);
     const f2 x1 = f2_add(f2_pack(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])), bb[i]);
-    pk[2 * i] = f2_to_bf2(GELU ? gelu2h(x0) : x0);
-    pk[2 * i + 1] = f2_to_bf2(GELU ? gelu2h(x1) : x1);
+    pk[2 * i] = f2_to_bf2(GELU ? gelu2(x0) : x0);
+    pk[2 * i + 1] = f2_to_bf2(GELU ? gelu2(x1) : x1);
   }
 }
 
