@@ -14,5 +14,9 @@ x = torch.randn(B, H * H, C, device=dev).to(torch.bfloat16)
 with torch.no_grad():
     for _ in range(reps):
         y = blk(x)
-torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()          # ncu --profile-from-start off: only this block forward is profiled
+    y = blk(x)
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
 print("ok", float(y.float().abs().mean()))
