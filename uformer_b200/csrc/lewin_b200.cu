@@ -43,6 +43,17 @@ extern "C" int lw_nch_ares(int K, int n_total) {
   return n_total < cap ? n_total : cap;
 }
 
+static int sm_count() {
+  static thread_local int cached_dev = -1, cached = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev != cached_dev) {
+    cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
+    cached_dev = dev;
+  }
+  return cached > 0 ? cached : 148;
+}
+
 static int pow2_cols(int n) {
   int c = 32;
   while (c < n) c <<= 1;
@@ -161,8 +172,11 @@ extern "C" int lw_leff2_fwd(const lw_leff2_args* p, lw_stream_t stream) {
   a.tiles_x = (p->W + 15) / 16;
   const int tiles = a.tiles_x * (p->H / 8) * p->B;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if ((long long)p->B * p->H * p->W * p->hidden >= (1ll << 32)) return LW_ERR_BAD_SHAPE;   // 32-bit element offsets in the halo prefetch
+  const int nbuf_d = (2 * a.N <= 512) ? 2 : 1;                 // double-buffer the TMEM accumulator when it fits
   LW_TRY(cudaFuncSetAttribute(leff2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Leff2Cfg::SMEM_BYTES));
-  leff2_kernel<<<tiles, kL2Threads, Leff2Cfg::SMEM_BYTES, st>>>(a, pow2_cols(a.N));
+  const int grid = tiles < sm_count() ? tiles : sm_count();    // persistent: one CTA per SM
+  leff2_kernel<<<grid, kL2Threads, Leff2Cfg::SMEM_BYTES, st>>>(a, pow2_cols(nbuf_d * a.N), tiles, nbuf_d);
   LW_TRY(cudaGetLastError());
   return LW_OK;
 }

@@ -235,34 +235,52 @@ __device__ __forceinline__ uint4 add_bf16x8(const uint4& a, const uint4& b) {
 }
 // copy a staged tile to global rows with 256 threads.  row_tok (smem) gives the destination row of each tile
 // row (-1: skip).  All shared/global loads of a thread are issued before its first store (latency overlap).
-template <int VSHIFT>   // log2(16-byte vectors per row) = log2(ncols) - 3
+template <int VSHIFT, int NT = 256>   // log2(16-byte vectors per row) = log2(ncols) - 3 ; NT cooperating threads
 __device__ __forceinline__ void store_staged_rows_t(uint32_t stage_s, int pitch, uint32_t row_tok_s,
                                                     bf16* __restrict__ out, const bf16* __restrict__ resid,
                                                     size_t row_stride, int col0, int tid) {
-  constexpr int ITER = ((128 << VSHIFT) + 255) / 256;
-  uint4 v[ITER], rv[ITER];
-  size_t g[ITER];
-  int tok[ITER];
+  constexpr int TOTAL = 128 << VSHIFT;
+  constexpr int ITER_ALL = (TOTAL + NT - 1) / NT;
+  constexpr int CAP = (NT == 128) ? 4 : 8;                    // vectors in flight per pass (register budget)
+  constexpr int ITER = ITER_ALL > CAP ? CAP : ITER_ALL;
+#pragma unroll 1
+  for (int p0 = 0; p0 < ITER_ALL; p0 += ITER) {
+    uint4 v[ITER], rv[ITER];
+    size_t g[ITER];
+    int tok[ITER];
 #pragma unroll
-  for (int k = 0; k < ITER; ++k) {
-    const int i = tid + k * 256;
-    const int row = i >> VSHIFT, vec = i & ((1 << VSHIFT) - 1);
-    const bool in = (128 << VSHIFT) >= 256 || i < (128 << VSHIFT);
-    int t;
-    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(t) : "r"(row_tok_s + (in ? row : 0) * 4));
-    tok[k] = in ? t : -1;
-    v[k] = lds128(stage_s + (in ? row : 0) * pitch + vec * 16);
-    g[k] = (size_t)(tok[k] < 0 ? 0 : tok[k]) * row_stride + col0 + vec * 8;
+    for (int k = 0; k < ITER; ++k) {
+      const int i = tid + (p0 + k) * NT;
+      const int row = i >> VSHIFT, vec = i & ((1 << VSHIFT) - 1);
+      const bool in = i < TOTAL;
+      int t;
+      asm volatile("ld.shared.s32 %0, [%1];" : "=r"(t) : "r"(row_tok_s + (in ? row : 0) * 4));
+      tok[k] = in ? t : -1;
+      v[k] = lds128(stage_s + (in ? row : 0) * pitch + vec * 16);
+      g[k] = (size_t)(tok[k] < 0 ? 0 : tok[k]) * row_stride + col0 + vec * 8;
+    }
+    if (resid != nullptr) {
+#pragma unroll
+      for (int k = 0; k < ITER; ++k) rv[k] = (tok[k] >= 0) ? __ldg(reinterpret_cast<const uint4*>(resid + g[k])) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int k = 0; k < ITER; ++k) v[k] = add_bf16x8(v[k], rv[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < ITER; ++k)
+      if (tok[k] >= 0) *reinterpret_cast<uint4*>(out + g[k]) = v[k];
   }
-  if (resid != nullptr) {
-#pragma unroll
-    for (int k = 0; k < ITER; ++k) rv[k] = (tok[k] >= 0) ? __ldg(reinterpret_cast<const uint4*>(resid + g[k])) : make_uint4(0, 0, 0, 0);
-#pragma unroll
-    for (int k = 0; k < ITER; ++k) v[k] = add_bf16x8(v[k], rv[k]);
+}
+// 128-thread variant (dedicated epilogue warps of the persistent kernels)
+__device__ __forceinline__ void store_staged_rows128(uint32_t stage_s, int pitch, int ncols_log2, const int* row_tok,
+                                                     bf16* __restrict__ out, const bf16* __restrict__ resid,
+                                                     size_t row_stride, int col0, int tid) {
+  const uint32_t rts = smem_u32(row_tok);
+  switch (ncols_log2) {
+    case 7: store_staged_rows_t<4, 128>(stage_s, pitch, rts, out, resid, row_stride, col0, tid); break;
+    case 6: store_staged_rows_t<3, 128>(stage_s, pitch, rts, out, resid, row_stride, col0, tid); break;
+    case 5: store_staged_rows_t<2, 128>(stage_s, pitch, rts, out, resid, row_stride, col0, tid); break;
+    default: store_staged_rows_t<1, 128>(stage_s, pitch, rts, out, resid, row_stride, col0, tid); break;
   }
-#pragma unroll
-  for (int k = 0; k < ITER; ++k)
-    if (tok[k] >= 0) *reinterpret_cast<uint4*>(out + g[k]) = v[k];
 }
 __device__ __forceinline__ void store_staged_rows(uint32_t stage_s, int pitch, int ncols_log2, const int* row_tok,
                                                   bf16* __restrict__ out, const bf16* __restrict__ resid,
