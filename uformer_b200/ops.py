@@ -72,7 +72,7 @@ def wmsa(x: Tensor, p: dict, *, H: int, W: int, shift: int, windowed: bool, resi
     a.n_windows, a.H, a.W, a.C, a.head_dim = n_windows, H, W, Cc, p["head_dim"]
     a.shift, a.windowed, a.ln_eps = shift, int(windowed), p.get("ln_eps", 1e-5)
     ntok = n_windows * 64
-    _launch(f"wmsa_C{Cc}", 2.0 * ntok * (4 * Cc * Cc + 128 * Cc), lambda: _lib.load().lw_wmsa_fwd(C.byref(a), _stream()), "lw_wmsa_fwd")
+    _launch(f"wmsa_C{Cc}_T{ntok}", 2.0 * ntok * (4 * Cc * Cc + 128 * Cc), lambda: _lib.load().lw_wmsa_fwd(C.byref(a), _stream()), "lw_wmsa_fwd")
     return out
 
 
@@ -88,14 +88,14 @@ def leff(x: Tensor, p: dict, *, B: int, H: int, W: int, resid: Tensor | None, ou
     a.w1_img, a.b1 = _ptr(p["w1_img"]), _ptr(p["b1"])
     a.n_tokens, a.C, a.hidden, a.ln_eps = n_tokens, Cc, hidden, p.get("ln_eps", 1e-5)
     lib = _lib.load()
-    _launch(f"leff1_C{Cc}", 2.0 * n_tokens * Cc * hidden, lambda: lib.lw_leff1_fwd(C.byref(a), _stream()), "lw_leff1_fwd")
+    _launch(f"leff1_C{Cc}_T{n_tokens}", 2.0 * n_tokens * Cc * hidden, lambda: lib.lw_leff1_fwd(C.byref(a), _stream()), "lw_leff1_fwd")
     if out is None:
         out = torch.empty_like(x)
     b = _lib.Leff2Args()
     b.h1, b.out, b.resid = _ptr(h1), _ptr(out), _ptr(resid)
     b.wd, b.bd, b.w2_img, b.b2 = _ptr(p["wd"]), _ptr(p["bd"]), _ptr(p["w2_img"]), _ptr(p["b2"])
     b.B, b.H, b.W, b.C, b.hidden = B, H, W, Cc, hidden
-    _launch(f"leff2_C{Cc}", 2.0 * n_tokens * (hidden * Cc + 9 * hidden), lambda: lib.lw_leff2_fwd(C.byref(b), _stream()), "lw_leff2_fwd")
+    _launch(f"leff2_C{Cc}_T{n_tokens}", 2.0 * n_tokens * (hidden * Cc + 9 * hidden), lambda: lib.lw_leff2_fwd(C.byref(b), _stream()), "lw_leff2_fwd")
     return out
 
 
