@@ -321,7 +321,8 @@ class LeWinTransformerBlock(nn.Module):
         am = m.unsqueeze(2) * m.unsqueeze(1)
         return torch.where(am != 0, torch.full_like(am, -100.0), torch.zeros_like(am))
 
-    def forward(self, x, mask=None):
+    def forward(self, x, mask=None, out=None):
+        """`out` (optional, bf16, same shape as x): write the block output there (used by the stage scheduler)."""
         B, L, C = x.shape
         H = W = int(math.sqrt(L))
         if H * W != L or H % 8 or self.win_size != 8:
@@ -338,8 +339,8 @@ class LeWinTransformerBlock(nn.Module):
         amask = None if mask is None else self.input_mask_to_attn_mask(mask.to(x.device), H, W, 8)
         x1 = ops.wmsa(xb, pa, H=H, W=W, shift=self.shift_size, windowed=False, resid=xb, mask=amask)
         pm = dict(self.mlp.packed(), ln_w=pk["ln2_w"], ln_b=pk["ln2_b"], ln_eps=self.norm2.eps)
-        out = ops.leff(x1, pm, B=B, H=H, W=W, resid=x1)
-        return out if back is None else out.to(back)
+        res = ops.leff(x1, pm, B=B, H=H, W=W, resid=x1, out=out if back is None else None)
+        return res if back is None else res.to(back)
 
     def flops(self):
         H, W = self.input_resolution

@@ -11,12 +11,16 @@ decoder input buffer, the skip is copied once into the right half.
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 import torch.nn as nn
 
 from . import ops
 from .modules import Downsample, LeWinTransformerBlock, Upsample, _no_grad_guard
+
+# working-set budget (MB) for the optional images-outer stage schedule (B200 L2 is 126 MB)
+L2_BUDGET_BYTES = int(os.environ.get("UFORMER_B200_L2_BUDGET_MB", str(1 << 20))) << 20     # default: off (measured slower)
 
 _STAGE_NAMES = ["encoderlayer_0", "encoderlayer_1", "encoderlayer_2", "encoderlayer_3", "conv",
                 "decoderlayer_0", "decoderlayer_1", "decoderlayer_2", "decoderlayer_3"]
@@ -43,9 +47,26 @@ class LeWinStage(nn.Module):
         return f"dim={self.dim}, input_resolution={self.input_resolution}, depth={self.depth}"
 
     def forward(self, x, mask=None):
-        for blk in self.blocks:
-            x = blk(x, mask)
-        return x
+        """Runs the blocks of this stage.  When the stage's per-batch working set (token map, W-MSA output and the
+        4C-wide LeFF hidden map, ~14*L*C bytes per image in bf16) exceeds the L2 budget, the loop order is
+        images-outer / blocks-inner: each sub-batch of images runs through ALL blocks before the next one starts,
+        so x1 / h1 / the next block's input are produced and consumed while still L2-resident and the scratch
+        buffers are re-used at the same addresses (the reference loops blocks-outer, model.py:1054-1060; the
+        result is identical because no op couples images)."""
+        B, L, C = x.shape
+        per_image = 14 * L * C
+        chunk = max(1, min(B, L2_BUDGET_BYTES // per_image))
+        if chunk >= B or mask is not None or x.dtype != torch.bfloat16 or len(self.blocks) == 0:
+            for blk in self.blocks:
+                x = blk(x, mask)
+            return x
+        out = torch.empty_like(x)
+        for i0 in range(0, B, chunk):
+            y = x[i0:i0 + chunk]
+            for bi, blk in enumerate(self.blocks):
+                last = bi == len(self.blocks) - 1
+                y = blk(y, None, out=out[i0:i0 + chunk] if last else None)
+        return out
 
     def flops(self):
         return sum(b.flops() for b in self.blocks)
@@ -177,3 +198,28 @@ class Uformer(nn.Module):
             f += getattr(self, f"encoderlayer_{i}").flops() + getattr(self, f"dowsample_{i}").flops(r // 2 ** i, r // 2 ** i)
             f += getattr(self, f"upsample_{i}").flops(r // 2 ** (4 - i), r // 2 ** (4 - i)) + getattr(self, f"decoderlayer_{i}").flops()
         return f
+
+
+class GraphedForward:
+    """Capture `net(x)` for a fixed input shape into a CUDA graph and replay it: the ~130 native launches of a
+    forward become one graph launch (no Python / ctypes cost on the critical path).  All kernels of this
+    library are capture-safe: they never allocate or synchronise."""
+
+    def __init__(self, net, example: torch.Tensor, warmup: int = 2):
+        self.net = net
+        self.x = example.clone()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s), torch.no_grad():
+            for _ in range(warmup):                       # packs weights, primes the allocator
+                net(self.x)
+        torch.cuda.current_stream().wait_stream(s)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            self.y = net(self.x)
+
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        if x.data_ptr() != self.x.data_ptr():
+            self.x.copy_(x, non_blocking=True)
+        self.graph.replay()
+        return self.y
