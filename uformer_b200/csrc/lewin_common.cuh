@@ -112,6 +112,11 @@ __device__ __forceinline__ f2 f2_mul(f2 a, f2 b) {
 __device__ __forceinline__ f2 bf2_to_f2(uint32_t u) {
   return f2_pack(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
 }
+__device__ __forceinline__ float exp2_approx(float x) {       // x <= 0 in the softmax: single MUFU.EX2
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float tanh_approx(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));

@@ -85,33 +85,34 @@ __global__ void __launch_bounds__(128) output_proj_kernel(const bf16* __restrict
   const int b = (int)(pp / (H * Wp)), t = (int)(pp % (H * Wp)), y = t / Wp, x0 = (t % Wp) * 2;
   const uint32_t sw_s = smem_u32(swo);
   float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
+  // For every kernel row ky the four input columns x0-1 .. x0+2 are held in registers (8 channels at a time); tap
+  // (ky,kx) multiplies column kx for pixel 0 and column kx+1 for pixel 1, so each broadcast weight read feeds both.
 #pragma unroll 1
   for (int ky = 0; ky < 3; ++ky) {
     const int yy = y + ky - 1;
     if (yy < 0 || yy >= H) continue;
+    const bf16* rowp = tok + (((size_t)b * H + yy) * W) * Cin;
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {                      // input column x0-1+c feeds pixel0 with kx=c (c<3) and pixel1 with kx=c-1 (c>0)
-      const int xx = x0 + c - 1;
-      if (xx < 0 || xx >= W) continue;
-      const bf16* row = tok + (((size_t)b * H + yy) * W + xx) * Cin;
-      for (int c0 = 0; c0 < Cin; c0 += 8) {
-        float f[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(row + c0)), f);
-        if (c < 3) {
-          const uint32_t wb = sw_s + (((ky * 3 + c) * Cin + c0) * 4) * 4;
+    for (int c0 = 0; c0 < Cin; c0 += 8) {
+      float f[4][8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 w4 = lds128f(wb + j * 16);
-            a0[0] = fmaf(f[j], w4.x, a0[0]); a0[1] = fmaf(f[j], w4.y, a0[1]); a0[2] = fmaf(f[j], w4.z, a0[2]); a0[3] = fmaf(f[j], w4.w, a0[3]);
-          }
+      for (int c = 0; c < 4; ++c) {
+        const int xx = x0 + c - 1;
+        if (xx >= 0 && xx < W) unpack8(__ldg(reinterpret_cast<const uint4*>(rowp + (size_t)xx * Cin + c0)), f[c]);
+        else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[c][j] = 0.f;
         }
-        if (c > 0) {
-          const uint32_t wb = sw_s + (((ky * 3 + c - 1) * Cin + c0) * 4) * 4;
+      }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 w4 = lds128f(wb + j * 16);
-            a1[0] = fmaf(f[j], w4.x, a1[0]); a1[1] = fmaf(f[j], w4.y, a1[1]); a1[2] = fmaf(f[j], w4.z, a1[2]); a1[3] = fmaf(f[j], w4.w, a1[3]);
-          }
+      for (int kx = 0; kx < 3; ++kx) {
+        const uint32_t wb = sw_s + (((ky * 3 + kx) * Cin + c0) * 4) * 4;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 w4 = lds128f(wb + j * 16);
+          a0[0] = fmaf(f[kx][j], w4.x, a0[0]); a0[1] = fmaf(f[kx][j], w4.y, a0[1]); a0[2] = fmaf(f[kx][j], w4.z, a0[2]);
+          a1[0] = fmaf(f[kx + 1][j], w4.x, a1[0]); a1[1] = fmaf(f[kx + 1][j], w4.y, a1[1]); a1[2] = fmaf(f[kx + 1][j], w4.z, a1[2]);
+          a0[3] = fmaf(f[kx][j], w4.w, a0[3]); a1[3] = fmaf(f[kx + 1][j], w4.w, a1[3]);
         }
       }
     }

@@ -343,8 +343,8 @@ __global__ void __launch_bounds__(kThreads8, (C <= 128) ? 2 : 1) wmsa_kernel(con
         sum0 = 0.f; sum1 = 0.f;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          s0[j] = exp2f(fmaf(s0[j], kLog2e, -ms0)); sum0 += s0[j];
-          s1[j] = exp2f(fmaf(s1[j], kLog2e, -ms1)); sum1 += s1[j];
+          s0[j] = exp2_approx(fmaf(s0[j], kLog2e, -ms0)); sum0 += s0[j];
+          s1[j] = exp2_approx(fmaf(s1[j], kLog2e, -ms1)); sum1 += s1[j];
         }
         sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
         sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
