@@ -151,3 +151,52 @@ def test_window_attention_permutation_property_full_size():
         a = att(x)[perm]
         b = att(x[perm].contiguous())
     assert torch.equal(a, b)
+
+
+def test_graphed_forward_equals_eager():
+    """CUDA-graph replay of the whole forward (uformer_b200.GraphedForward) is bit-identical to eager launches."""
+    import uformer_b200 as U
+    g = load_golden("uformer_t2_128")
+    net, _ = build_module(g)
+    net = net.to(DEV)
+    x = g["x"].to(DEV)
+    with torch.no_grad():
+        eager = net(x).clone()
+    gf = U.GraphedForward(net, x)
+    y1 = gf(x).clone()
+    y2 = gf(x).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(y1, eager) and torch.equal(y2, eager)
+    _check(y1.float().cpu(), g["y"], "graphed uformer_t2_128")
+
+
+def test_upsample_writes_into_concat_buffer():
+    """Skip-concat fusion (model.py:1288): Upsample writes the left half of a wider (B, 4HW, 2*Cout) buffer in place."""
+    import uformer_b200 as U
+    from oracle import lewin_oracle as O
+    from paramgen import randomize_state
+    torch.manual_seed(4)
+    mod = U.Upsample(128, 32).eval()
+    st = randomize_state(mod.state_dict(), 8)
+    mod.load_state_dict(st)
+    mod = mod.to(DEV)
+    x = torch.randn(2, 16 * 16, 128).to(torch.bfloat16)
+    cat = torch.full((2, 32 * 32, 64), 7.0, dtype=torch.bfloat16, device=DEV)
+    with torch.no_grad():
+        mod(x.to(DEV), out=cat)
+    torch.cuda.synchronize()
+    ref = O.upsample(x.float(), st["deconv.0.weight"], st["deconv.0.bias"])
+    _check(cat[:, :, :32].float().cpu(), ref, "upsample into concat")
+    assert torch.all(cat[:, :, 32:] == 7.0)          # right half untouched
+
+
+def test_hardware_probes():
+    """The tcgen05 operand-layout probe (every descriptor variant the kernels rely on) must pass on this GPU."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "cuda", "umma_probe")
+    if not os.path.isfile(exe):
+        pytest.skip("probe binary not built (run __graft_entry__.build())")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120).stdout
+    assert "PROBE OK" in out, out[-2000:]

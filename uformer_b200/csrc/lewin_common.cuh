@@ -1,12 +1,13 @@
-// lewin_common.cuh — CTA organisation shared by the LeWin kernels.
+// lewin_common.cuh — CTA organisation and device helpers shared by the LeWin kernels.
 //
-// Every kernel processes one 128-row tile (128 tokens) per CTA with three roles:
-//   warps 0-3  "workers": 128 threads, thread r owns tile row r == TMEM lane r.  They gather /
-//              normalise the A operand into shared memory and run every epilogue.
-//   warp 4     "producer": lane 0 streams pre-swizzled weight chunk images global -> shared with
-//              cp.async.bulk (UBLKCP) into a ring of 16 KB stages guarded by full/empty mbarriers.
-//              The warp also owns the TMEM allocation.
-//   warp 5     "issuer": lane 0 issues every tcgen05.mma and commits completion to mbarriers.
+// Every GEMM-type kernel processes 128-row tiles (128 tokens) with specialised warps:
+//   worker warps (8)  : thread <-> (TMEM lane quadrant = warp & 3, 16-row group / column half = warp >> 2).
+//                       They gather / normalise / convolve the A operand into shared memory and run the epilogues
+//                       on 16x256b TMEM fragments (stmatrix-staged, coalesced copy-out).
+//   producer warp     : lane 0 streams pre-swizzled weight chunk images global -> shared with cp.async.bulk
+//                       (UBLKCP) into a ring of 16/32 KB stages guarded by full/empty mbarriers; owns the TMEM allocation.
+//   issuer warp       : warp-uniform loop; one elected lane issues tcgen05.mma / tcgen05.commit.
+// The persistent LeFF-2 kernel adds a dedicated epilogue warpgroup (leff2.cuh).
 #pragma once
 #include "umma.cuh"
 
@@ -139,25 +140,7 @@ __device__ __forceinline__ f2 gelu2(f2 x) {
   const f2 hx = f2_mul(x, f2_pack(0.5f, 0.5f));
   return f2_fma(hx, t, hx);
 }
-// Same GELU with ONE MUFU op per pair: tanh.approx.f16x2 (f16 keeps 11 mantissa bits, the same 2^-11 the f32
-// approximation delivers; |q| <= 13.2 is far inside the f16 range).
-__device__ __forceinline__ f2 gelu2h(f2 x) {
-  float a, b;
-  f2_unpack(x, a, b);
-  const f2 xc = f2_pack(fminf(fmaxf(a, -8.f), 8.f), fminf(fmaxf(b, -8.f), 8.f));
-  const f2 x2 = f2_mul(xc, xc);
-  f2 p = f2_fma(x2, f2_pack(-3.72804244e-4f, -3.72804244e-4f), f2_pack(3.71494616e-2f, 3.71494616e-2f));
-  p = f2_fma(x2, p, f2_pack(0.797344279f, 0.797344279f));
-  float qa, qb;
-  f2_unpack(f2_mul(xc, p), qa, qb);
-  uint32_t hq, ht;
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hq) : "f"(qb), "f"(qa));      // {hi = qb, lo = qa}
-  asm("tanh.approx.f16x2 %0, %1;" : "=r"(ht) : "r"(hq));
-  float ta, tb2;
-  asm("{\n\t.reg .f16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(ta), "=f"(tb2) : "r"(ht));
-  const f2 hx = f2_mul(x, f2_pack(0.5f, 0.5f));
-  return f2_fma(hx, f2_pack(ta, tb2), hx);
-}
+// (A tanh.approx.f16x2 variant with one MUFU per pair was measured 2 % slower end to end: conversion overhead.)
 __device__ __forceinline__ float gelu1(float x) {
   const float xc = fminf(fmaxf(x, -8.f), 8.f);
   const float x2 = xc * xc;
