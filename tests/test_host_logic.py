@@ -104,3 +104,21 @@ def test_pack_cache_invalidation():
     with torch.no_grad():
         att.proj.weight.add_(1.0)
     assert att.packed() is not p1
+
+
+def test_pack_roundtrip_property():
+    """hypothesis: pack/unpack is the identity on bf16-representable matrices for every legal (N, K, nch, order)."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=25, deadline=None)
+    @given(nchunks=st.integers(1, 4), nch=st.sampled_from([16, 32, 48, 64, 96, 128, 256]), k=st.sampled_from([16, 32, 64, 96, 128, 320]),
+           order=st.sampled_from(["nk", "kn"]), seed=st.integers(0, 2 ** 16))
+    def run(nchunks, nch, k, order, seed):
+        g = torch.Generator().manual_seed(seed)
+        w = torch.randn(nchunks * nch, k, generator=g).to(torch.bfloat16).float()
+        img = packing.pack_kmajor(w, nch, order)
+        assert torch.equal(packing.unpack_kmajor(img, nchunks * nch, k, nch, order), w)
+        # zero padding of K up to a multiple of 64 really is zero in the image
+        assert img.float().abs().sum().item() == pytest.approx(w.abs().sum().item(), rel=1e-6)
+
+    run()

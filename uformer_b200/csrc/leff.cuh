@@ -173,7 +173,6 @@ __global__ void __launch_bounds__(kThreads8, (K <= 128) ? 2 : 1) ares_kernel(con
     if (!LW_DBG(a, 8)) stage_rows_ln<K, 8>(smem + Cfg::S_X, a.x, ms.row_tok, a.ln_w, a.ln_b, a.ln_eps, nullptr);
     fence_async_smem();
     mbar_arrive(smem_u32(&ms.bar_a_ready));
-    const int half = warp >> 2;
     const uint32_t stage_s = smem_u32(smem + Cfg::S_STAGE);
     if (EPI == 1) {
       // destination base row of every input token: (b, 2y, 2x) in the (B, 2H, 2W) output map
