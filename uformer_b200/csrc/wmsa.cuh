@@ -119,25 +119,8 @@ __global__ void __launch_bounds__(kThreads8, (C <= 128) ? 2 : 1) wmsa_kernel(con
       constexpr uint32_t idesc_proj = make_idesc_bf16(128, Cfg::NCH);
       const uint32_t ring_base = smem_u32(smem + Cfg::S_RING);
       const uint64_t a_desc0 = kmajor_desc<128>(sX), b_desc0 = kmajor_desc<128>(ring_base);   // address field += bytes >> 4
-      auto issue_pv = [&]() {       // D_o[128 x HD] = P[128 x 128 keys] (TMEM, bf16) * V_h (MN-major tile)
-        tc_fence_after();
-        if (elect_one()) {
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            const uint64_t bd = mnmajor_desc<Cfg::SWH>(sV + ks * 16 * Cfg::SWH, 8 * Cfg::SWH);
-            umma_ts(tb + Cfg::T_DO, tb + Cfg::T_WORK + ks * 8, bd, idesc_pv, ks != 0);
-          }
-          umma_commit(smem_u32(&ms.bar_o_full));
-        }
-        __syncwarp();
-      };
-      // D_qkv[128 x 3HD] = Xn * Wqkv_h^T for the next head in the weight stream.  While issuing it (pipelined mode)
-      // the issuer polls p_ready of the current head between k-blocks and slips P·V in as soon as the softmax is
-      // done, so the O epilogue is not held up by the length of the QKV issue loop.
-      auto issue_qkv = [&](int pv_phase /* -1: nothing pending */) -> bool {
-        bool pv_done = (pv_phase < 0);
+      auto issue_qkv = [&]() {      // D_qkv[128 x 3HD] = Xn * Wqkv_h^T for the next head in the weight stream
         for (int kb = 0; kb < Cfg::KB; ++kb) {
-          if (!pv_done && mbar_try_wait(smem_u32(&ms.bar_p_ready), (uint32_t)pv_phase)) { issue_pv(); pv_done = true; }
           const uint32_t wst = ring.acquire();
           constexpr int KS = (C >= 64) ? 4 : C / 16;
           const uint64_t ad = a_desc0 + (uint64_t)(kb * 1024), bd = b_desc0 + (uint64_t)((wst - ring_base) >> 4);
@@ -150,16 +133,15 @@ __global__ void __launch_bounds__(kThreads8, (C <= 128) ? 2 : 1) wmsa_kernel(con
         }
         if (elect_one()) umma_commit(smem_u32(&ms.bar_qkv_full));
         __syncwarp();
-        return pv_done;
       };
       mbar_wait(smem_u32(&ms.bar_xn), 0);
       tc_fence_after();
-      if (Cfg::PIPE) issue_qkv(-1);
+      if (Cfg::PIPE) issue_qkv();
       for (int h = 0; h < Cfg::NH; ++h) {
         const uint32_t ph = h & 1;
         if (!Cfg::PIPE) {
           if (h > 0) { mbar_wait(smem_u32(&ms.bar_o_full), ph ^ 1); tc_fence_after(); }  // PV(h-1) done: S/P columns reusable
-          issue_qkv(-1);
+          issue_qkv();
         }
         // --- S[128 x 128] = Q_h K_h^T (block-diagonal 64x64 halves are the two windows) ---
         mbar_wait(smem_u32(&ms.bar_qkv_staged), ph);
@@ -175,12 +157,19 @@ __global__ void __launch_bounds__(kThreads8, (C <= 128) ? 2 : 1) wmsa_kernel(con
         }
         __syncwarp();
         // QKV GEMM of the next head runs while the workers do this head's softmax (D_qkv(h) was drained before qkv_staged)
-        bool pv_done = false;
-        if (Cfg::PIPE && h + 1 < Cfg::NH) pv_done = issue_qkv((int)ph);
-        if (!pv_done) {
-          mbar_wait(smem_u32(&ms.bar_p_ready), ph);
-          issue_pv();
+        if (Cfg::PIPE && h + 1 < Cfg::NH) issue_qkv();
+        // --- D_o[128 x HD] = P[128 x 128 keys] (TMEM, bf16) * V_h (MN-major tile) ---
+        mbar_wait(smem_u32(&ms.bar_p_ready), ph);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t bd = mnmajor_desc<Cfg::SWH>(sV + ks * 16 * Cfg::SWH, 8 * Cfg::SWH);
+            umma_ts(tb + Cfg::T_DO, tb + Cfg::T_WORK + ks * 8, bd, idesc_pv, ks != 0);
+          }
+          umma_commit(smem_u32(&ms.bar_o_full));
         }
+        __syncwarp();
       }
       // --- output projection: D_out[128 x C] = O_all (TMEM) * Wp^T, N chunks of NCH ---
       mbar_wait(smem_u32(&ms.bar_oall), 0);
