@@ -51,7 +51,7 @@ struct AResCfg {
   static constexpr int S_RING = KB * 16384;
   static constexpr int S_STAGE = S_RING + STAGES * STAGE_BYTES;      // epilogue staging tile: 128 rows x 272 B
   static constexpr int STAGE_PITCH = 272;
-  static constexpr int S_BIAS = S_STAGE + 35840;                     // bias of the whole N range (<= 2048 fp32)
+  static constexpr int S_BIAS = S_STAGE + 36864;                     // (2 halves x 128 rows x 144 B) ; bias of the whole N range (<= 2048 fp32)
   static constexpr int S_MISC = S_BIAS + 8192;
   static constexpr int SMEM_BYTES = S_MISC + 1024 + 1024;
   static constexpr int T_ALLOC = 2 * NCH_MAX;                        // two accumulator buffers
@@ -84,7 +84,7 @@ __device__ __forceinline__ void ares_phase_a(const AResArgs& a, uint32_t tcol, i
   for (int hl = 0; hl < 2; ++hl) {
     uint32_t pk[2 * NB];
     frag_bias_act_pack<NB, EPI == 0>(v[hl], bb, pk);
-    stage_frag<NB>(stage_s, pitch, q * 32 + hl * 16, half * CPH, pk);
+    stage_frag<NB>(stage_s, pitch, q * 32 + hl * 16, 0, pk);       // the column half owns a private staging tile
   }
 }
 
@@ -186,9 +186,14 @@ __global__ void __launch_bounds__(kThreads8, (K <= 128) ? 2 : 1) ares_kernel(con
       }
       worker_bar8();
     }
-    const int sub_cols = a.nch < 128 ? a.nch : 128;          // staged 128 columns at a time
-    int sub_log2 = 4;
-    while ((1 << sub_log2) < sub_cols) ++sub_log2;
+    const int sub_cols = a.nch < 128 ? a.nch : 128;          // 128 accumulator columns per pass: 64 per column half
+    const int grp = warp >> 2;                               // column half == synchronisation group (128 threads)
+    const int cph = sub_cols >> 1;
+    int cph_log2 = 4;
+    while ((1 << cph_log2) < cph) ++cph_log2;
+    const int pitch_g = cph * 2 + 16;
+    const uint32_t stage_g = stage_s + grp * 18432;          // 128 rows x 144 B per half
+    auto group_bar = [](int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 2) : "memory"); };
     LW_TRACE_STMT(const bool trw = (a.dbg & 16) && blockIdx.x == 0 && tid == 0 && a.trace != nullptr; int tw = 512, tw2 = 1024;)
     LW_TRACE_STMT(if (trw) a.trace[tw++] = clock64();)
     for (int nc = 0; nc < NC; ++nc) {
@@ -197,38 +202,36 @@ __global__ void __launch_bounds__(kThreads8, (K <= 128) ? 2 : 1) ares_kernel(con
       tc_fence_after();
       LW_TRACE_STMT(if (trw) a.trace[tw++] = clock64();)
       for (int sc = 0; sc < a.nch; sc += 128) {
-        // ---- phase A: TMEM (16x256b fragments) -> (+bias, GELU) -> bf16 -> stmatrix into the staging tile.
-        // warp (q, half): lanes q*32..+32 as two 16-lane groups, columns half*cph .. +cph of the sub-chunk ----
-        if (sub_cols == 128) ares_phase_a<8, EPI>(a, tb + buf * Cfg::NCH_MAX + sc, nc * a.nch + sc, bias_s, stage_s, Cfg::STAGE_PITCH);
-        else ares_phase_a<4, EPI>(a, tb + buf * Cfg::NCH_MAX + sc, nc * a.nch + sc, bias_s, stage_s, Cfg::STAGE_PITCH);
-        LW_TRACE_STMT(if (trw && nc == 1) a.trace[tw2++] = clock64();)
+        // ---- phase A: TMEM (16x256b fragments) -> (+bias, GELU) -> bf16 -> stmatrix into this column half's private
+        // staging tile.  The two halves (warps 0-3 / 4-7) synchronise only among themselves, so one half's
+        // copy-out overlaps the other half's GELU math. ----
+        if (sub_cols == 128) ares_phase_a<8, EPI>(a, tb + buf * Cfg::NCH_MAX + sc, nc * a.nch + sc, bias_s, stage_g, pitch_g);
+        else ares_phase_a<4, EPI>(a, tb + buf * Cfg::NCH_MAX + sc, nc * a.nch + sc, bias_s, stage_g, pitch_g);
         if (sc + 128 >= a.nch) {            // accumulator fully read: hand the buffer back to the issuer
           tc_fence_before();
           mbar_arrive(smem_u32(&ms.bar_d_empty[buf]));
         }
-        worker_bar8();
-        LW_TRACE_STMT(if (trw && nc == 1) a.trace[tw2++] = clock64();)
-        // ---- phase B: coalesced copy-out ----
+        group_bar(grp);
+        // ---- phase B: coalesced copy-out of this half's columns by its 128 threads ----
         if (!LW_DBG(a, 1)) {
+          const int colg = nc * a.nch + sc + grp * cph;
           if (EPI == 0) {
-            store_staged_rows(stage_s, Cfg::STAGE_PITCH, sub_log2, ms.row_tok, a.out, nullptr, (size_t)a.n_total,
-                              nc * a.nch + sc, tid, kWorkers8);
+            store_staged_rows128(stage_g, pitch_g, cph_log2, ms.row_tok, a.out, nullptr, (size_t)a.n_total, colg, tid & 127);
           } else {
-            const int vshift = sub_log2 - 3;
+            const int vshift = cph_log2 - 3;
             const int total = 128 << vshift;
-            for (int i2 = tid; i2 < total; i2 += kWorkers8) {
+            for (int i2 = (tid & 127); i2 < total; i2 += 128) {
               const int row = i2 >> vshift, vec = i2 & ((1 << vshift) - 1);
               const int obase = ms.row_tok[row];
               if (obase < 0) continue;
-              const int n0 = nc * a.nch + sc + vec * 8;
+              const int n0 = colg + vec * 8;
               const int q = n0 / a.Cout, co = n0 % a.Cout;
               const size_t orow = (size_t)obase + (q >> 1) * (2 * a.W) + (q & 1);
-              *reinterpret_cast<uint4*>(a.out + orow * a.out_stride + co) = lds128(stage_s + row * Cfg::STAGE_PITCH + vec * 16);
+              *reinterpret_cast<uint4*>(a.out + orow * a.out_stride + co) = lds128(stage_g + row * pitch_g + vec * 16);
             }
           }
         }
-        LW_TRACE_STMT(if (trw && nc == 1) a.trace[tw2++] = clock64();)
-        worker_bar8();                      // staging tile free for the next phase A
+        group_bar(grp);                     // this half's staging tile is free for its next phase A
         LW_TRACE_STMT(if (trw) a.trace[tw++] = clock64();)
       }
     }
