@@ -30,3 +30,13 @@ def pytest_collection_modifyitems(config, items):
     for it in items:
         if "gpu" in it.keywords:
             it.add_marker(skip)
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _native_library_built():
+    """The shared library is git-ignored (built in-tree by __graft_entry__.build()); build it if this checkout lacks it."""
+    lib = os.path.join(ROOT, "uformer_b200", "lib", "liblewin_b200.so")
+    if not os.path.isfile(lib):
+        import __graft_entry__
+        __graft_entry__.build()
+    yield
