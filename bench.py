@@ -1,7 +1,10 @@
 #!/usr/bin/env python
 """bench.py — images/sec of the Uformer-B 256x256 forward (BASELINE.json configs[1]) on N B200s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--mode fwd|train]
+
+`--mode train` (not the default; BASELINE configs[2]) times the data-parallel training step instead: batch 8 per GPU,
+native forward + recompute backward + NCCL bucketed gradient all-reduce + native AdamW (uformer_b200.training).
 
 A "step" is one forward of a batch of 32 synthetic 256x256x3 images through the native engine
 (bf16 activations, fp32 accumulate).  Weights: Uformer-B architecture, seeded synthetic init
@@ -162,6 +165,141 @@ def run_reference_arm(args, rank, world):
         "gpu_launches": 0}))
 
 
+TRAIN_GFLOP_PER_IMG = 3 * GFLOP_PER_IMG      # fwd + bwd (2x fwd); the recompute in backward is overhead, not counted
+
+
+def run_reference_train(args, rank):
+    """CPU arm of --mode train: fwd + bwd + AdamW of the oracle port (torch autograd over its library-op formulation)."""
+    if rank != 0:
+        return
+    from oracle import lewin_oracle as O
+    from paramgen import randomize_state
+    import uformer_b200
+    O.FAST = True
+    st = randomize_state(uformer_b200.Uformer(**UFORMER_B).state_dict(), 1234)
+    params = {k: v.clone().requires_grad_(True) for k, v in st.items() if torch.is_floating_point(v)}
+    full = dict(st)
+    full.update(params)
+    opt = torch.optim.AdamW(list(params.values()), lr=2e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.02)
+    nimg = 1
+    torch.manual_seed(1234)
+    clean = torch.rand(nimg, 3, 256, 256)
+    noisy = (clean + 0.1 * torch.randn_like(clean)).clamp(0, 1)
+    threads = min(os.cpu_count() or 8, 32)
+    torch.set_num_threads(threads)
+
+    def step():
+        opt.zero_grad()
+        out = O.uformer_forward(noisy, full, 256, 32, UFORMER_B["depths"])
+        torch.sqrt((out - clean) ** 2 + 1e-6).mean().backward()
+        opt.step()
+    step()
+    steps = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    v = nimg / dt
+    sample = f"{nimg} image of the batch-8 step per timed step (fp32 oracle port + torch autograd + torch AdamW, {threads} host threads)"
+    print(json.dumps({
+        "impl": "reference", "metric": "images/sec Uformer-B 256x256 train step", "value": v, "unit": "img/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": "Uformer-B 256x256 training step (BASELINE configs[2]), CPU port of the reference", "global_batch": nimg},
+        "cpu_baseline": {"value": v, "unit": "img/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+
+
+def run_train(args, rank, world, local):
+    """BASELINE configs[2]: Uformer-B 256x256 training step, bf16, batch 8 per GPU, gradient all-reduce over NCCL."""
+    import torch.distributed as dist
+    import uformer_b200
+    from uformer_b200 import ops
+    from uformer_b200.training import TrainStep
+    from paramgen import randomize_state
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    warm = max(args.warmup, 3)
+    B = args.batch if args.batch != 32 else 8
+    net = uformer_b200.Uformer(**UFORMER_B, drop_path_rate=0.1)                  # the reference's default (model.py:1075)
+    net.load_state_dict(randomize_state(net.state_dict(), 1234), strict=True)    # same weights on every rank
+    net = net.to(dev)
+    step = TrainStep(net, lr=2e-4, weight_decay=0.02)
+    torch.manual_seed(1234 + rank)                                               # every rank draws its own shard
+    clean_h = torch.rand(B, 3, 256, 256).pin_memory()
+    noisy_h = (clean_h + 0.1 * torch.randn_like(clean_h)).clamp(0, 1).pin_memory()
+    clean_d, noisy_d = clean_h.to(dev), noisy_h.to(dev)
+    loss_h = torch.zeros(1).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        for s, e in evs:
+            flush.zero_()
+            s.record()
+            fn()
+            e.record()
+        barrier()
+        t = torch.tensor([sum(s.elapsed_time(e) for s, e in evs)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    def step_dev():
+        return step(noisy_d, clean_d)
+
+    def step_e2e():
+        x = noisy_h.to(dev, non_blocking=True)
+        t = clean_h.to(dev, non_blocking=True)
+        loss_h.copy_(step(x, t).view(1), non_blocking=True)
+
+    note("train: engine + arena built; warm-up")
+    for _ in range(warm):
+        step_dev()
+    torch.cuda.synchronize()
+    ops.LAUNCH_COUNT = 0
+    step_dev()
+    launches_per_step = ops.LAUNCH_COUNT + 3                  # + charbonnier (2 kernels) + adamw (1)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    total_ms = timed(step_dev, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_ms = timed(step_e2e, args.steps)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = measured_peaks()
+    value = world * B * args.steps / (total_ms / 1e3)
+    e2e_val = world * B * args.steps / (e2e_ms / 1e3)
+    ach = TRAIN_GFLOP_PER_IMG * value / world / 1e3
+    print(json.dumps({
+        "metric": "images/sec Uformer-B 256x256 train step", "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
+        "warmup": warm, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "Uformer-B 256x256 training step: fwd + bwd + AdamW, Charbonnier loss, batch 8 per GPU (BASELINE configs[2])",
+                   "global_batch": B * world, "per_gpu_batch": B, "parallelism": f"dp{world} (NCCL bucketed gradient all-reduce, overlapped)",
+                   "l2": "256MB flush between timed steps", "drop_path_rate": 0.1,
+                   "backward": "recompute-from-block-input; restated torch statements under bf16 autocast (cuBLAS/ATen), not yet native"},
+        "e2e": {"value": e2e_val, "unit": "img/s", "h2d_bytes_per_step": 2 * clean_h.numel() * 4, "d2h_bytes_per_step": 4,
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "whole training step", "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                     "frac": ach / peaks["tf_sustained"], "peak_source": peaks["src"] + " sustained", "traffic": None,
+                     "flops_per_image": TRAIN_GFLOP_PER_IMG * 1e9}}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -170,13 +308,20 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="fwd", choices=["fwd", "train"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
 
     if args.impl == "reference":
-        run_reference_arm(args, rank, world)
+        if args.mode == "train":
+            run_reference_train(args, rank)
+        else:
+            run_reference_arm(args, rank, world)
+        return
+    if args.mode == "train":
+        run_train(args, rank, world, local)
         return
 
     import torch.distributed as dist

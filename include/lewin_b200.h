@@ -128,6 +128,31 @@ int lw_output_proj_fwd(const void* tokens, const float* w /* (Cout,Cin,3,3) */, 
                        const float* img /* residual or NULL */, float* out, int32_t B, int32_t Cin,
                        int32_t H, int32_t W, int32_t Cout, lw_stream_t stream);
 
+/* ---- training-step periphery: HBM-bound streaming kernels ----
+ * CharbonnierLoss (losses.py:41-52) forward AND backward in one pass over the data:
+ *   *loss = mean( sqrt((x-y)^2 + eps^2) );   grad[i] = (x[i]-y[i]) / sqrt((x[i]-y[i])^2 + eps^2) / n   (grad may be NULL)
+ * x, y, grad: fp32, n elements, 16-byte aligned.  `partial` is caller-provided scratch of LW_CHARBONNIER_PARTIALS
+ * floats (the library never allocates); the reduction order is fixed, so the loss is reproducible run to run. */
+#define LW_CHARBONNIER_PARTIALS 1024
+int lw_charbonnier_fwd_bwd(const float* x, const float* y, float* grad, float* loss, float* partial, int64_t n, float eps,
+                           lw_stream_t stream);
+
+/* AdamW over flat fp32 arenas in ONE launch — the arithmetic of torch.optim.AdamW(lr, betas, eps, weight_decay)
+ * as the reference constructs it (train/train_denoise.py:77), preceded by g *= grad_scale (1/world after the NCCL sum
+ * all-reduce of the gradient arena) and optionally followed by g = 0 (the next step's zero_grad, train_denoise.py:172):
+ *   p *= 1 - lr*wd;  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps) */
+typedef struct lw_adamw_args {
+  float* p;                /* parameters  (n) fp32, updated in place */
+  float* g;                /* gradients   (n) fp32 */
+  float* m;                /* exp_avg     (n) fp32 */
+  float* v;                /* exp_avg_sq  (n) fp32 */
+  int64_t n;
+  int32_t step;            /* t >= 1: the step being taken */
+  int32_t zero_grad;       /* 1: write zeros to g after reading it */
+  float lr, beta1, beta2, eps, weight_decay, grad_scale;
+} lw_adamw_args;
+int lw_adamw_step(const lw_adamw_args* a, lw_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -63,7 +63,7 @@ def test_c_abi_exports_every_declared_symbol():
     lib = _lib.load()
     for s in declared:
         assert hasattr(lib, s), s
-    assert lib.lw_abi_version() == 1
+    assert lib.lw_abi_version() == 2
     # struct sizes agree with the header layout (pointers 8 B, ints 4 B)
     assert ctypes.sizeof(_lib.WmsaArgs) == 12 * 8 + 10 * 4 + 8      # 12 pointers, 9 ints + float, trace pointer
     assert ctypes.sizeof(_lib.Leff2Args) == 7 * 8 + 5 * 4 + 4

@@ -48,3 +48,73 @@ def test_replica_sharding_and_max_reduction():
     assert ms == 20.0                                     # max over ranks, not the mean
     assert abs(value - 2 * 4 * 3 / 0.020) < 1e-6          # whole-job images / slowest rank's time
     assert sums[0] != sums[1]                             # ranks really processed different shards
+
+
+def _ddp_worker(rank, world, port, out):
+    """Data-parallel gradient path of the training step (uformer_b200.training): FlatArena + GradReducer over gloo.
+    The model is two LeWin blocks + samplers stated with uformer_b200.restated on CPU (the native forward needs a B200;
+    the arena / bucket / hook / all-reduce logic under test is device agnostic)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import torch.nn as nn
+    import uformer_b200 as U
+    from uformer_b200 import restated as R
+    from uformer_b200 import training as T
+    from paramgen import randomize_state
+
+    class Tiny(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.b0 = U.LeWinTransformerBlock(16, (16, 16), 1, win_size=8, shift_size=0)
+            self.down = U.Downsample(16, 32)
+            self.b1 = U.LeWinTransformerBlock(32, (8, 8), 2, win_size=8, shift_size=0, modulator=True)
+            self.unused = nn.Linear(4, 4)                        # never touched by forward: its bucket must still reduce
+
+        def forward(self, x):
+            return R.lewin_block(self.b1, R.downsample(self.down, R.lewin_block(self.b0, x)))
+
+    net = Tiny()
+    net.load_state_dict(randomize_state(net.state_dict(), 7))    # same weights on every rank
+    torch.manual_seed(0)
+    x_all = torch.randn(4, 256, 16)
+    # single-process full-batch gradient (the thing data parallelism must reproduce)
+    full = Tiny()
+    full.load_state_dict(net.state_dict())
+    full(x_all).pow(2).mean().backward()
+    want = {k: p.grad.clone() for k, p in full.named_parameters() if p.grad is not None}
+
+    arena = T.FlatArena(list(net.parameters())[::-1])
+    red = T.GradReducer(arena, None, bucket_bytes=16 << 10)
+    assert red.world == world and len(red.buckets) >= 3
+    for it in range(2):                                          # two steps: begin() must re-arm the hooks
+        arena.zero_grad()
+        red.begin()
+        shard = x_all[rank * 2:(rank + 1) * 2]
+        net(shard).pow(2).mean().backward()
+        fired_in_backward = list(red.launch_order)
+        red.finish()
+        arena.grad.div_(world)                                   # FlatAdamW folds this scale into its kernel
+        err = max(((p.grad - want[k]).norm() / want[k].norm()).item() for k, p in net.named_parameters() if k in want)
+        unused_zero = float(net.unused.weight.grad.abs().sum())
+    if rank == 0:
+        out.put((err, fired_in_backward, list(red.launch_order), len(red.buckets), unused_zero))
+    dist.destroy_process_group()
+
+
+def test_gradient_arena_bucketed_allreduce_matches_full_batch():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    err, early, order, nb, unused = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert err < 1e-5                                            # mean of shard gradients == full-batch gradient
+    # buckets were reduced WHILE backward was running, in arena order (= reverse execution order); only the bucket
+    # holding the never-used parameter (registered last -> arena bucket 0) had to wait for finish()
+    assert len(early) == nb - 1 and early == sorted(early) and 0 not in early and order[-1] == 0
+    assert sorted(order) == list(range(nb))                      # every bucket reduced exactly once, incl. the unused one
+    assert unused == 0.0

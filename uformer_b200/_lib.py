@@ -47,9 +47,17 @@ class UpArgs(C.Structure):
                 ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32), ("Cout", C.c_int32), ("out_stride", C.c_int32)]
 
 
+class AdamWArgs(C.Structure):
+    _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("n", C.c_int64), ("step", C.c_int32),
+                ("zero_grad", C.c_int32), ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+                ("weight_decay", C.c_float), ("grad_scale", C.c_float)]
+
+
+CHARBONNIER_PARTIALS = 1024      # LW_CHARBONNIER_PARTIALS
+
 # every symbol include/lewin_b200.h declares
 EXPORTS = ["lw_abi_version", "lw_last_cuda_error", "lw_check_device", "lw_nch_ares", "lw_wmsa_fwd", "lw_leff1_fwd", "lw_leff2_fwd",
-           "lw_downsample_fwd", "lw_upsample_fwd", "lw_input_proj_fwd", "lw_output_proj_fwd"]
+           "lw_downsample_fwd", "lw_upsample_fwd", "lw_input_proj_fwd", "lw_output_proj_fwd", "lw_charbonnier_fwd_bwd", "lw_adamw_step"]
 
 _lib = None
 
@@ -76,6 +84,10 @@ def load():
     lib.lw_input_proj_fwd.argtypes = [C.c_void_p] * 4 + [C.c_int32] * 5 + [C.c_void_p]
     lib.lw_output_proj_fwd.restype = C.c_int
     lib.lw_output_proj_fwd.argtypes = [C.c_void_p] * 5 + [C.c_int32] * 5 + [C.c_void_p]
+    lib.lw_charbonnier_fwd_bwd.restype = C.c_int
+    lib.lw_charbonnier_fwd_bwd.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_float, C.c_void_p]
+    lib.lw_adamw_step.restype = C.c_int
+    lib.lw_adamw_step.argtypes = [C.POINTER(AdamWArgs), C.c_void_p]
     _lib = lib
     return lib
 

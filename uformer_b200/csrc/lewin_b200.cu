@@ -8,6 +8,8 @@
 #include "leff2.cuh"
 #include "down.cuh"
 #include "proj.cuh"
+#include "train.cuh"
+#include <cmath>
 
 using namespace lw;
 
@@ -23,7 +25,7 @@ static int cuda_fail(cudaError_t e) {
     if (_e != cudaSuccess) return cuda_fail(_e);   \
   } while (0)
 
-extern "C" int lw_abi_version(void) { return 1; }
+extern "C" int lw_abi_version(void) { return 2; }
 extern "C" const char* lw_last_cuda_error(void) { return g_err; }
 extern "C" int lw_check_device(void) {
   int dev = 0, major = 0;
@@ -218,6 +220,43 @@ extern "C" int lw_output_proj_fwd(const void* tokens, const float* w, const floa
   const size_t smem = (size_t)9 * Cin * 4 * sizeof(float);
   output_proj_kernel<<<blocks, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const bf16*>(tokens), w, b, img, out, B, Cin, H,
                                                                                     W, Cout);
+  LW_TRY(cudaGetLastError());
+  return LW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+extern "C" int lw_charbonnier_fwd_bwd(const float* x, const float* y, float* grad, float* loss, float* partial, int64_t n, float eps,
+                                      lw_stream_t stream) {
+  if (!x || !y || !loss || !partial) return LW_ERR_NULL;
+  if (n <= 0 || !aligned16(x) || !aligned16(y) || !aligned16(grad)) return LW_ERR_BAD_SHAPE;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int grid = 4 * sm_count();
+  if (grid > LW_CHARBONNIER_PARTIALS) grid = LW_CHARBONNIER_PARTIALS;
+  const long long work = (n / 4 + kTrainThreads - 1) / kTrainThreads;
+  if (work < grid) grid = work > 0 ? (int)work : 1;
+  const float inv_n = (float)(1.0 / (double)n);
+  charbonnier_kernel<<<grid, kTrainThreads, 0, st>>>(x, y, grad, partial, n, eps * eps, inv_n);
+  LW_TRY(cudaGetLastError());
+  charbonnier_finish_kernel<<<1, kTrainThreads, 0, st>>>(partial, grid, inv_n, loss);
+  LW_TRY(cudaGetLastError());
+  return LW_OK;
+}
+
+extern "C" int lw_adamw_step(const lw_adamw_args* a, lw_stream_t stream) {
+  if (!a || !a->p || !a->g || !a->m || !a->v) return LW_ERR_NULL;
+  if (a->n <= 0 || a->step < 1 || !aligned16(a->p) || !aligned16(a->g) || !aligned16(a->m) || !aligned16(a->v)) return LW_ERR_BAD_SHAPE;
+  if (!(a->beta1 >= 0.f && a->beta1 < 1.f && a->beta2 >= 0.f && a->beta2 < 1.f)) return LW_ERR_BAD_SHAPE;
+  AdamWConsts c;
+  c.lr = a->lr; c.beta1 = a->beta1; c.beta2 = a->beta2; c.eps = a->eps; c.weight_decay = a->weight_decay;
+  c.bias_corr1 = (float)(1.0 - std::pow((double)a->beta1, (double)a->step));
+  c.inv_sqrt_bc2 = (float)(1.0 / std::sqrt(1.0 - std::pow((double)a->beta2, (double)a->step)));
+  c.grad_scale = a->grad_scale;
+  int grid = 8 * sm_count();
+  const long long work = (a->n / 4 + kTrainThreads - 1) / kTrainThreads;
+  if (work < grid) grid = work > 0 ? (int)work : 1;
+  adamw_kernel<<<grid, kTrainThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a->p, a->g, a->m, a->v, a->n, c, a->zero_grad);
   LW_TRY(cudaGetLastError());
   return LW_OK;
 }

@@ -4,9 +4,11 @@ Each class keeps the reference's constructor signature, attributes, ``flops()`` 
 the exact child-module tree, so ``state_dict()`` keys/shapes are identical (strict checkpoint
 loading, utils/model_utils.py:23-33) and ``Uformer._init_weights`` (model.py:1249-1256) still finds
 real nn.Linear / nn.LayerNorm children.  Only ``forward`` differs: it packs the parameters once
-(cached, invalidated on in-place updates) and calls the native sm_100a kernels.  Forward is
-inference-only this round (no autograd graph is built).  There is NO CPU path: calling forward on
-a non-CUDA tensor raises ``EngineUnavailable``.
+(cached, invalidated on in-place updates) and calls the native sm_100a kernels.  When autograd is
+recording (training, BASELINE configs[2]) the same native forward runs inside
+``autograd.NativeFn``, which saves only the op's input and builds the backward by recomputing the op
+from it (uformer_b200/restated.py).  There is NO CPU path: calling forward on a non-CUDA tensor
+raises ``EngineUnavailable``.
 """
 from __future__ import annotations
 
@@ -15,7 +17,7 @@ import math
 import torch
 import torch.nn as nn
 
-from . import _lib, ops, packing
+from . import _lib, autograd, ops, packing, restated
 from ._lib import EngineUnavailable  # noqa: F401  (re-export)
 
 
@@ -24,8 +26,9 @@ def _to_2tuple(v):
 
 
 class DropPath(nn.Module):
-    """Stochastic depth (timm semantics).  Identity in eval; the fused kernels do not implement the
-    training-time per-sample mask yet, so training-mode forward with p>0 raises in the block."""
+    """Stochastic depth (timm semantics, un-vendored dependency of model.py:4,887): identity in eval; in training a
+    per-sample Bernoulli(keep)/keep factor on the residual branch.  LeWinTransformerBlock does not call this module
+    (its two branches live inside fused kernels); it draws the same factors with `draw` and applies them itself."""
 
     def __init__(self, drop_prob: float = 0.0):
         super().__init__()
@@ -38,6 +41,23 @@ class DropPath(nn.Module):
         shape = (x.shape[0],) + (1,) * (x.ndim - 1)
         return x * x.new_empty(shape).bernoulli_(keep).div_(keep)
 
+    def draw(self, batch: int, device):
+        """(batch,1,1) fp32 factor in {0, 1/keep}, or None when the branch is kept as is."""
+        if self.drop_prob == 0.0 or not self.training:
+            return None
+        keep = 1.0 - self.drop_prob
+        return torch.empty((batch, 1, 1), dtype=torch.float32, device=device).bernoulli_(keep).div_(keep)
+
+
+_WEIGHTS_EPOCH = [0]
+
+
+def invalidate_packed():
+    """Declare every cached operand image stale.  torch bumps a tensor's version on in-place torch ops, which the
+    caches already watch; a native optimizer step writes the parameter arena through raw pointers, so
+    uformer_b200.training.FlatAdamW calls this after each step."""
+    _WEIGHTS_EPOCH[0] += 1
+
 
 class _PackCache:
     """Packed-parameter cache: recomputed when any source tensor is replaced or modified in place."""
@@ -47,7 +67,7 @@ class _PackCache:
         self._val = None
 
     def get(self, tensors, build):
-        key = tuple((t.data_ptr(), t._version, str(t.device)) for t in tensors if t is not None)
+        key = (_WEIGHTS_EPOCH[0],) + tuple((t.data_ptr(), t._version, str(t.device)) for t in tensors if t is not None)
         if key != self._key:
             with torch.no_grad():
                 self._val = build()
@@ -64,11 +84,13 @@ def _as_bf16(x):
     return x.to(torch.bfloat16).contiguous(), x.dtype
 
 
-def _no_grad_guard(*tensors):
-    _lib.require_device(tensors[0].device)      # device check first: no CPU fallback, fail loudly
-    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
-        raise NotImplementedError("uformer_b200: backward kernels are not implemented yet (inference only); "
-                                  "wrap the call in torch.no_grad()")
+def _run(mod, native, restate, acts):
+    """Native forward of `mod`; under autograd the same call is wrapped so that backward recomputes it from `acts`."""
+    _lib.require_device(acts[0].device)         # device check first: no CPU fallback, fail loudly
+    params = [p for p in mod.parameters() if p.requires_grad]
+    if autograd.wants_grad(*acts, *params):
+        return autograd.apply(native, restate, acts, params)
+    return native(*acts)
 
 
 # -------------------------------------------------------------------------------------------------
@@ -146,9 +168,11 @@ class WindowAttention(nn.Module):
         if attn_kv is not None:
             raise NotImplementedError("cross-attention keys (attn_kv) are never used by Uformer configs")
         self._check_supported()
-        _no_grad_guard(x, self.proj.weight)
+        _lib.require_device(x.device)
         xb, back = _as_bf16(x)
-        out = ops.wmsa(xb, self.packed(), H=0, W=0, shift=0, windowed=True, resid=None, mask=mask)
+        acts = [xb] if mask is None else [xb, mask.to(device=x.device, dtype=torch.float32)]
+        out = _run(self, lambda t, m=None: ops.wmsa(t, self.packed(), H=0, W=0, shift=0, windowed=True, resid=None, mask=m),
+                   lambda t, m=None: restated.window_attention(self, t, m), acts)
         return out if back is None else out.to(back)
 
     def extra_repr(self) -> str:
@@ -196,11 +220,11 @@ class LeFF(nn.Module):
 
     def forward(self, x):
         self._check_supported()
-        _no_grad_guard(x, self.linear1[0].weight)
+        _lib.require_device(x.device)
         B, L, _ = x.shape
         H = int(math.sqrt(L))
         xb, back = _as_bf16(x)
-        out = ops.leff(xb, self.packed(), B=B, H=H, W=H, resid=None)
+        out = _run(self, lambda t: ops.leff(t, self.packed(), B=B, H=H, W=H, resid=None), lambda t: restated.leff(self, t), [xb])
         return out if back is None else out.to(back)
 
     def flops(self, H, W):
@@ -225,11 +249,11 @@ class Downsample(nn.Module):
             cout=self.out_channel))
 
     def forward(self, x):
-        _no_grad_guard(x, self.conv[0].weight)
+        _lib.require_device(x.device)
         B, L, _ = x.shape
         H = int(math.sqrt(L))
         xb, back = _as_bf16(x)
-        out = ops.downsample(xb, self.packed(), B=B, H=H, W=H)
+        out = _run(self, lambda t: ops.downsample(t, self.packed(), B=B, H=H, W=H), lambda t: restated.downsample(self, t), [xb])
         return out if back is None else out.to(back)
 
     def flops(self, H, W):
@@ -253,11 +277,13 @@ class Upsample(nn.Module):
             cout=self.out_channel))
 
     def forward(self, x, out=None):
-        _no_grad_guard(x, self.deconv[0].weight)
+        _lib.require_device(x.device)
         B, L, _ = x.shape
         H = int(math.sqrt(L))
         xb, back = _as_bf16(x)
-        res = ops.upsample(xb, self.packed(), B=B, H=H, W=H, out=out)
+        if out is not None and autograd.wants_grad(xb, *self.parameters()):
+            raise ValueError("Upsample(out=...) writes in place and cannot be recorded by autograd; call it without `out`")
+        res = _run(self, lambda t: ops.upsample(t, self.packed(), B=B, H=H, W=H, out=out), lambda t: restated.upsample(self, t), [xb])
         return res if back is None else res.to(back)
 
     def flops(self, H, W):
@@ -328,18 +354,44 @@ class LeWinTransformerBlock(nn.Module):
         if H * W != L or H % 8 or self.win_size != 8:
             raise NotImplementedError(f"uformer_b200 block needs a square token map with side % 8 == 0 and 8x8 windows "
                                       f"(L={L}, win_size={self.win_size})")
-        if self.training and isinstance(self.drop_path, DropPath) and self.drop_path.drop_prob > 0:
-            raise NotImplementedError("stochastic depth in training mode is not fused yet; call .eval()")
         self.attn._check_supported()
         self.mlp._check_supported()
-        _no_grad_guard(x, self.norm1.weight)
+        _lib.require_device(x.device)
         xb, back = _as_bf16(x)
-        pk = self.packed()
-        pa = dict(self.attn.packed(), ln_w=pk["ln1_w"], ln_b=pk["ln1_b"], modulator=pk["modulator"], ln_eps=self.norm1.eps)
-        amask = None if mask is None else self.input_mask_to_attn_mask(mask.to(x.device), H, W, 8)
-        x1 = ops.wmsa(xb, pa, H=H, W=W, shift=self.shift_size, windowed=False, resid=xb, mask=amask)
-        pm = dict(self.mlp.packed(), ln_w=pk["ln2_w"], ln_b=pk["ln2_b"], ln_eps=self.norm2.eps)
-        res = ops.leff(x1, pm, B=B, H=H, W=W, resid=x1, out=out if back is None else None)
+        # stochastic depth (model.py:986-987): the two per-sample factors, drawn in the reference's order
+        dp = self.drop_path if isinstance(self.drop_path, DropPath) else None
+        s1 = dp.draw(B, x.device) if dp is not None else None
+        s2 = dp.draw(B, x.device) if dp is not None else None
+        acts = [xb] + ([s1, s2] if s1 is not None else [])
+        if mask is not None:
+            acts.append(mask.to(device=x.device, dtype=torch.float32))
+        has_dp, has_mask = s1 is not None, mask is not None
+        dst = out if back is None else None
+
+        def split(rest):
+            sc = rest[:2] if has_dp else (None, None)
+            return sc[0], sc[1], (rest[-1] if has_mask else None)
+
+        def native(t, *rest):
+            a1, a2, m = split(rest)
+            pk = self.packed()
+            pa = dict(self.attn.packed(), ln_w=pk["ln1_w"], ln_b=pk["ln1_b"], modulator=pk["modulator"], ln_eps=self.norm1.eps)
+            pm = dict(self.mlp.packed(), ln_w=pk["ln2_w"], ln_b=pk["ln2_b"], ln_eps=self.norm2.eps)
+            amask = None if m is None else self.input_mask_to_attn_mask(m, H, W, 8)
+            if a1 is None:
+                x1 = ops.wmsa(t, pa, H=H, W=W, shift=self.shift_size, windowed=False, resid=t, mask=amask)
+                return ops.leff(x1, pm, B=B, H=H, W=W, resid=x1, out=dst)
+            br = ops.wmsa(t, pa, H=H, W=W, shift=self.shift_size, windowed=False, resid=None, mask=amask)
+            x1 = torch.addcmul(t.float(), br.float(), a1).to(torch.bfloat16)
+            br = ops.leff(x1, pm, B=B, H=H, W=W, resid=None)
+            y = torch.addcmul(x1.float(), br.float(), a2).to(torch.bfloat16)
+            return y if dst is None else dst.copy_(y)
+
+        def restate(t, *rest):
+            a1, a2, m = split(rest)
+            return restated.lewin_block(self, t, m, a1, a2)
+
+        res = _run(self, native, restate, acts)
         return res if back is None else res.to(back)
 
     def flops(self):

@@ -16,8 +16,8 @@ import os
 import torch
 import torch.nn as nn
 
-from . import ops
-from .modules import Downsample, LeWinTransformerBlock, Upsample, _no_grad_guard
+from . import _lib, autograd, ops, restated
+from .modules import Downsample, LeWinTransformerBlock, Upsample, _run
 
 # working-set budget (MB) for the optional images-outer stage schedule (B200 L2 is 126 MB)
 L2_BUDGET_BYTES = int(os.environ.get("UFORMER_B200_L2_BUDGET_MB", str(1 << 20))) << 20     # default: off (measured slower)
@@ -56,7 +56,7 @@ class LeWinStage(nn.Module):
         B, L, C = x.shape
         per_image = 14 * L * C
         chunk = max(1, min(B, L2_BUDGET_BYTES // per_image))
-        if chunk >= B or mask is not None or x.dtype != torch.bfloat16 or len(self.blocks) == 0:
+        if chunk >= B or mask is not None or x.dtype != torch.bfloat16 or len(self.blocks) == 0 or autograd.wants_grad(x, *self.parameters()):
             for blk in self.blocks:
                 x = blk(x, mask)
             return x
@@ -84,7 +84,8 @@ class InputProj(nn.Module):
 
     def forward(self, x):
         cv = self.proj[0]
-        return ops.input_proj(x, cv.weight.detach().float().contiguous(), cv.bias.detach().float().contiguous())
+        return _run(self, lambda im: ops.input_proj(im, cv.weight.detach().float().contiguous(), cv.bias.detach().float().contiguous()),
+                    lambda im: restated.input_proj(self, im), [x])
 
     def flops(self, H, W):
         return H * W * self.in_channel * self.out_channel * 3 * 3
@@ -104,8 +105,9 @@ class OutputProj(nn.Module):
         H = int(math.sqrt(L))
         cv = self.proj[0]
         xb = x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16)
-        return ops.output_proj(xb.contiguous(), cv.weight.detach().float().contiguous(), cv.bias.detach().float().contiguous(),
-                               residual, H, H)
+        acts = [xb.contiguous()] + ([residual] if residual is not None else [])
+        return _run(self, lambda t, r=None: ops.output_proj(t, cv.weight.detach().float().contiguous(), cv.bias.detach().float().contiguous(), r, H, H),
+                    lambda t, r=None: restated.output_proj(self, t, r), acts)
 
     def flops(self, H, W):
         return H * W * self.in_channel * self.out_channel * 3 * 3
@@ -169,10 +171,32 @@ class Uformer(nn.Module):
     def extra_repr(self):
         return f"embed_dim={self.embed_dim}, token_projection={self.token_projection}, token_mlp={self.mlp},win_size={self.win_size}"
 
-    @torch.no_grad()
     def forward(self, x, mask=None):
-        """x: (B, dd_in, H, W) float image on a B200; returns fp32 (B, in_chans, H, W)."""
-        _no_grad_guard(x)
+        """x: (B, dd_in, H, W) float image on a B200; returns fp32 (B, in_chans, H, W).  In eval mode (or under
+        torch.no_grad) this is the inference schedule below; in training mode with autograd recording it is
+        `_forward_train` (same kernels, each op wrapped for recompute-backward)."""
+        _lib.require_device(x.device)
+        if self.training and autograd.wants_grad(x, *self.parameters()):
+            return self._forward_train(x, mask)
+        with torch.no_grad():
+            return self._forward_infer(x, mask)
+
+    def _forward_train(self, x, mask=None):
+        """Training forward: native kernels, autograd-recorded per op; the skip-concat is a plain torch.cat here
+        (model.py:1288-1300) because the in-place concat fusion of the inference path cannot be recorded."""
+        y = self.input_proj(x)
+        skips = []
+        for i in range(4):
+            y = getattr(self, f"encoderlayer_{i}")(y, mask)
+            skips.append(y)
+            y = getattr(self, f"dowsample_{i}")(y)
+        y = self.conv(y, mask)
+        for j in range(4):
+            y = torch.cat([getattr(self, f"upsample_{j}")(y), skips[3 - j]], -1)
+            y = getattr(self, f"decoderlayer_{j}")(y, mask)
+        return self.output_proj(y, x if self.dd_in == 3 else None)
+
+    def _forward_infer(self, x, mask=None):
         B = x.shape[0]
         y = self.input_proj(x)
         skips = []

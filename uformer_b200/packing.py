@@ -56,16 +56,13 @@ def pack_qkv(wq: Tensor, bq: Tensor, wkv: Tensor, bkv: Tensor, heads: int, scale
     The attention scale (model.py:497, q * hd^-0.5) is folded into the q rows and q bias."""
     C = wq.shape[0]
     hd = C // heads
-    wk, wv = wkv[:C], wkv[C:]
-    bk, bv = bkv[:C], bkv[C:]
-    rows, bias = [], []
-    for h in range(heads):
-        s = slice(h * hd, (h + 1) * hd)
-        rows += [wq[s].float() * scale, wk[s].float(), wv[s].float()]
-        bias += [bq[s].float() * scale, bk[s].float(), bv[s].float()]
-    wcat = torch.cat(rows, 0)                                   # (heads*3*hd, C)
+    sc = torch.tensor([scale, 1.0, 1.0], dtype=torch.float32, device=wq.device)
+    w3 = torch.stack([wq.float(), wkv[:C].float(), wkv[C:].float()], 0)           # (3, C, C): q | k | v
+    wcat = (w3.view(3, heads, hd, C) * sc.view(3, 1, 1, 1)).permute(1, 0, 2, 3).reshape(heads * 3 * hd, C)
+    b3 = torch.stack([bq.float(), bkv[:C].float(), bkv[C:].float()], 0)
+    bias = (b3.view(3, heads, hd) * sc.view(3, 1, 1)).permute(1, 0, 2).reshape(-1)
     img = pack_kmajor(wcat, 3 * hd, "nk")                       # [heads][KB][3hd*64]
-    return img, torch.cat(bias, 0).contiguous()                 # bias (heads*3*hd,)
+    return img, bias.contiguous()                               # bias (heads*3*hd,)
 
 
 def pack_relpos(table: Tensor) -> Tensor:
