@@ -267,7 +267,7 @@ def run_train(args, rank, world, local):
     torch.cuda.synchronize()
     ops.LAUNCH_COUNT = 0
     step_dev()
-    launches_per_step = ops.LAUNCH_COUNT + 3                  # + charbonnier (2 kernels) + adamw (1)
+    launches_per_step = ops.LAUNCH_COUNT                      # forward kernels + charbonnier + adamw (all go through ops)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()

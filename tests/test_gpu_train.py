@@ -90,7 +90,7 @@ def test_train_step_updates_weights_and_reduces_loss():
     from uformer_b200.training import TrainStep
     g = load_golden("train_t2_128")
     net = _engine_net(g)
-    step = TrainStep(net, lr=2e-3, weight_decay=0.0)
+    step = TrainStep(net, lr=2e-4, weight_decay=0.0)
     x, t = g["x"].to(DEV), g["target"].to(DEV)
     losses = [step(x, t).item() for _ in range(5)]
     print("losses:", losses)

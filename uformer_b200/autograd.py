@@ -33,15 +33,18 @@ class NativeFn(torch.autograd.Function):
         tensors = ctx.saved_tensors
         n_act = ctx.n_act
         need = ctx.needs_input_grad[3:]
+        dev = g.device.type
+        amp = autocast_enabled(dev)
         acts = []
         for i, t in enumerate(tensors[:n_act]):
             t = t.detach()
+            if not amp and t.dtype == torch.bfloat16:
+                t = t.float()                                # no autocast (CPU test runs): plain fp32 statements
             if need[i] and torch.is_floating_point(t):
                 t.requires_grad_(True)
             acts.append(t)
         params = tensors[n_act:]
-        dev = g.device.type
-        with torch.enable_grad(), torch.autocast(device_type=dev, dtype=torch.bfloat16, enabled=autocast_enabled(dev)):
+        with torch.enable_grad(), torch.autocast(device_type=dev, dtype=torch.bfloat16, enabled=amp):
             out = ctx.restate(*acts)
         wrt = [a for a in acts if a.requires_grad] + [p for i, p in enumerate(params) if need[n_act + i]]
         grads = list(torch.autograd.grad(out, wrt, g.to(out.dtype), allow_unused=True))

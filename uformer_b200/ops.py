@@ -148,3 +148,32 @@ def output_proj(tok: Tensor, w: Tensor, b: Tensor, img: Tensor | None, H: int, W
             lambda: _lib.load().lw_output_proj_fwd(_ptr(tok), _ptr(w), _ptr(b), _ptr(img), _ptr(out), B, Cin, H, W, Cout, _stream()),
             "lw_output_proj_fwd")
     return out
+
+
+def charbonnier(x: Tensor, y: Tensor, eps: float, need_grad: bool):
+    """(loss (1,) fp32, d loss / d x or None) of mean(sqrt((x-y)^2 + eps^2)) in one pass (two tiny launches)."""
+    _lib.require_device(x.device)
+    if x.dtype != torch.float32 or y.dtype != torch.float32 or x.shape != y.shape or not x.is_contiguous() or not y.is_contiguous():
+        raise TypeError("charbonnier expects two contiguous fp32 tensors of one shape")
+    grad = torch.empty_like(x) if need_grad else None
+    loss = torch.empty(1, dtype=torch.float32, device=x.device)
+    partial = torch.empty(_lib.CHARBONNIER_PARTIALS, dtype=torch.float32, device=x.device)
+    n = x.numel()
+    _launch("charbonnier", 8.0 * n, lambda: _lib.load().lw_charbonnier_fwd_bwd(_ptr(x), _ptr(y), _ptr(grad), _ptr(loss), _ptr(partial), n, eps,
+                                                                             _stream()), "lw_charbonnier_fwd_bwd")
+    return loss, grad
+
+
+def adamw_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, *, step: int, lr: float, beta1: float, beta2: float, eps: float,
+               weight_decay: float, grad_scale: float, zero_grad: bool):
+    """One AdamW update over flat fp32 arenas, in place (p, m, v; g zeroed when zero_grad)."""
+    _lib.require_device(p.device)
+    for t in (p, g, m, v):
+        if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != p.numel():
+            raise TypeError("adamw_step expects four contiguous fp32 tensors of one size")
+    a = _lib.AdamWArgs()
+    a.p, a.g, a.m, a.v, a.n = _ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel()
+    a.step, a.zero_grad = step, int(zero_grad)
+    a.lr, a.beta1, a.beta2, a.eps, a.weight_decay, a.grad_scale = lr, beta1, beta2, eps, weight_decay, grad_scale
+    with torch.cuda.device(p.device):
+        _launch("adamw", 12.0 * p.numel(), lambda: _lib.load().lw_adamw_step(C.byref(a), _stream()), "lw_adamw_step")

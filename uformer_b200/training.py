@@ -22,13 +22,11 @@ raise ``EngineUnavailable`` anywhere else.
 """
 from __future__ import annotations
 
-import ctypes as C
-
 import torch
 import torch.distributed as dist
 import torch.nn as nn
 
-from . import _lib, modules
+from . import modules, ops
 from ._lib import EngineUnavailable
 
 Tensor = torch.Tensor
@@ -185,15 +183,9 @@ class FlatAdamW:
 
     def step(self, grad_scale: float = 1.0, zero_grad: bool = True):
         a = self.arena
-        _lib.require_device(a.flat.device)
         self.steps += 1
-        args = _lib.AdamWArgs()
-        args.p, args.g, args.m, args.v = a.flat.data_ptr(), a.grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr()
-        args.n, args.step, args.zero_grad = a.numel, self.steps, int(zero_grad)
-        args.lr, args.beta1, args.beta2, args.eps = self.lr, self.betas[0], self.betas[1], self.eps
-        args.weight_decay, args.grad_scale = self.weight_decay, grad_scale
-        with torch.cuda.device(a.flat.device):
-            _lib.check(_lib.load().lw_adamw_step(C.byref(args), torch.cuda.current_stream().cuda_stream), "lw_adamw_step")
+        ops.adamw_step(a.flat, a.grad, self.exp_avg, self.exp_avg_sq, step=self.steps, lr=self.lr, beta1=self.betas[0],
+                       beta2=self.betas[1], eps=self.eps, weight_decay=self.weight_decay, grad_scale=grad_scale, zero_grad=zero_grad)
         modules.invalidate_packed()          # the kernel wrote the weights behind torch's version counters
 
     def state_dict(self):
@@ -211,17 +203,8 @@ class FlatAdamW:
 class _CharbonnierFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, y, eps):
-        _lib.require_device(x.device)
-        if x.dtype != torch.float32 or y.dtype != torch.float32 or x.shape != y.shape:
-            raise TypeError("CharbonnierLoss expects two fp32 tensors of one shape")
-        x, y = x.contiguous(), y.contiguous()
         need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
-        grad = torch.empty_like(x) if need else None
-        loss = torch.empty(1, dtype=torch.float32, device=x.device)
-        partial = torch.empty(_lib.CHARBONNIER_PARTIALS, dtype=torch.float32, device=x.device)
-        rc = _lib.load().lw_charbonnier_fwd_bwd(x.data_ptr(), y.data_ptr(), None if grad is None else grad.data_ptr(), loss.data_ptr(),
-                                                partial.data_ptr(), x.numel(), eps, torch.cuda.current_stream().cuda_stream)
-        _lib.check(rc, "lw_charbonnier_fwd_bwd")
+        loss, grad = ops.charbonnier(x.contiguous(), y.contiguous(), eps, need)
         ctx.grad = grad
         return loss.view(())
 
