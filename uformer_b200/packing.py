@@ -16,12 +16,21 @@ import torch
 Tensor = torch.Tensor
 
 
+_PERMS = {}
+
+
 def _swizzle128_perm(nch: int, device) -> Tensor:
-    """perm[n, k] = element offset inside a (nch x 64) bf16 SWIZZLE_128B tile image."""
-    n = torch.arange(nch, device=device)[:, None]
-    k = torch.arange(64, device=device)[None, :]
-    chunk = (k // 8) ^ (n % 8)
-    return n * 64 + chunk * 8 + (k % 8)
+    """perm[n, k] = element offset inside a (nch x 64) bf16 SWIZZLE_128B tile image (cached per (nch, device): a
+    training step re-packs ~200 weights after every optimizer update)."""
+    key = (nch, str(device))
+    perm = _PERMS.get(key)
+    if perm is None:
+        n = torch.arange(nch)[:, None]
+        k = torch.arange(64)[None, :]
+        chunk = (k // 8) ^ (n % 8)
+        perm = (n * 64 + chunk * 8 + (k % 8)).to(device)
+        _PERMS[key] = perm
+    return perm
 
 
 def pack_kmajor(w: Tensor, nch: int, order: str = "nk") -> Tensor:
@@ -30,15 +39,16 @@ def pack_kmajor(w: Tensor, nch: int, order: str = "nk") -> Tensor:
     N, K = w.shape
     assert N % nch == 0, (N, nch)
     KB = (K + 63) // 64
-    wp = torch.zeros(N, KB * 64, dtype=torch.float32, device=w.device)
-    wp[:, :K] = w.float()
+    wp = w.to(torch.bfloat16)                         # round first: the permutation then moves half the bytes
+    if KB * 64 != K:
+        wp = torch.nn.functional.pad(wp, (0, KB * 64 - K))
     perm = _swizzle128_perm(nch, w.device).reshape(-1)
     t = wp.reshape(N // nch, nch, KB, 64).permute(0, 2, 1, 3).reshape(N // nch, KB, nch * 64)
     img = torch.empty_like(t)
     img[:, :, perm] = t
     if order == "kn":
         img = img.permute(1, 0, 2)
-    return img.contiguous().to(torch.bfloat16)
+    return img.contiguous()
 
 
 def unpack_kmajor(img: Tensor, N: int, K: int, nch: int, order: str = "nk") -> Tensor:
@@ -56,11 +66,10 @@ def pack_qkv(wq: Tensor, bq: Tensor, wkv: Tensor, bkv: Tensor, heads: int, scale
     The attention scale (model.py:497, q * hd^-0.5) is folded into the q rows and q bias."""
     C = wq.shape[0]
     hd = C // heads
-    sc = torch.tensor([scale, 1.0, 1.0], dtype=torch.float32, device=wq.device)
-    w3 = torch.stack([wq.float(), wkv[:C].float(), wkv[C:].float()], 0)           # (3, C, C): q | k | v
-    wcat = (w3.view(3, heads, hd, C) * sc.view(3, 1, 1, 1)).permute(1, 0, 2, 3).reshape(heads * 3 * hd, C)
-    b3 = torch.stack([bq.float(), bkv[:C].float(), bkv[C:].float()], 0)
-    bias = (b3.view(3, heads, hd) * sc.view(3, 1, 1)).permute(1, 0, 2).reshape(-1)
+    w3 = torch.cat([wq.float() * scale, wkv.float()], 0)                          # (3C, C): q (scaled) | k | v
+    wcat = w3.view(3, heads, hd, C).permute(1, 0, 2, 3).reshape(heads * 3 * hd, C)
+    b3 = torch.cat([bq.float() * scale, bkv.float()], 0)
+    bias = b3.view(3, heads, hd).permute(1, 0, 2).reshape(-1)
     img = pack_kmajor(wcat, 3 * hd, "nk")                       # [heads][KB][3hd*64]
     return img, bias.contiguous()                               # bias (heads*3*hd,)
 
