@@ -200,3 +200,20 @@ def test_hardware_probes():
         pytest.skip("probe binary not built (run __graft_entry__.build())")
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120).stdout
     assert "PROBE OK" in out, out[-2000:]
+
+
+def test_restore_arbitrary_resolution():
+    """BASELINE configs[3] host path (test/test_sidd.py:79-108): a 300x260 image through a model built for 128x128 —
+    zero-padded to 384x384 (token maps 384, 192, 96, 48, 24: none a power of two), valid region cut out, clamped."""
+    import uformer_b200 as U
+    g = load_golden("uformer_t1_128")
+    net, st = build_module(g)
+    net = net.to(DEV)
+    torch.manual_seed(9)
+    noisy = torch.rand(1, 3, 300, 260)
+    out = U.restore_image(net, noisy.to(DEV), factor=128).float().cpu()
+    padded, mask = U.expand2square(noisy, factor=128)
+    assert padded.shape[-1] == 384
+    ref = oracle_run(g, st, padded)
+    want = torch.masked_select(ref, mask.bool()).reshape(1, 3, 300, 260).clamp(0, 1)
+    _check(out, want, "restore 300x260 via 384x384")

@@ -117,3 +117,33 @@ def test_reference_model_with_engine_installed_through_contract_model():
         assert rel_l2(y, g["y"]) < TOL
     finally:
         U.uninstall(m)
+
+
+def test_arbitrary_resolution_restore_through_contract_model():
+    """BASELINE configs[3]: model built for 128x128 restores a 200x150 image (padded to 256x256 by expand2square,
+    test/test_sidd.py:79-108); compared with the reference's own model driven by the reference's own host code when it
+    is mounted, else with the oracle forward on the padded image."""
+    from refshim import import_reference_model, reference_available
+    g = load_golden("uformer_t1_128")
+    net, st = build_module(g)
+    torch.manual_seed(3)
+    noisy = torch.rand(1, 3, 200, 150)
+    padded, mask = U.expand2square(noisy, factor=128)
+    assert padded.shape == (1, 3, 256, 256) and int(mask.sum()) == 200 * 150
+    assert torch.equal(torch.masked_select(padded, mask.bool()).reshape(1, 3, 200, 150), noisy)
+    with KM.patched():
+        out = U.restore_image(net, noisy, factor=128)
+    assert out.shape == noisy.shape and out.min() >= 0 and out.max() <= 1
+    if reference_available():
+        m = import_reference_model()
+        ref_net = m.Uformer(**g["cfg"])
+        ref_net.load_state_dict(st, strict=True)
+        ref_net.eval()
+        with torch.no_grad():
+            r = ref_net(padded)
+    else:
+        from oracle import lewin_oracle as O
+        c = g["cfg"]
+        r = O.uformer_forward(padded, st, c["img_size"], c["embed_dim"], c["depths"], win_size=c["win_size"])
+    want = torch.masked_select(r, mask.bool()).reshape(1, 3, 200, 150).clamp(0, 1)
+    assert rel_l2(out, want) < TOL

@@ -12,11 +12,12 @@ rebind the `Downsample` / `Upsample` globals, because the originals' `super(Down
 """
 from .modules import (Downsample, DropPath, EngineUnavailable, LeFF, LeWinTransformerBlock, LinearProjection,  # noqa: F401
                       Upsample, WindowAttention)
+from .inference import expand2square, restore_image  # noqa: F401
 from .network import GraphedForward, InputProj, LeWinStage, OutputProj, Uformer  # noqa: F401
 from .training import CharbonnierLoss, FlatAdamW, FlatArena, GradReducer, TrainStep  # noqa: F401
 
 __all__ = ["install", "uninstall", "LeWinTransformerBlock", "WindowAttention", "LeFF", "Downsample", "Upsample", "Uformer",
-           "EngineUnavailable", "TrainStep", "CharbonnierLoss", "FlatAdamW", "FlatArena", "GradReducer"]
+           "EngineUnavailable", "restore_image", "expand2square", "TrainStep", "CharbonnierLoss", "FlatAdamW", "FlatArena", "GradReducer"]
 
 _SAVED = {}
 
