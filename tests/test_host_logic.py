@@ -122,3 +122,30 @@ def test_pack_roundtrip_property():
         assert img.float().abs().sum().item() == pytest.approx(w.abs().sum().item(), rel=1e-6)
 
     run()
+
+
+def test_batched_prepack_is_bit_identical_to_lazy_packing():
+    """uformer_b200.prepack.prepack(net): one permutation per (stage, weight kind) == per-module packing, and the
+    modules' caches are hit afterwards."""
+    from uformer_b200 import modules as M
+    from uformer_b200.prepack import prepack
+    from paramgen import randomize_state
+    for cfg in [dict(img_size=128, embed_dim=16, depths=[2, 1, 2, 1, 2, 1, 2, 1, 2], win_size=8, modulator=True),
+                dict(img_size=128, embed_dim=32, depths=[1, 2, 1, 1, 1, 1, 1, 2, 1], win_size=8, modulator=True)]:
+        net = uformer_b200.Uformer(**cfg)
+        net.load_state_dict(randomize_state(net.state_dict(), 11))
+        mods = [m for m in net.modules() if hasattr(m, "packed")]
+        lazy = [{k: (v.clone() if torch.is_tensor(v) else v) for k, v in m.packed().items()} for m in mods]
+        M.invalidate_packed()
+        assert prepack(net) == sum(cfg["depths"]) + 8
+        for m, want in zip(mods, lazy):
+            key_before = m._cache._key
+            got = m.packed()
+            assert m._cache._key == key_before                      # cache hit: nothing was rebuilt
+            assert set(got) == set(want), type(m)
+            for k, v in want.items():
+                if torch.is_tensor(v):
+                    assert got[k].shape == v.shape and got[k].dtype == v.dtype and got[k].is_contiguous(), (type(m).__name__, k)
+                    assert torch.equal(got[k], v), (type(m).__name__, k)
+                else:
+                    assert got[k] == v or (got[k] is None and v is None), (type(m).__name__, k)

@@ -67,7 +67,20 @@ def test_train_step_through_contract_model():
         step.optimizer.step(grad_scale=1.0, zero_grad=True)
         assert step.arena.grad.abs().sum() == 0
         n_pack_calls = calls["wmsa"]
-        losses = [loss.item()] + [step(g["x"], g["target"]).item() for _ in range(3)]
+        from uformer_b200 import packing
+        n_perm, orig = [0], packing.pack_kmajor
+
+        def counting(*a, **k):
+            n_perm[0] += 1
+            return orig(*a, **k)
+        packing.pack_kmajor = counting
+        try:
+            losses = [loss.item()] + [step(g["x"], g["target"]).item() for _ in range(3)]
+        finally:
+            packing.pack_kmajor = orig
+        # steps 2 and 3 re-pack through prepack(): 4 GEMM weights per (stage shape) group + 8 samplers, not 4 per block
+        groups = len({(b.dim, b.num_heads) for b in net.modules() if isinstance(b, U.LeWinTransformerBlock)})
+        assert n_perm[0] <= 4 * sum(g["cfg"]["depths"]) + 8 + 3 * (4 * groups + 8), n_perm[0]
         assert calls["wmsa"] > n_pack_calls and calls["adamw_step"] == 4 and calls["charbonnier"] == 4
     print("losses:", losses)
     assert losses[-1] < losses[0] and len({round(v, 7) for v in losses}) == 4      # weights (and their packed images) really moved

@@ -66,13 +66,21 @@ class _PackCache:
         self._key = None
         self._val = None
 
+    @staticmethod
+    def key_for(tensors):
+        return (_WEIGHTS_EPOCH[0],) + tuple((t.data_ptr(), t._version, str(t.device)) for t in tensors if t is not None)
+
     def get(self, tensors, build):
-        key = (_WEIGHTS_EPOCH[0],) + tuple((t.data_ptr(), t._version, str(t.device)) for t in tensors if t is not None)
+        key = self.key_for(tensors)
         if key != self._key:
             with torch.no_grad():
                 self._val = build()
             self._key = key
         return self._val
+
+    def put(self, tensors, value):
+        """Install a value built elsewhere (uformer_b200/prepack.py batches the packing of same-shaped modules)."""
+        self._key, self._val = self.key_for(tensors), value
 
 
 def _as_bf16(x):
@@ -140,9 +148,13 @@ class WindowAttention(nn.Module):
         self._cache = _PackCache()
 
     # ---- packing -------------------------------------------------------------------------------
+    def pack_sources(self):
+        q, kv, pr = self.qkv.to_q, self.qkv.to_kv, self.proj
+        return [q.weight, q.bias, kv.weight, kv.bias, pr.weight, pr.bias, self.relative_position_bias_table]
+
     def packed(self):
         q, kv, pr = self.qkv.to_q, self.qkv.to_kv, self.proj
-        srcs = [q.weight, q.bias, kv.weight, kv.bias, pr.weight, pr.bias, self.relative_position_bias_table]
+        srcs = self.pack_sources()
 
         def build():
             C = self.dim
@@ -203,9 +215,13 @@ class LeFF(nn.Module):
         self.eca = nn.Identity()
         self._cache = _PackCache()
 
+    def pack_sources(self):
+        l1, dw, l2 = self.linear1[0], self.dwconv[0], self.linear2[0]
+        return [l1.weight, l1.bias, dw.weight, dw.bias, l2.weight, l2.bias]
+
     def packed(self):
         l1, dw, l2 = self.linear1[0], self.dwconv[0], self.linear2[0]
-        srcs = [l1.weight, l1.bias, dw.weight, dw.bias, l2.weight, l2.bias]
+        srcs = self.pack_sources()
 
         def build():
             wd, bd = packing.pack_dwconv(dw.weight, dw.bias)

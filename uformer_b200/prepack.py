@@ -1,0 +1,76 @@
+"""Batched re-packing of a whole network's operand images.
+
+A training step invalidates every packed weight image (the optimizer rewrites the parameter arena), and building
+them lazily costs ~6 tiny torch launches per weight x ~200 weights = 26 ms per Uformer-B step, twice the native
+forward (profiles/r01d_train_probe.json).  Blocks of one stage have identical shapes, so their weights are stacked
+and permuted together: one `pack_kmajor` per (stage, weight kind) instead of one per block.  The images are
+bit-identical to the lazily built ones (tests/test_host_logic.py) and are installed into the modules' pack caches.
+"""
+from __future__ import annotations
+
+from collections import defaultdict
+
+import torch
+
+from . import _lib, packing
+from .modules import Downsample, LeWinTransformerBlock, Upsample
+
+
+@torch.no_grad()
+def prepack(net: torch.nn.Module) -> int:
+    """Rebuild and cache the packed parameters of every engine module under `net`; returns the number of modules."""
+    groups = defaultdict(list)
+    n = 0
+    for m in net.modules():
+        if isinstance(m, LeWinTransformerBlock):
+            a = m.attn
+            key = (m.dim, m.num_heads, m.mlp.hidden_dim, float(a.scale), a.qkv.to_q.bias is not None, a.qkv.to_kv.bias is not None,
+                   str(a.proj.weight.device))
+            groups[key].append(m)
+        elif isinstance(m, (Downsample, Upsample)):
+            m.packed()                              # four of each, all different shapes: nothing to batch
+            n += 1
+    for blks in groups.values():
+        _pack_blocks(blks)
+        n += len(blks)
+    return n
+
+
+def _pack_blocks(blks):
+    b0 = blks[0]
+    nb, C, heads, hid = len(blks), b0.dim, b0.num_heads, b0.mlp.hidden_dim
+    hd = C // heads
+    dev = b0.attn.proj.weight.device
+    scale = float(b0.attn.scale)
+
+    def stack(get):
+        return torch.stack([get(b).detach().float() for b in blks], 0)
+
+    # ---- attention: per-head [q*scale | k | v] row blocks (packing.pack_qkv), proj, bias table ----
+    zeros_c, zeros_2c = torch.zeros(C, device=dev), torch.zeros(2 * C, device=dev)
+    wq = stack(lambda b: b.attn.qkv.to_q.weight)                                        # (nb, C, C)
+    wkv = stack(lambda b: b.attn.qkv.to_kv.weight)                                      # (nb, 2C, C)
+    bq = stack(lambda b: b.attn.qkv.to_q.bias if b.attn.qkv.to_q.bias is not None else zeros_c)
+    bkv = stack(lambda b: b.attn.qkv.to_kv.bias if b.attn.qkv.to_kv.bias is not None else zeros_2c)
+    w3 = torch.cat([wq * scale, wkv], 1)                                                # (nb, 3C, C): q | k | v
+    wcat = w3.view(nb, 3, heads, hd, C).permute(0, 2, 1, 3, 4).reshape(nb * heads * 3 * hd, C)
+    wqkv_img = packing.pack_kmajor(wcat, 3 * hd, "nk").view(nb, heads, -1, 3 * hd * 64)
+    bqkv = torch.cat([bq * scale, bkv], 1).view(nb, 3, heads, hd).permute(0, 2, 1, 3).reshape(nb, -1).contiguous()
+    nchp = min(C, 128)
+    wproj_img = packing.pack_kmajor(stack(lambda b: b.attn.proj.weight).view(nb * C, C), nchp, "nk").view(nb, C // nchp, -1, nchp * 64)
+    relpos = stack(lambda b: b.attn.relative_position_bias_table).transpose(1, 2).contiguous()          # (nb, heads, 225)
+    # ---- LeFF: linear1 (A-resident, "nk"), depthwise taps, linear2 (A-streamed, "kn") ----
+    nch1 = _lib.load().lw_nch_ares(C, hid)
+    w1_img = packing.pack_kmajor(stack(lambda b: b.mlp.linear1[0].weight).view(nb * hid, C), nch1, "nk").view(nb, hid // nch1, -1, nch1 * 64)
+    w2_nk = packing.pack_kmajor(stack(lambda b: b.mlp.linear2[0].weight).view(nb * C, hid), nchp, "nk").view(nb, C // nchp, -1, nchp * 64)
+    w2_img = w2_nk.permute(0, 2, 1, 3).contiguous()                                     # per block [KB][C/nch][nch*64]
+    wd = stack(lambda b: b.mlp.dwconv[0].weight).view(nb, hid, 9).transpose(1, 2).contiguous()          # (nb, 9, hid)
+
+    for i, b in enumerate(blks):
+        a, m = b.attn, b.mlp
+        a._cache.put(a.pack_sources(), dict(wqkv_img=wqkv_img[i], bqkv=bqkv[i], wproj_img=wproj_img[i],
+                                            bproj=a.proj.bias.detach().float().contiguous(), relpos=relpos[i], head_dim=hd))
+        m._cache.put(m.pack_sources(), dict(w1_img=w1_img[i], b1=m.linear1[0].bias.detach().float().contiguous(), wd=wd[i],
+                                            bd=m.dwconv[0].bias.detach().float().contiguous(), w2_img=w2_img[i],
+                                            b2=m.linear2[0].bias.detach().float().contiguous(), hidden=hid))
+        b.packed()                                  # LN affine / modulator: fp32 views of the parameters, no launches

@@ -27,6 +27,7 @@ import torch.distributed as dist
 import torch.nn as nn
 
 from . import modules, ops
+from .prepack import prepack
 from ._lib import EngineUnavailable
 
 Tensor = torch.Tensor
@@ -243,8 +244,9 @@ class TrainStep:
     """
 
     def __init__(self, net: nn.Module, lr: float = 2e-4, weight_decay: float = 0.02, betas=(0.9, 0.999), eps: float = 1e-8,
-                 process_group=None, bucket_bytes: int = 32 << 20, criterion: nn.Module | None = None):
+                 process_group=None, bucket_bytes: int = 32 << 20, criterion: nn.Module | None = None, batched_repack: bool = True):
         self.net = net
+        self.batched_repack = batched_repack
         params = execution_ordered_parameters(net)[::-1]                 # reverse execution order
         self.arena = FlatArena(params)
         self.reducer = GradReducer(self.arena, process_group, bucket_bytes)
@@ -260,6 +262,8 @@ class TrainStep:
         loss.backward()
         self.reducer.finish()
         self.optimizer.step(grad_scale=1.0 / self.world, zero_grad=True)
+        if self.batched_repack:
+            prepack(self.net)                # one permutation per (stage, weight kind) instead of ~6 launches per weight
         return loss.detach()
 
 
