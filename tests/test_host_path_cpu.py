@@ -160,3 +160,61 @@ def test_arbitrary_resolution_restore_through_contract_model():
         r = O.uformer_forward(padded, st, c["img_size"], c["embed_dim"], c["depths"], win_size=c["win_size"])
     want = torch.masked_select(r, mask.bool()).reshape(1, 3, 200, 150).clamp(0, 1)
     assert rel_l2(out, want) < TOL
+
+
+def test_reference_training_loop_with_engine_installed_through_contract_model():
+    """Drop-in for the training script: the REFERENCE's Uformer class, built on the engine's modules by
+    install(), trained by TrainStep — its own InputProj/OutputProj/BasicUformerLayer code drives our blocks under autograd.
+    The first step's gradients are compared with the golden produced by the unmodified reference."""
+    from refshim import import_reference_model, reference_available
+    from uformer_b200.training import TrainStep
+    if not reference_available():
+        pytest.skip("reference not mounted")
+    m = import_reference_model()
+    g = load_golden("train_t2_128")
+    U.install(m)
+    try:
+        net = m.Uformer(**g["cfg"])
+        net.load_state_dict(randomize_state(net.state_dict(), g["seed"]), strict=True)
+        with KM.patched() as calls:
+            step = TrainStep(net, lr=2e-4, weight_decay=0.0)
+            net.train()
+            loss = step.criterion(net(g["x"]), g["target"])
+            loss.backward()
+            assert calls["wmsa"] == sum(g["cfg"]["depths"]) and calls["input_proj"] == 0       # the reference's own projections ran
+            got = torch.cat([p.grad.reshape(-1)[::g["grads"][k]["stride"]] for k, p in net.named_parameters()])
+            want = torch.cat([g["grads"][k]["sample"] for k, _ in net.named_parameters()])
+            assert abs(loss.item() - g["loss"]) < 2e-2 * g["loss"] and rel_l2(got, want) < 5e-2
+            step.optimizer.step(zero_grad=True)
+            l2 = step(g["x"], g["target"]).item()
+            l3 = step(g["x"], g["target"]).item()
+        assert l3 < l2 < loss.item()
+    finally:
+        U.uninstall(m)
+
+
+def test_train_step_checkpoint_resume_through_contract_model():
+    """state_dict()/load_state_dict(): 2 steps + save + 2 steps == restore into a fresh TrainStep + 2 steps, bit for bit."""
+    from uformer_b200.training import TrainStep
+    cfg = dict(img_size=128, embed_dim=16, depths=[1] * 9, win_size=8, modulator=True, drop_path_rate=0.0)
+    torch.manual_seed(0)
+    x, t = torch.rand(1, 3, 128, 128), torch.rand(1, 3, 128, 128)
+
+    def fresh():
+        net = U.Uformer(**cfg)
+        net.load_state_dict(randomize_state(net.state_dict(), 2), strict=True)
+        return net, TrainStep(net, lr=1e-4)
+    with KM.patched():
+        net, ts = fresh()
+        for _ in range(2):
+            ts(x, t)
+        ck = ts.state_dict()
+        assert set(ck["state_dict"]) == set(net.state_dict())          # the reference's checkpoint keys
+        cont = [ts(x, t).item() for _ in range(2)]
+        net2, ts2 = fresh()
+        ts2.load_state_dict(ck)
+        assert ts2.optimizer.steps == 2
+        resumed = [ts2(x, t).item() for _ in range(2)]
+    assert resumed == cont
+    for a, b in zip(net.parameters(), net2.parameters()):
+        assert torch.equal(a, b)

@@ -266,6 +266,25 @@ class TrainStep:
             prepack(self.net)                # one permutation per (stage, weight kind) instead of ~6 launches per weight
         return loss.detach()
 
+    # ---- checkpoint / resume (the reference saves {'epoch', 'state_dict', 'optimizer'}, train_denoise.py:222-236) ----
+    def state_dict(self):
+        """Model weights under the reference's key names (parameters are views of the arena, so this is a snapshot of
+        it in checkpoint layout) + the optimizer moments in arena layout."""
+        return dict(state_dict={k: v.detach().clone() for k, v in self.net.state_dict().items()},
+                    optimizer={k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in self.optimizer.state_dict().items()})
+
+    def load_state_dict(self, st):
+        with torch.no_grad():
+            own = self.net.state_dict()
+            missing = set(own) ^ set(st["state_dict"])
+            if missing:
+                raise KeyError(f"checkpoint / model key mismatch: {sorted(missing)[:5]}")
+            for k, v in st["state_dict"].items():
+                own[k].copy_(v)                                      # in place: the arena views stay intact
+        self.optimizer.load_state_dict(st["optimizer"])
+        self.arena.zero_grad()
+        modules.invalidate_packed()
+
 
 __all__ = ["FlatArena", "GradReducer", "FlatAdamW", "CharbonnierLoss", "TrainStep", "mixup",
            "execution_ordered_parameters", "EngineUnavailable"]
