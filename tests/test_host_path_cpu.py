@@ -218,3 +218,14 @@ def test_train_step_checkpoint_resume_through_contract_model():
     assert resumed == cont
     for a, b in zip(net.parameters(), net2.parameters()):
         assert torch.equal(a, b)
+
+
+def test_smoke_host_logic_through_contract_model(capsys):
+    """__graft_entry__.smoke() is what the driver runs on the B200 before the bench; its host logic (oracle calls,
+    tolerances, arena / optimizer plumbing) is exercised here on CPU with the kernel model standing in."""
+    import __graft_entry__ as ge
+    with KM.patched() as calls:
+        ge.smoke(device="cpu")
+    assert "smoke: ok" in capsys.readouterr().out
+    assert calls["wmsa"] >= 2 and calls["leff"] >= 2 and calls["downsample"] == 1 and calls["upsample"] == 1
+    assert calls["charbonnier"] == 1 and calls["adamw_step"] == 1
