@@ -314,6 +314,16 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
 
+    lib = os.path.join(ROOT, "uformer_b200", "lib", "liblewin_b200.so")
+    if args.impl != "reference" and not os.path.isfile(lib):
+        if local == 0:                       # the .so is git-ignored: build it in-tree if this checkout lacks it
+            note("native library missing; building it (nvcc, ~30 s)")
+            import __graft_entry__
+            __graft_entry__.build()
+        else:
+            while not os.path.isfile(lib):
+                time.sleep(1.0)
+            time.sleep(2.0)
     if args.impl == "reference":
         if args.mode == "train":
             run_reference_train(args, rank)

@@ -217,3 +217,31 @@ def test_restore_arbitrary_resolution():
     ref = oracle_run(g, st, padded)
     want = torch.masked_select(ref, mask.bool()).reshape(1, 3, 300, 260).clamp(0, 1)
     _check(out, want, "restore 300x260 via 384x384")
+
+
+def test_block_batch_permutation_property_full_size():
+    """No op on the path couples images, so a LeWin block commutes with permuting the batch — checked
+    bit-exactly at BASELINE config #2's largest stage (enc0: batch 32, 256x256 tokens, C=32; 2.1 M tokens)."""
+    import uformer_b200 as U
+    torch.manual_seed(3)
+    blk = U.LeWinTransformerBlock(32, (256, 256), 1, win_size=8, shift_size=0).to(DEV).eval()
+    x = torch.randn(32, 256 * 256, 32, device=DEV).to(torch.bfloat16)
+    perm = torch.randperm(32, device=DEV)
+    with torch.no_grad():
+        a = blk(x)[perm]
+        b = blk(x[perm].contiguous())
+    assert torch.isfinite(a.float()).all()
+    assert torch.equal(a, b)
+
+
+def test_downsample_linearity_property_full_size():
+    """Downsample is affine: f(x+y) + f(0) == f(x) + f(y) up to bf16 rounding, at enc0 -> enc1 of config #2 (batch 8)."""
+    import uformer_b200 as U
+    torch.manual_seed(4)
+    mod = U.Downsample(32, 64).to(DEV).eval()
+    x = torch.randn(8, 256 * 256, 32, device=DEV).to(torch.bfloat16)
+    y = torch.randn(8, 256 * 256, 32, device=DEV).to(torch.bfloat16)
+    with torch.no_grad():
+        lhs = mod(x + y).float() + mod(torch.zeros_like(x)).float()
+        rhs = mod(x).float() + mod(y).float()
+    assert (lhs - rhs).abs().max() < 0.05 * rhs.abs().max()
