@@ -139,9 +139,9 @@ def test_batched_prepack_is_bit_identical_to_lazy_packing():
         M.invalidate_packed()
         assert prepack(net) == sum(cfg["depths"]) + 8
         for m, want in zip(mods, lazy):
-            key_before = m._cache._key
+            key_before = m._cache._entry[0]
             got = m.packed()
-            assert m._cache._key == key_before                      # cache hit: nothing was rebuilt
+            assert m._cache._entry[0] == key_before                      # cache hit: nothing was rebuilt
             assert set(got) == set(want), type(m)
             for k, v in want.items():
                 if torch.is_tensor(v):

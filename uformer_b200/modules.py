@@ -60,11 +60,12 @@ def invalidate_packed():
 
 
 class _PackCache:
-    """Packed-parameter cache: recomputed when any source tensor is replaced or modified in place."""
+    """Packed-parameter cache: recomputed when any source tensor is replaced or modified in place.  The (key, value)
+    pair is one attribute read/written atomically: nn.DataParallel replicas (train/train_denoise.py:83) share this
+    object across threads and devices, and a replica must never pick up another replica's value."""
 
     def __init__(self):
-        self._key = None
-        self._val = None
+        self._entry = (None, None)
 
     @staticmethod
     def key_for(tensors):
@@ -72,15 +73,16 @@ class _PackCache:
 
     def get(self, tensors, build):
         key = self.key_for(tensors)
-        if key != self._key:
+        k, v = self._entry
+        if k != key:
             with torch.no_grad():
-                self._val = build()
-            self._key = key
-        return self._val
+                v = build()
+            self._entry = (key, v)
+        return v
 
     def put(self, tensors, value):
         """Install a value built elsewhere (uformer_b200/prepack.py batches the packing of same-shaped modules)."""
-        self._key, self._val = self.key_for(tensors), value
+        self._entry = (self.key_for(tensors), value)
 
 
 def _as_bf16(x):
