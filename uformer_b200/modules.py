@@ -409,7 +409,11 @@ class LeWinTransformerBlock(nn.Module):
             a1, a2, m = split(rest)
             return restated.lewin_block(self, t, m, a1, a2)
 
-        res = _run(self, native, restate, acts)
+        named = [(k, p) for k, p in self.named_parameters() if p.requires_grad]
+        if autograd.explicit_block_backward() and autograd.wants_grad(xb, *[p for _, p in named]):
+            res = autograd.BlockFn.apply(native, self, (has_dp, has_mask), tuple(k for k, _ in named), *acts, *[p for _, p in named])
+        else:
+            res = _run(self, native, restate, acts)
         return res if back is None else res.to(back)
 
     def flops(self):
