@@ -49,15 +49,11 @@ class NativeFn(torch.autograd.Function):
         with torch.enable_grad(), torch.autocast(device_type=dev, dtype=torch.bfloat16, enabled=amp):
             out = ctx.restate(*acts)
         wrt = [a for a in acts if a.requires_grad] + [p for i, p in enumerate(params) if need[n_act + i]]
-        grads = list(torch.autograd.grad(out, wrt, g.to(out.dtype), allow_unused=True))
-        res = []
-        for i, a in enumerate(acts):
-            res.append(grads.pop(0) if a.requires_grad else None)
-        for i, p in enumerate(params):
-            res.append(grads.pop(0) if need[n_act + i] else None)
-        for i, t in enumerate(tensors):                     # gradient dtype must match the input's
-            if res[i] is not None and res[i].dtype != t.dtype:
-                res[i] = res[i].to(t.dtype)
+        grads = torch.autograd.grad(out, wrt, g.to(out.dtype), allow_unused=True)
+        it = iter(grads)
+        res = [next(it) if a.requires_grad else None for a in acts]
+        res += [next(it) if need[n_act + i] else None for i in range(len(params))]
+        res = [r if r is None or r.dtype == t.dtype else r.to(t.dtype) for r, t in zip(res, tensors)]   # match input dtypes
         return (None, None, None, *res)
 
 
