@@ -97,9 +97,10 @@ def _as_bf16(x):
 def _run(mod, native, restate, acts):
     """Native forward of `mod`; under autograd the same call is wrapped so that backward recomputes it from `acts`."""
     _lib.require_device(acts[0].device)         # device check first: no CPU fallback, fail loudly
-    params = [p for p in mod.parameters() if p.requires_grad]
-    if autograd.wants_grad(*acts, *params):
-        return autograd.apply(native, restate, acts, params)
+    if torch.is_grad_enabled():                 # (inference runs under no_grad: skip the parameter walk entirely)
+        params = [p for p in mod.parameters() if p.requires_grad]
+        if autograd.wants_grad(*acts, *params):
+            return autograd.apply(native, restate, acts, params)
     return native(*acts)
 
 
@@ -155,18 +156,16 @@ class WindowAttention(nn.Module):
         return [q.weight, q.bias, kv.weight, kv.bias, pr.weight, pr.bias, self.relative_position_bias_table]
 
     def packed(self):
-        q, kv, pr = self.qkv.to_q, self.qkv.to_kv, self.proj
         srcs = self.pack_sources()
 
         def build():
+            wq, bq, wkv, bkv, wp, bp, table = srcs
             C = self.dim
-            dev = q.weight.device
-            bq = q.bias if q.bias is not None else torch.zeros(C, device=dev)
-            bkv = kv.bias if kv.bias is not None else torch.zeros(2 * C, device=dev)
-            wimg, bqkv = packing.pack_qkv(q.weight, bq, kv.weight, bkv, self.num_heads, float(self.scale))
-            return dict(wqkv_img=wimg, bqkv=bqkv, wproj_img=packing.pack_kmajor(pr.weight, min(C, 128), "nk"),
-                        bproj=pr.bias.float().contiguous(), relpos=packing.pack_relpos(self.relative_position_bias_table),
-                        head_dim=C // self.num_heads)
+            bq_ = bq if bq is not None else torch.zeros(C, device=wq.device)
+            bkv_ = bkv if bkv is not None else torch.zeros(2 * C, device=wq.device)
+            wimg, bqkv = packing.pack_qkv(wq, bq_, wkv, bkv_, self.num_heads, float(self.scale))
+            return dict(wqkv_img=wimg, bqkv=bqkv, wproj_img=packing.pack_kmajor(wp, min(C, 128), "nk"),
+                        bproj=bp.float().contiguous(), relpos=packing.pack_relpos(table), head_dim=C // self.num_heads)
         return self._cache.get(srcs, build)
 
     def _check_supported(self):
@@ -222,14 +221,14 @@ class LeFF(nn.Module):
         return [l1.weight, l1.bias, dw.weight, dw.bias, l2.weight, l2.bias]
 
     def packed(self):
-        l1, dw, l2 = self.linear1[0], self.dwconv[0], self.linear2[0]
         srcs = self.pack_sources()
 
         def build():
-            wd, bd = packing.pack_dwconv(dw.weight, dw.bias)
-            return dict(w1_img=packing.pack_kmajor(l1.weight, _lib.load().lw_nch_ares(self.dim, self.hidden_dim), "nk"), b1=l1.bias.float().contiguous(),
-                        wd=wd, bd=bd, w2_img=packing.pack_kmajor(l2.weight, min(self.dim, 128), "kn"),
-                        b2=l2.bias.float().contiguous(), hidden=self.hidden_dim)
+            w1, b1, wdw, bdw, w2, b2 = srcs
+            wd, bd = packing.pack_dwconv(wdw, bdw)
+            return dict(w1_img=packing.pack_kmajor(w1, _lib.load().lw_nch_ares(self.dim, self.hidden_dim), "nk"), b1=b1.float().contiguous(),
+                        wd=wd, bd=bd, w2_img=packing.pack_kmajor(w2, min(self.dim, 128), "kn"),
+                        b2=b2.float().contiguous(), hidden=self.hidden_dim)
         return self._cache.get(srcs, build)
 
     def _check_supported(self):
@@ -299,7 +298,7 @@ class Upsample(nn.Module):
         B, L, _ = x.shape
         H = int(math.sqrt(L))
         xb, back = _as_bf16(x)
-        if out is not None and autograd.wants_grad(xb, *self.parameters()):
+        if out is not None and torch.is_grad_enabled() and autograd.wants_grad(xb, *self.parameters()):
             raise ValueError("Upsample(out=...) writes in place and cannot be recorded by autograd; call it without `out`")
         res = _run(self, lambda t: ops.upsample(t, self.packed(), B=B, H=H, W=H, out=out), lambda t: restated.upsample(self, t), [xb])
         return res if back is None else res.to(back)
@@ -409,10 +408,12 @@ class LeWinTransformerBlock(nn.Module):
             a1, a2, m = split(rest)
             return restated.lewin_block(self, t, m, a1, a2)
 
-        named = [(k, p) for k, p in self.named_parameters() if p.requires_grad]
-        if autograd.explicit_block_backward() and autograd.wants_grad(xb, *[p for _, p in named]):
-            res = autograd.BlockFn.apply(native, self, (has_dp, has_mask), tuple(k for k, _ in named), *acts, *[p for _, p in named])
-        else:
+        res = None
+        if autograd.explicit_block_backward() and torch.is_grad_enabled():
+            named = [(k, p) for k, p in self.named_parameters() if p.requires_grad]
+            if autograd.wants_grad(xb, *[p for _, p in named]):
+                res = autograd.BlockFn.apply(native, self, (has_dp, has_mask), tuple(k for k, _ in named), *acts, *[p for _, p in named])
+        if res is None:
             res = _run(self, native, restate, acts)
         return res if back is None else res.to(back)
 
