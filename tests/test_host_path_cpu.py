@@ -229,3 +229,30 @@ def test_smoke_host_logic_through_contract_model(capsys):
     assert "smoke: ok" in capsys.readouterr().out
     assert calls["wmsa"] >= 2 and calls["leff"] >= 2 and calls["downsample"] == 1 and calls["upsample"] == 1
     assert calls["charbonnier"] == 1 and calls["adamw_step"] == 1
+
+
+@pytest.mark.parametrize("dim,heads", [(16, 1), (32, 1), (32, 2), (64, 2), (64, 4), (128, 4), (128, 8), (256, 8), (256, 16), (512, 16)])
+def test_every_supported_channel_count_through_contract_model(dim, heads):
+    """Operand-image packing for every (C, head_dim in {16, 32}) the kernels are instantiated for: block through the
+    contract model (which decodes the images) == oracle on the raw weights."""
+    from oracle import lewin_oracle as O
+    shift = 4 if dim % 64 == 0 else 0
+    blk = U.LeWinTransformerBlock(dim, (16, 16), heads, win_size=8, shift_size=shift, modulator=dim >= 64).eval()
+    st = randomize_state(blk.state_dict(), dim + heads)
+    blk.load_state_dict(st)
+    x = torch.randn(2, 256, dim).to(torch.bfloat16)
+    with KM.patched(), torch.no_grad():
+        y = blk(x).float()
+    ref = O.lewin_block(x.float(), st, "", heads, 8, shift)
+    assert rel_l2(y, ref) < TOL, (dim, heads, rel_l2(y, ref))
+    for m, cin, cout in [(U.Downsample, dim, 2 * dim), (U.Upsample, dim, dim // 2)]:
+        if cout > 512 or cout < 8:
+            continue
+        mod = m(cin, cout).eval()
+        sm = randomize_state(mod.state_dict(), 1)
+        mod.load_state_dict(sm)
+        with KM.patched(), torch.no_grad():
+            z = mod(x).float()
+        want = O.downsample(x.float(), sm["conv.0.weight"], sm["conv.0.bias"]) if m is U.Downsample else \
+            O.upsample(x.float(), sm["deconv.0.weight"], sm["deconv.0.bias"])
+        assert rel_l2(z, want) < TOL, (m.__name__, cin, cout)
