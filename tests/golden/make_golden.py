@@ -97,7 +97,30 @@ def main():
     x = torch.rand(1, 3, 128, 128)
     out["uformer_s2_128"] = dict(kind="model", cfg=cfg3, seed=5, x=x, y=net(x), checksum=state_checksum(st))
 
+    # ---- the flagship: Uformer-B 256x256 (BASELINE configs[1]; utils/model_utils.py:76-78), one image ----
+    # (a) the bench's weights (seed 1234, O(1) activations through all 40 blocks): after 40 blocks even the reference's
+    #     own bf16-autocast forward is ~1.3e-2 away from its fp32 forward, so that error is recorded as the yardstick;
+    # (b) the same weights scaled by 0.5 (residual branch ~0.1, like a trained denoiser): plain 1e-2 bound.
+    cfgb = dict(img_size=256, embed_dim=32, win_size=8, token_projection="linear", token_mlp="leff", depths=[1, 2, 8, 8, 2, 8, 8, 2, 1],
+                modulator=True, dd_in=3)
+    x = torch.rand(1, 3, 256, 256)
+    for name, gain in [("uformer_b_256", 1.0), ("uformer_b_256_g05", 0.5)]:
+        net = m.Uformer(**cfgb)
+        st = randomize_state(net.state_dict(), 1234, gain)
+        net.load_state_dict(st, strict=True)
+        net.eval()
+        y = net(x)
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            yb = net(x).float()
+        rl2 = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm())   # noqa: E731
+        out[name] = dict(kind="model", cfg=cfgb, seed=1234, gain=gain, x=x, y=y, checksum=state_checksum(st),
+                         ref_bf16=dict(full=rl2(yb, y), resid=rl2(yb - x, y - x)))
+        print(name, "reference bf16-autocast vs fp32:", out[name]["ref_bf16"])
+
+    only = os.environ.get("GOLDEN_ONLY")
     for k, v in out.items():
+        if only and not k.startswith(only):
+            continue
         path = os.path.join(HERE, k + ".pt")
         torch.save(v, path)
         print("%-28s %8.1f KB" % (k, os.path.getsize(path) / 1024))

@@ -60,9 +60,21 @@ def build_module(g):
         mod = U.Uformer(**g["cfg"])
     else:
         raise KeyError(kind)
-    st = randomize_state(mod.state_dict(), g["seed"])
+    st = randomize_state(mod.state_dict(), g["seed"], g.get("gain", 1.0))
     mod.load_state_dict(st, strict=True)
     return mod.eval(), st
+
+
+def model_tolerances(g):
+    """(full-output, residual-branch) rel-L2 bounds for a whole-model fixture.  north_star's 1e-2 (bf16) applies to the
+    output; the residual branch out - x gets 2x (the identity term hides error).  Fixtures that record the
+    reference's OWN bf16-autocast error (the flagship model with O(1)-activation weights, where that error exceeds 1e-2
+    after 40 blocks) are bounded by 1.25x that error instead: the engine must not be noisier than the reference in bf16."""
+    full, resid = TOL_BF16, 2 * TOL_BF16
+    if "ref_bf16" in g:
+        full = max(full, 1.25 * g["ref_bf16"]["full"])
+        resid = max(resid, 1.25 * g["ref_bf16"]["resid"])
+    return full, resid
 
 
 def oracle_run(g, st, x, dtype=torch.float32, mask=None):

@@ -256,3 +256,22 @@ def test_every_supported_channel_count_through_contract_model(dim, heads):
         want = O.downsample(x.float(), sm["conv.0.weight"], sm["conv.0.bias"]) if m is U.Downsample else \
             O.upsample(x.float(), sm["deconv.0.weight"], sm["deconv.0.bias"])
         assert rel_l2(z, want) < TOL, (m.__name__, cin, cout)
+
+
+@pytest.mark.parametrize("name", ["uformer_b_256", "uformer_b_256_g05"])
+def test_flagship_model_through_contract_model(name):
+    """Uformer-B 256x256 (BASELINE configs[1], the bench's architecture; (a) the bench's weights, (b) scaled to a
+    denoiser-like small residual branch) through the contract model with bf16 HBM round trips modelled: predicts the
+    GPU's parity error (on uformer_t2_128 the model says 7.3e-3, the B200 measured 7.7e-3) and is held to the same
+    bounds as the GPU test (helpers.model_tolerances)."""
+    from helpers import model_tolerances
+    g = load_golden(name)
+    net, _ = build_module(g)
+    with KM.patched():
+        y = net(g["x"])
+    tf, tr = model_tolerances(g)
+    ef, er = rel_l2(y, g["y"]), rel_l2(y - g["x"], g["y"] - g["x"])
+    print(f"{name}: modelled rel-L2 full {ef:.3e} (bound {tf:.3e}), residual branch {er:.3e} (bound {tr:.3e}); "
+          f"reference's own bf16 autocast: {g['ref_bf16']}")
+    assert ef < tf and er < tr
+    assert ef < 1.05 * g["ref_bf16"]["full"] or ef < 5e-3          # not noisier than the reference's own bf16 forward
