@@ -149,3 +149,22 @@ def test_batched_prepack_is_bit_identical_to_lazy_packing():
                     assert torch.equal(got[k], v), (type(m).__name__, k)
                 else:
                     assert got[k] == v or (got[k] is None and v is None), (type(m).__name__, k)
+
+
+def test_bench_reference_arm_contract():
+    """bench.py --impl reference prints exactly one JSON line with the keys the driver reads (metric/unit/config of our
+    arm, impl, cpu_baseline{kind,cores,sample,value}, e2e with zero copy bytes) and does not need a GPU."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "images/sec Uformer-B 256x256 fwd" and d["unit"] == "img/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["gpu_launches"] == 0
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "images" in cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
