@@ -222,7 +222,7 @@ def run_train(args, rank, world, local):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     warm = max(args.warmup, 3)
-    B = args.batch if args.batch != 32 else 8
+    B = args.batch or 8
     net = uformer_b200.Uformer(**UFORMER_B, drop_path_rate=0.1)                  # the reference's default (model.py:1075)
     net.load_state_dict(randomize_state(net.state_dict(), 1234), strict=True)    # same weights on every rank
     net = net.to(dev)
@@ -306,7 +306,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--batch", type=int, default=None, help="images per GPU per step (default: 32 for fwd, 8 for train)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="fwd", choices=["fwd", "train"])
     args = ap.parse_args()
@@ -341,7 +341,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     warm = max(args.warmup, 3)
-    B = args.batch
+    B = args.batch or 32
     net = build_engine(dev)
     torch.manual_seed(1234 + rank)
     x_host = torch.rand(B, 3, 256, 256).pin_memory()
