@@ -181,3 +181,23 @@ def test_training_ops_have_no_cpu_path():
     net = U.Uformer(img_size=128, embed_dim=16, depths=[1] * 9, win_size=8, modulator=True).train()
     with pytest.raises(U.EngineUnavailable):
         net(torch.rand(1, 3, 128, 128))
+
+
+@pytest.mark.skipif(not reference_available(), reason="reference not mounted")
+def test_stochastic_depth_schedule_and_flops_equal_reference():
+    """Per-block drop_path rates (model.py:1093-1095 and the decoder slices :1170-1232) and Uformer.flops() of the engine's
+    own caller equal the reference's for the Uformer-B configuration."""
+    import contextlib
+    import io
+    m = import_reference_model()
+    cfg = dict(img_size=256, embed_dim=32, win_size=8, token_projection="linear", token_mlp="leff", depths=[1, 2, 8, 8, 2, 8, 8, 2, 1],
+               modulator=True, dd_in=3, drop_path_rate=0.1)
+    r, o = m.Uformer(**cfg), U.Uformer(**cfg)
+    stages = ["encoderlayer_0", "encoderlayer_1", "encoderlayer_2", "encoderlayer_3", "conv", "decoderlayer_0", "decoderlayer_1",
+              "decoderlayer_2", "decoderlayer_3"]
+
+    def rates(net):
+        return [round(getattr(b.drop_path, "drop_prob", 0.0), 7) for n in stages for b in getattr(net, n).blocks]
+    assert rates(r) == rates(o) and max(rates(o)) == 0.1
+    with contextlib.redirect_stdout(io.StringIO()):                 # the reference prints per-layer GFLOPs
+        assert r.flops() == o.flops()
