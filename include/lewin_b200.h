@@ -27,6 +27,8 @@ extern "C" {
 #define LW_ERR_NULL (-2)        /* required pointer is NULL */
 #define LW_ERR_CUDA (-3)        /* launch failed; see lw_last_cuda_error() */
 #define LW_ERR_ARCH (-4)        /* device is not sm_100 */
+#define LW_ERR_ALIGN (-5)       /* a pointer read/written with 16-byte vectors or bulk copies is not 16-byte aligned
+                                   (activations, packed images, fp32 per-channel vectors; torch allocations always are) */
 
 typedef void* lw_stream_t;      /* cudaStream_t */
 

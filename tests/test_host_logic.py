@@ -168,3 +168,25 @@ def test_bench_reference_arm_contract():
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "images" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="uses fake device pointers: only meaningful (and safe) where no launch can happen")
+def test_alignment_validation_without_gpu():
+    """Pointers the kernels access with 16-byte vectors / bulk copies must be 16-byte aligned: rejected with LW_ERR_ALIGN
+    before any launch (a DataParallel replica's coalesced parameter views can be 4-byte aligned); 4-byte alignment is
+    enough for the scalar-read tables (bqkv, relpos)."""
+    lib = _lib.load()
+    a = _lib.WmsaArgs()
+    for f in ("x", "out", "wqkv_img", "bqkv", "wproj_img", "bproj", "relpos"):
+        setattr(a, f, 0x10000)
+    a.n_windows, a.windowed, a.C, a.head_dim = 2, 1, 32, 32
+    for f in ("x", "out", "wqkv_img", "wproj_img", "bproj"):
+        setattr(a, f, 0x10004)
+        assert lib.lw_wmsa_fwd(ctypes.byref(a), None) == -5, f
+        setattr(a, f, 0x10000)
+    a.relpos = a.bqkv = 0x10004
+    assert lib.lw_wmsa_fwd(ctypes.byref(a), None) in (0, -3)      # passes validation (-3: no CUDA device in this container)
+    d = _lib.AdamWArgs()
+    d.p, d.g, d.m, d.v, d.n, d.step, d.beta1, d.beta2 = 0x20000, 0x20004, 0x20000, 0x20000, 64, 1, 0.9, 0.999
+    assert lib.lw_adamw_step(ctypes.byref(d), None) == -5
+    assert _lib.LW_ERRORS[-5] == "LW_ERR_ALIGN"

@@ -25,6 +25,16 @@ static int cuda_fail(cudaError_t e) {
     if (_e != cudaSuccess) return cuda_fail(_e);   \
   } while (0)
 
+// Every pointer the kernels touch with 16-byte vector accesses or cp.async.bulk must be 16-byte aligned (NULL passes).
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+template <typename... P>
+static bool all_aligned16(P... ps) {
+  bool ok = true;
+  const void* v[] = {ps...};
+  for (const void* p : v) ok = ok && aligned16(p);
+  return ok;
+}
+
 extern "C" int lw_abi_version(void) { return 2; }
 extern "C" const char* lw_last_cuda_error(void) { return g_err; }
 extern "C" int lw_check_device(void) {
@@ -86,6 +96,7 @@ extern "C" int lw_wmsa_fwd(const lw_wmsa_args* a, lw_stream_t stream) {
     return LW_ERR_BAD_SHAPE;
   }
   if (a->mask && a->n_mask_windows <= 0) return LW_ERR_BAD_SHAPE;
+  if (!all_aligned16(a->x, a->out, a->resid, a->ln_w, a->ln_b, a->modulator, a->wqkv_img, a->wproj_img, a->bproj)) return LW_ERR_ALIGN;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   lw_wmsa_args aa = *a;
   aa.dbg = debug_flags();
@@ -131,6 +142,7 @@ extern "C" int lw_leff1_fwd(const lw_leff1_args* p, lw_stream_t stream) {
   if (!p || !p->x || !p->h1 || !p->w1_img || !p->b1) return LW_ERR_NULL;
   if ((p->ln_w == nullptr) != (p->ln_b == nullptr)) return LW_ERR_NULL;
   if (p->n_tokens <= 0 || p->hidden % 64) return LW_ERR_BAD_SHAPE;
+  if (!all_aligned16(p->x, p->h1, p->ln_w, p->ln_b, p->w1_img, p->b1)) return LW_ERR_ALIGN;
   AResArgs a{};
   a.x = reinterpret_cast<const bf16*>(p->x); a.n_rows = p->n_tokens; a.K = p->C;
   a.ln_w = p->ln_w; a.ln_b = p->ln_b; a.ln_eps = p->ln_eps;
@@ -147,6 +159,7 @@ extern "C" int lw_leff1_fwd(const lw_leff1_args* p, lw_stream_t stream) {
 extern "C" int lw_upsample_fwd(const lw_up_args* p, lw_stream_t stream) {
   if (!p || !p->x || !p->out || !p->w_img || !p->bias) return LW_ERR_NULL;
   if (p->B <= 0 || p->H <= 0 || p->W <= 0 || p->Cout % 16 || p->out_stride < p->Cout || p->out_stride % 8) return LW_ERR_BAD_SHAPE;
+  if (!all_aligned16(p->x, p->out, p->w_img, p->bias)) return LW_ERR_ALIGN;
   AResArgs a{};
   a.x = reinterpret_cast<const bf16*>(p->x); a.n_rows = p->B * p->H * p->W; a.K = p->Cin;
   a.w_img = reinterpret_cast<const uint8_t*>(p->w_img); a.n_total = 4 * p->Cout; a.nch = lw_nch_ares(p->Cin, 4 * p->Cout);
@@ -159,6 +172,7 @@ extern "C" int lw_upsample_fwd(const lw_up_args* p, lw_stream_t stream) {
 extern "C" int lw_leff2_fwd(const lw_leff2_args* p, lw_stream_t stream) {
   if (!p || !p->h1 || !p->out || !p->wd || !p->bd || !p->w2_img || !p->b2) return LW_ERR_NULL;
   if (p->B <= 0 || p->H <= 0 || p->W < 8 || p->hidden % 64 || p->C % 16 || p->C > 512) return LW_ERR_BAD_SHAPE;
+  if (!all_aligned16(p->h1, p->out, p->resid, p->wd, p->bd, p->w2_img, p->b2)) return LW_ERR_ALIGN;
   AStreamArgs a{};
   a.src = reinterpret_cast<const bf16*>(p->h1); a.B = p->B; a.H = p->H; a.W = p->W; a.K = p->hidden;
   a.wd = p->wd; a.bd = p->bd; a.w_img = reinterpret_cast<const uint8_t*>(p->w2_img);
@@ -187,6 +201,7 @@ extern "C" int lw_downsample_fwd(const lw_down_args* p, lw_stream_t stream) {
   if (!p || !p->x || !p->out || !p->w_img || !p->bias) return LW_ERR_NULL;
   if (p->B <= 0 || p->H % 2 || p->W % 2 || p->Cin % 8 || (16 * p->Cin) % 64 || p->Cout % 16 || p->Cout > 512) return LW_ERR_BAD_SHAPE;
   if (!((64 % p->Cin == 0) || (p->Cin % 64 == 0))) return LW_ERR_BAD_SHAPE;
+  if (!all_aligned16(p->x, p->out, p->w_img, p->bias)) return LW_ERR_ALIGN;
   AStreamArgs a{};
   a.src = reinterpret_cast<const bf16*>(p->x); a.B = p->B; a.H = p->H; a.W = p->W; a.K = 16 * p->Cin; a.Cin = p->Cin;
   a.w_img = reinterpret_cast<const uint8_t*>(p->w_img); a.N = p->Cout; a.nch = p->Cout < 128 ? p->Cout : 128;
@@ -225,12 +240,11 @@ extern "C" int lw_output_proj_fwd(const void* tokens, const float* w, const floa
 }
 
 // ------------------------------------------------------------------------------------------------
-static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
-
 extern "C" int lw_charbonnier_fwd_bwd(const float* x, const float* y, float* grad, float* loss, float* partial, int64_t n, float eps,
                                       lw_stream_t stream) {
   if (!x || !y || !loss || !partial) return LW_ERR_NULL;
-  if (n <= 0 || !aligned16(x) || !aligned16(y) || !aligned16(grad)) return LW_ERR_BAD_SHAPE;
+  if (n <= 0) return LW_ERR_BAD_SHAPE;
+  if (!all_aligned16(x, y, grad)) return LW_ERR_ALIGN;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   int grid = 4 * sm_count();
   if (grid > LW_CHARBONNIER_PARTIALS) grid = LW_CHARBONNIER_PARTIALS;
@@ -246,7 +260,8 @@ extern "C" int lw_charbonnier_fwd_bwd(const float* x, const float* y, float* gra
 
 extern "C" int lw_adamw_step(const lw_adamw_args* a, lw_stream_t stream) {
   if (!a || !a->p || !a->g || !a->m || !a->v) return LW_ERR_NULL;
-  if (a->n <= 0 || a->step < 1 || !aligned16(a->p) || !aligned16(a->g) || !aligned16(a->m) || !aligned16(a->v)) return LW_ERR_BAD_SHAPE;
+  if (a->n <= 0 || a->step < 1) return LW_ERR_BAD_SHAPE;
+  if (!all_aligned16(a->p, a->g, a->m, a->v)) return LW_ERR_ALIGN;
   if (!(a->beta1 >= 0.f && a->beta1 < 1.f && a->beta2 >= 0.f && a->beta2 < 1.f)) return LW_ERR_BAD_SHAPE;
   AdamWConsts c;
   c.lr = a->lr; c.beta1 = a->beta1; c.beta2 = a->beta2; c.eps = a->eps; c.weight_decay = a->weight_decay;
