@@ -246,3 +246,24 @@ def test_downsample_linearity_property_full_size():
         lhs = mod(x + y).float() + mod(torch.zeros_like(x)).float()
         rhs = mod(x).float() + mod(y).float()
     assert (lhs - rhs).abs().max() < 0.05 * rhs.abs().max()
+
+
+@pytest.mark.parametrize("name", ["uformer_b_256", "uformer_t2_128"])
+def test_fp32_residual_precision_mode(name):
+    """Precision mode (uformer_b200.set_residual_precision): residual stream in fp32 between the same kernels.  Must be at
+    least as accurate as the default path; the CPU contract model predicts 8.0e-3 (flagship) / 5.7e-3 (t2)."""
+    import uformer_b200 as U
+    g = load_golden(name)
+    net, _ = build_module(g)
+    net = net.to(DEV)
+    x = g["x"].to(DEV)
+    with torch.no_grad():
+        y_bf = net(x).float().cpu()
+        U.set_residual_precision(net, torch.float32)
+        y_32 = net(x).float().cpu()
+    e_bf, e_32 = rel_l2(y_bf, g["y"]), rel_l2(y_32, g["y"])
+    print(f"{name}: bf16 residual stream {e_bf:.3e} -> fp32 residual stream {e_32:.3e}")
+    tol_full, tol_resid = model_tolerances(g)
+    _check(y_32, g["y"], name + " fp32-residual", tol=tol_full)
+    _check(y_32 - g["x"], g["y"] - g["x"], name + " fp32-residual residual-branch", tol=tol_resid)
+    assert e_32 < e_bf

@@ -11,13 +11,13 @@ rebind the `Downsample` / `Upsample` globals, because the originals' `super(Down
 (model.py:732, :758) resolve that global.  See INTEGRATION.md.
 """
 from .modules import (Downsample, DropPath, EngineUnavailable, LeFF, LeWinTransformerBlock, LinearProjection,  # noqa: F401
-                      Upsample, WindowAttention)
+                      Upsample, WindowAttention, set_residual_precision)
 from .inference import expand2square, restore_image  # noqa: F401
 from .network import GraphedForward, InputProj, LeWinStage, OutputProj, Uformer  # noqa: F401
 from .training import CharbonnierLoss, FlatAdamW, FlatArena, GradReducer, TrainStep  # noqa: F401
 
 __all__ = ["install", "uninstall", "LeWinTransformerBlock", "WindowAttention", "LeFF", "Downsample", "Upsample", "Uformer",
-           "EngineUnavailable", "restore_image", "expand2square", "TrainStep", "CharbonnierLoss", "FlatAdamW", "FlatArena", "GradReducer"]
+           "EngineUnavailable", "restore_image", "expand2square", "set_residual_precision", "TrainStep", "CharbonnierLoss", "FlatAdamW", "FlatArena", "GradReducer"]
 
 _SAVED = {}
 
