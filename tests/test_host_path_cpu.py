@@ -293,3 +293,29 @@ def test_fp32_residual_precision_mode_through_contract_model(name):
     print(f"{name}: bf16 residual stream {e_bf:.3e} -> fp32 residual stream {e_32:.3e}")
     assert e_32 < TOL and e_32 < 0.8 * e_bf
     assert rel_l2(y_32 - g["x"], g["y"] - g["x"]) < TOL
+
+
+def test_block_property_random_shapes_through_contract_model():
+    """hypothesis: for random (C, heads, map side, batch, shift, modulator, input mask) the module -> packing -> contract
+    path equals the oracle (SURVEY §8c 'property tests over shapes')."""
+    from hypothesis import given, settings, strategies as st
+    from oracle import lewin_oracle as O
+
+    @settings(max_examples=12, deadline=None)
+    @given(ch=st.sampled_from([(16, 1), (32, 1), (32, 2), (64, 2), (64, 4), (128, 4)]), side=st.sampled_from([8, 16, 24, 40]),
+           batch=st.integers(1, 3), shifted=st.booleans(), modu=st.booleans(), masked=st.booleans(), seed=st.integers(0, 2 ** 16))
+    def run(ch, side, batch, shifted, modu, masked, seed):
+        dim, heads = ch
+        shift = 4 if (shifted and side > 8) else 0
+        blk = U.LeWinTransformerBlock(dim, (max(side, 16), max(side, 16)), heads, win_size=8, shift_size=shift, modulator=modu).eval()
+        st_ = randomize_state(blk.state_dict(), seed)
+        blk.load_state_dict(st_)
+        g = torch.Generator().manual_seed(seed)
+        x = torch.randn(batch, side * side, dim, generator=g).to(torch.bfloat16)
+        mask = (torch.rand(batch, 1, side, side, generator=g) > 0.5).float() if masked else None
+        with KM.patched(), torch.no_grad():
+            y = blk(x, mask=mask).float()
+        ref = O.lewin_block(x.float(), st_, "", heads, 8, shift, input_mask=mask)
+        assert rel_l2(y, ref) < TOL, (ch, side, batch, shift, modu, masked, rel_l2(y, ref))
+
+    run()
