@@ -215,11 +215,14 @@ def upsample(x: Tensor, weight: Tensor, bias: Tensor) -> Tensor:
 # LeWin block
 # --------------------------------------------------------------------------------------------
 def lewin_block(x: Tensor, p: Dict[str, Tensor], prefix: str, heads: int, ws: int, shift: int,
-                input_mask: Optional[Tensor] = None) -> Tensor:
-    """LeWinTransformerBlock.forward (model.py:908-989), eval mode (DropPath = identity).
+                input_mask: Optional[Tensor] = None, drop_scales=None) -> Tensor:
+    """LeWinTransformerBlock.forward (model.py:908-989).  Eval mode by default (DropPath = identity).
 
-    x1 = x + reverse(WMSA(partition(roll(LN1(x), -s)) + modulator), +s); out = x1 + LeFF(LN2(x1)).
-    ``input_mask`` is the optional (B,1,h,w) mask of model.py:914-921 (nearest-resized)."""
+    x1 = x + DP1(reverse(WMSA(partition(roll(LN1(x), -s)) + modulator), +s)); out = x1 + DP2(LeFF(LN2(x1))).
+    ``input_mask`` is the optional (B,1,h,w) mask of model.py:914-921 (nearest-resized).
+    ``drop_scales`` = (s1, s2), two (B,1,1) tensors in {0, 1/keep}: the per-sample factors timm's DropPath
+    (model.py:887, applied at :986-987) multiplies the two branches with in training mode — the caller draws them
+    (``bernoulli_(keep).div_(keep)``, first branch first) so that oracle and engine see the same stochastic depth."""
     B, L, C = x.shape
     H = W = int(math.isqrt(L))
     mask = None
@@ -241,9 +244,14 @@ def lewin_block(x: Tensor, p: Dict[str, Tensor], prefix: str, heads: int, ws: in
     y = window_reverse(a.reshape(-1, ws, ws, C), ws, H, W)
     if shift > 0:
         y = torch.roll(y, shifts=(shift, shift), dims=(1, 2))
-    x1 = x + y.reshape(B, L, C)
-    z = layer_norm(x1, p[prefix + "norm2.weight"], p[prefix + "norm2.bias"])
-    return x1 + leff(z, p, prefix + "mlp.")
+    y = y.reshape(B, L, C)
+    if drop_scales is not None:
+        y = y * drop_scales[0].to(y.dtype)
+    x1 = x + y
+    z = leff(layer_norm(x1, p[prefix + "norm2.weight"], p[prefix + "norm2.bias"]), p, prefix + "mlp.")
+    if drop_scales is not None:
+        z = z * drop_scales[1].to(z.dtype)
+    return x1 + z
 
 
 # --------------------------------------------------------------------------------------------

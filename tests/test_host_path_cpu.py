@@ -313,9 +313,69 @@ def test_block_property_random_shapes_through_contract_model():
         g = torch.Generator().manual_seed(seed)
         x = torch.randn(batch, side * side, dim, generator=g).to(torch.bfloat16)
         mask = (torch.rand(batch, 1, side, side, generator=g) > 0.5).float() if masked else None
+        if masked and shift > 0 and batch > 1:
+            # the reference itself rejects this combination: model.py:942 adds the (B*nW,N,N) input mask to the (nW,N,N)
+            # shift mask, which does not broadcast for B > 1 — oracle and engine both raise like it does
+            with pytest.raises(RuntimeError):
+                O.lewin_block(x.float(), st_, "", heads, 8, shift, input_mask=mask)
+            with KM.patched(), torch.no_grad(), pytest.raises(RuntimeError):
+                blk(x, mask=mask)
+            return
         with KM.patched(), torch.no_grad():
             y = blk(x, mask=mask).float()
         ref = O.lewin_block(x.float(), st_, "", heads, 8, shift, input_mask=mask)
         assert rel_l2(y, ref) < TOL, (ch, side, batch, shift, modu, masked, rel_l2(y, ref))
 
     run()
+
+
+def _data_parallel_replica(mod):
+    """What torch.nn.parallel.replicate builds for one device (it needs CUDA, so it is re-enacted here): every module is
+    `_replicate_for_data_parallel()`-ed (its `_parameters` becomes {}), the broadcast copies of the parameters — autograd
+    non-leaf tensors whose gradient flows back to the source parameter — are set as plain attributes and recorded in
+    `_former_parameters`."""
+    from collections import OrderedDict
+    mods = list(mod.modules())
+    idx = {m: i for i, m in enumerate(mods)}
+    reps = []
+    for m in mods:
+        r = m._replicate_for_data_parallel()
+        r._former_parameters = OrderedDict()
+        reps.append(r)
+    for m, r in zip(mods, reps):
+        for k, child in m._modules.items():
+            if child is None:
+                r._modules[k] = None
+            else:
+                setattr(r, k, reps[idx[child]])
+        for k, p in m._parameters.items():
+            if p is None:
+                r._parameters[k] = None
+            else:
+                cp = p.view_as(p)                     # stand-in for Broadcast.apply: non-leaf, grads reach p
+                setattr(r, k, cp)
+                r._former_parameters[k] = cp
+    return reps[0]
+
+
+@pytest.mark.parametrize("explicit", [False, True])
+def test_data_parallel_replica_gets_parameter_gradients(explicit):
+    """the reference wraps the model in nn.DataParallel (train/train_denoise.py:83); replicas have an
+    empty `_parameters`, so collecting trainable tensors with `mod.parameters()` silently trained nothing."""
+    from uformer_b200 import autograd as AG
+    blk = U.LeWinTransformerBlock(32, (16, 16), 2, win_size=8, shift_size=4, modulator=True)
+    blk.load_state_dict(randomize_state(blk.state_dict(), 3))
+    blk.train()
+    rep = _data_parallel_replica(blk)
+    assert len(list(rep.parameters())) == 0 and len(AG.trainable_tensors(rep)) == len(list(blk.parameters()))
+    x = torch.randn(2, 256, 32).to(torch.bfloat16)
+    AG.use_explicit_block_backward(explicit)
+    try:
+        with KM.patched():
+            y = rep(x)
+            assert y.grad_fn is not None
+            y.float().pow(2).mean().backward()
+    finally:
+        AG.use_explicit_block_backward(False)
+    for k, p in blk.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all() and p.grad.abs().sum() > 0, k

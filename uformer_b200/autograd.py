@@ -108,6 +108,31 @@ def autocast_enabled(device_type: str) -> bool:
     return _AUTOCAST.get(device_type, False)
 
 
+def trainable_tensors(mod):
+    """Trainable parameter tensors of `mod`, also for nn.DataParallel replicas (train/train_denoise.py:83): torch's
+    `_replicate_for_data_parallel` empties `_parameters` in every replica and parks the broadcast copies (autograd
+    non-leaf tensors that route gradients back to the source module) in `_former_parameters` — `mod.parameters()` is
+    empty there, which would silently drop every weight gradient."""
+    out, seen = [], set()
+    for m in mod.modules():
+        for p in list(m._parameters.values()) + list(getattr(m, "_former_parameters", {}).values()):
+            if p is not None and p.requires_grad and id(p) not in seen:
+                seen.add(id(p))
+                out.append(p)
+    return out
+
+
+def named_trainable_tensors(mod):
+    """(dotted name, tensor) pairs in `named_parameters` order; replica-aware like trainable_tensors."""
+    out, seen = [], set()
+    for prefix, m in mod.named_modules():
+        for k, p in list(m._parameters.items()) + list(getattr(m, "_former_parameters", {}).items()):
+            if p is not None and p.requires_grad and id(p) not in seen:
+                seen.add(id(p))
+                out.append(((prefix + "." if prefix else "") + k, p))
+    return out
+
+
 def wants_grad(*tensors) -> bool:
     return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
 

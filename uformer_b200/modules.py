@@ -98,7 +98,7 @@ def _run(mod, native, restate, acts):
     """Native forward of `mod`; under autograd the same call is wrapped so that backward recomputes it from `acts`."""
     _lib.require_device(acts[0].device)         # device check first: no CPU fallback, fail loudly
     if torch.is_grad_enabled():                 # (inference runs under no_grad: skip the parameter walk entirely)
-        params = [p for p in mod.parameters() if p.requires_grad]
+        params = autograd.trainable_tensors(mod)     # replica-aware (nn.DataParallel empties _parameters)
         if autograd.wants_grad(*acts, *params):
             return autograd.apply(native, restate, acts, params)
     return native(*acts)
@@ -298,7 +298,7 @@ class Upsample(nn.Module):
         B, L, _ = x.shape
         H = int(math.sqrt(L))
         xb, back = _as_bf16(x)
-        if out is not None and torch.is_grad_enabled() and autograd.wants_grad(xb, *self.parameters()):
+        if out is not None and torch.is_grad_enabled() and autograd.wants_grad(xb, *autograd.trainable_tensors(self)):
             raise ValueError("Upsample(out=...) writes in place and cannot be recorded by autograd; call it without `out`")
         res = _run(self, lambda t: ops.upsample(t, self.packed(), B=B, H=H, W=H, out=out), lambda t: restated.upsample(self, t), [xb])
         return res if back is None or out is not None else res.to(back)
@@ -374,6 +374,11 @@ class LeWinTransformerBlock(nn.Module):
                                       f"(L={L}, win_size={self.win_size})")
         self.attn._check_supported()
         self.mlp._check_supported()
+        if mask is not None and self.shift_size > 0 and B > 1:
+            # same behaviour as the reference: model.py:942 adds the (B*nW,N,N) input mask to the (nW,N,N) shift mask,
+            # which cannot broadcast for B > 1 (its RuntimeError); never silently extend the semantics
+            raise RuntimeError(f"input mask with a shifted block needs batch 1 (got {B}): the reference's mask sum at "
+                               "model.py:942 does not broadcast (B*nW,N,N) + (nW,N,N)")
         _lib.require_device(x.device)
         if self.residual_fp32 and mask is None and not (self.training and torch.is_grad_enabled()):
             return self._forward_fp32_residual(x, B, H, W)
@@ -413,7 +418,7 @@ class LeWinTransformerBlock(nn.Module):
 
         res = None
         if autograd.explicit_block_backward() and torch.is_grad_enabled():
-            named = [(k, p) for k, p in self.named_parameters() if p.requires_grad]
+            named = autograd.named_trainable_tensors(self)
             if autograd.wants_grad(xb, *[p for _, p in named]):
                 res = autograd.BlockFn.apply(native, self, (has_dp, has_mask), tuple(k for k, _ in named), *acts, *[p for _, p in named])
         if res is None:

@@ -56,7 +56,7 @@ class LeWinStage(nn.Module):
         B, L, C = x.shape
         per_image = 14 * L * C
         chunk = max(1, min(B, L2_BUDGET_BYTES // per_image))
-        if chunk >= B or mask is not None or x.dtype != torch.bfloat16 or len(self.blocks) == 0 or autograd.wants_grad(x, *self.parameters()):
+        if chunk >= B or mask is not None or x.dtype != torch.bfloat16 or len(self.blocks) == 0 or autograd.wants_grad(x, *autograd.trainable_tensors(self)):
             for blk in self.blocks:
                 x = blk(x, mask)
             return x
@@ -176,7 +176,7 @@ class Uformer(nn.Module):
         torch.no_grad) this is the inference schedule below; in training mode with autograd recording it is
         `_forward_train` (same kernels, each op wrapped for recompute-backward)."""
         _lib.require_device(x.device)
-        if self.training and autograd.wants_grad(x, *self.parameters()):
+        if self.training and autograd.wants_grad(x, *autograd.trainable_tensors(self)):
             return self._forward_train(x, mask)
         with torch.no_grad():
             return self._forward_infer(x, mask)

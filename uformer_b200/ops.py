@@ -20,25 +20,27 @@ LAUNCH_COUNT = 0
 PROFILE = None
 
 
-def _launch(label: str, flops: float, fn, rc_name: str):
+def _launch(label: str, flops: float, fn, rc_name: str, device=None):
+    """fn(stream) -> return code.  The launch runs with `device` (the device of the op's tensors) current and on THAT
+    device's current stream: a tensor on cuda:1 while cuda:0 is current must not launch on cuda:0 with cuda:1 pointers."""
     global LAUNCH_COUNT
     LAUNCH_COUNT += 1
+    if device is not None and device.type == "cuda" and device.index is not None and device.index != torch.cuda.current_device():
+        with torch.cuda.device(device):
+            return _launch(label, flops, fn, rc_name, None)
+    stream = torch.cuda.currentst.cuda_stream
     if PROFILE is None:
-        _lib.check(fn(), rc_name)
+        _lib.check(fn(stream), rc_name)
         return
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
-    _lib.check(fn(), rc_name)
+    _lib.check(fn(stream), rc_name)
     e.record()
     PROFILE.append((label, flops, s, e))
 
 
 def _ptr(t):
     return None if t is None else t.data_ptr()
-
-
-def _stream():
-    return torch.cuda.current_stream().cuda_stream
 
 
 def _check_act(x: Tensor, name: str):
@@ -72,7 +74,7 @@ def wmsa(x: Tensor, p: dict, *, H: int, W: int, shift: int, windowed: bool, resi
     a.n_windows, a.H, a.W, a.C, a.head_dim = n_windows, H, W, Cc, p["head_dim"]
     a.shift, a.windowed, a.ln_eps = shift, int(windowed), p.get("ln_eps", 1e-5)
     ntok = n_windows * 64
-    _launch(f"wmsa_C{Cc}_T{ntok}", 2.0 * ntok * (4 * Cc * Cc + 128 * Cc), lambda: _lib.load().lw_wmsa_fwd(C.byref(a), _stream()), "lw_wmsa_fwd")
+    _launch(f"wmsa_C{Cc}_T{ntok}", 2.0 * ntok * (4 * Cc * Cc + 128 * Cc), lambda st: _lib.load().lw_wmsa_fwd(C.byref(a), st), "lw_wmsa_fwd", x.device)
     return out
 
 
@@ -88,14 +90,14 @@ def leff(x: Tensor, p: dict, *, B: int, H: int, W: int, resid: Tensor | None, ou
     a.w1_img, a.b1 = _ptr(p["w1_img"]), _ptr(p["b1"])
     a.n_tokens, a.C, a.hidden, a.ln_eps = n_tokens, Cc, hidden, p.get("ln_eps", 1e-5)
     lib = _lib.load()
-    _launch(f"leff1_C{Cc}_T{n_tokens}", 2.0 * n_tokens * Cc * hidden, lambda: lib.lw_leff1_fwd(C.byref(a), _stream()), "lw_leff1_fwd")
+    _launch(f"leff1_C{Cc}_T{n_tokens}", 2.0 * n_tokens * Cc * hidden, lambda st: lib.lw_leff1_fwd(C.byref(a), st), "lw_leff1_fwd", x.device)
     if out is None:
         out = torch.empty_like(x)
     b = _lib.Leff2Args()
     b.h1, b.out, b.resid = _ptr(h1), _ptr(out), _ptr(resid)
     b.wd, b.bd, b.w2_img, b.b2 = _ptr(p["wd"]), _ptr(p["bd"]), _ptr(p["w2_img"]), _ptr(p["b2"])
     b.B, b.H, b.W, b.C, b.hidden = B, H, W, Cc, hidden
-    _launch(f"leff2_C{Cc}_T{n_tokens}", 2.0 * n_tokens * (hidden * Cc + 9 * hidden), lambda: lib.lw_leff2_fwd(C.byref(b), _stream()), "lw_leff2_fwd")
+    _launch(f"leff2_C{Cc}_T{n_tokens}", 2.0 * n_tokens * (hidden * Cc + 9 * hidden), lambda st: lib.lw_leff2_fwd(C.byref(b), st), "lw_leff2_fwd", x.device)
     return out
 
 
@@ -106,8 +108,8 @@ def downsample(x: Tensor, p: dict, *, B: int, H: int, W: int) -> Tensor:
     a = _lib.DownArgs()
     a.x, a.out, a.w_img, a.bias = _ptr(x), _ptr(out), _ptr(p["w_img"]), _ptr(p["bias"])
     a.B, a.H, a.W, a.Cin, a.Cout = B, H, W, Cin, Cout
-    _launch(f"down_C{Cin}", 2.0 * B * (H // 2) * (W // 2) * 16 * Cin * Cout, lambda: _lib.load().lw_downsample_fwd(C.byref(a), _stream()),
-            "lw_downsample_fwd")
+    _launch(f"down_C{Cin}", 2.0 * B * (H // 2) * (W // 2) * 16 * Cin * Cout, lambda st: _lib.load().lw_downsample_fwd(C.byref(a), st),
+            "lw_downsample_fwd", x.device)
     return out
 
 
@@ -120,7 +122,7 @@ def upsample(x: Tensor, p: dict, *, B: int, H: int, W: int, out: Tensor | None =
     a = _lib.UpArgs()
     a.x, a.out, a.w_img, a.bias = _ptr(x), _ptr(out), _ptr(p["w_img"]), _ptr(p["bias"])
     a.B, a.H, a.W, a.Cin, a.Cout, a.out_stride = B, H, W, Cin, Cout, out.shape[-1]
-    _launch(f"up_C{Cin}", 2.0 * B * H * W * Cin * 4 * Cout, lambda: _lib.load().lw_upsample_fwd(C.byref(a), _stream()), "lw_upsample_fwd")
+    _launch(f"up_C{Cin}", 2.0 * B * H * W * Cin * 4 * Cout, lambda st: _lib.load().lw_upsample_fwd(C.byref(a), st), "lw_upsample_fwd", x.device)
     return out
 
 
@@ -132,7 +134,7 @@ def input_proj(img: Tensor, w: Tensor, b: Tensor) -> Tensor:
     E = w.shape[0]
     tok = torch.empty((B, H * W, E), dtype=torch.bfloat16, device=img.device)
     _launch("input_proj", 2.0 * B * H * W * 9 * Cin * E,
-            lambda: _lib.load().lw_input_proj_fwd(_ptr(img), _ptr(w), _ptr(b), _ptr(tok), B, Cin, H, W, E, _stream()), "lw_input_proj_fwd")
+            lambda st: _lib.load().lw_input_proj_fwd(_ptr(img), _ptr(w), _ptr(b), _ptr(tok), B, Cin, H, W, E, st), "lw_input_proj_fwd", img.device)
     return tok
 
 
@@ -145,8 +147,8 @@ def output_proj(tok: Tensor, w: Tensor, b: Tensor, img: Tensor | None, H: int, W
     if img is not None:
         img = img.float().contiguous()
     _launch("output_proj", 2.0 * B * H * W * 9 * Cin * Cout,
-            lambda: _lib.load().lw_output_proj_fwd(_ptr(tok), _ptr(w), _ptr(b), _ptr(img), _ptr(out), B, Cin, H, W, Cout, _stream()),
-            "lw_output_proj_fwd")
+            lambda st: _lib.load().lw_output_proj_fwd(_ptr(tok), _ptr(w), _ptr(b), _ptr(img), _ptr(out), B, Cin, H, W, Cout, st),
+            "lw_output_proj_fwd", tok.device)
     return out
 
 
@@ -159,8 +161,8 @@ def charbonnier(x: Tensor, y: Tensor, eps: float, need_grad: bool):
     loss = torch.empty(1, dtype=torch.float32, device=x.device)
     partial = torch.empty(_lib.CHARBONNIER_PARTIALS, dtype=torch.float32, device=x.device)
     n = x.numel()
-    _launch("charbonnier", 8.0 * n, lambda: _lib.load().lw_charbonnier_fwd_bwd(_ptr(x), _ptr(y), _ptr(grad), _ptr(loss), _ptr(partial), n, eps,
-                                                                             _stream()), "lw_charbonnier_fwd_bwd")
+    _launch("charbonnier", 8.0 * n, lambda st: _lib.load().lw_charbonnier_fwd_bwd(_ptr(x), _ptr(y), _ptr(grad), _ptr(loss), _ptr(partial), n, eps,
+                                                                             st), "lw_charbonnier_fwd_bwd", x.device)
     return loss, grad
 
 
@@ -175,5 +177,4 @@ def adamw_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, *, step: int, lr: flo
     a.p, a.g, a.m, a.v, a.n = _ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel()
     a.step, a.zero_grad = step, int(zero_grad)
     a.lr, a.beta1, a.beta2, a.eps, a.weight_decay, a.grad_scale = lr, beta1, beta2, eps, weight_decay, grad_scale
-    with torch.cuda.device(p.device):
-        _launch("adamw", 12.0 * p.numel(), lambda: _lib.load().lw_adamw_step(C.byref(a), _stream()), "lw_adamw_step")
+    _launch("adamw", 12.0 * p.numel(), lambda st: _lib.load().lw_adamw_step(C.byref(a), st), "lw_adamw_step", p.device)
