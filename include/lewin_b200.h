@@ -100,6 +100,39 @@ typedef struct lw_leff2_args {
 } lw_leff2_args;
 int lw_leff2_fwd(const lw_leff2_args* a, lw_stream_t stream);
 
+/* ---- fused LeFF (one launch; the 4C-wide hidden map stays in shared memory): replaces LeFF.forward (model.py:666-685) with
+ * norm2 of LeWinTransformerBlock.forward (model.py:987) folded in:
+ *   out = resid + GELU( dwconv3x3( GELU( LN(x) W1^T + b1 ) ) + bd ) W2^T + b2
+ * LayerNorm is folded into the first GEMM by the host packer (uformer_b200/packing.py pack_leff_fused):
+ *   w1_img = bf16( W1 diag(gamma) ),  b1f = b1 + W1 beta,  cs[n] = sum_k float(w1_img[n,k])
+ * and the kernel applies  rstd*(x w1_img^T) - rstd*mean*cs + b1f  per token (has_ln = 0: x is used as is; cs is ignored).
+ * x is read through a 4-D TMA tensor map built per call ((C, W, H, B), row stride x_stride), 10x18 halo'd boxes per 8x16 tile.
+ * The hidden dimension is walked in slices of SL = lw_leff_slice(C) channels (64 for C <= 128, 32 for C = 256).
+ * Supported: C in {16, 32, 64, 128, 256}, hidden % 64 == 0, hidden <= 1024 (lw_leff_fused_supported); C = 512 uses the
+ * lw_leff1_fwd + lw_leff2_fwd pair.  resid / out may be bf16 or fp32 (fp32 residual-stream mode) and may be column slices of a
+ * wider buffer (row strides in elements: skip-concat fusion, model.py:1288-1300).  out must not alias x (halo reads). */
+typedef struct lw_leff_args {
+  const void* x;           /* bf16 (B*H*W rows, C) with row stride x_stride */
+  void* out;               /* (B*H*W rows, C) bf16 or fp32, row stride out_stride */
+  const void* resid;       /* same shape, bf16 or fp32, row stride resid_stride; or NULL */
+  const void* w1_img;      /* packed bf16 [hidden/SL][KB][SL rows x SW bytes], SW = 2*min(C,64), swizzle SW */
+  const float* b1f;        /* (hidden) */
+  const float* cs;         /* (hidden) */
+  const float* taps;       /* [hidden/SL][10][SL] fp32 per hidden slice: 9 depthwise taps (tap = ky*3+kx), then the conv bias */
+  const void* w2_img;      /* packed bf16 [hidden/SL][C rows x 2*SL bytes] (K-major, swizzle 2*SL) */
+  const float* b2;         /* (C) */
+  int32_t B, H, W, C, hidden;
+  int32_t x_stride, resid_stride, out_stride;   /* elements */
+  int32_t resid_fp32, out_fp32;                 /* 0: bf16, 1: fp32 */
+  int32_t has_ln;
+  float ln_eps;
+} lw_leff_args;
+int lw_leff_fwd(const lw_leff_args* a, lw_stream_t stream);
+/* 1 if lw_leff_fwd handles (C, hidden), else 0 (use lw_leff1_fwd + lw_leff2_fwd). */
+int lw_leff_fused_supported(int C, int hidden);
+/* hidden channels per slice the fused kernel walks for this C (the host packer cuts w1_img / taps / w2_img with it). */
+int lw_leff_slice(int C);
+
 /* ---- Downsample: Conv2d(k4,s2,p1) on the token map as an implicit GEMM (model.py:739-746) */
 typedef struct lw_down_args {
   const void* x;           /* bf16 (B, H, W, Cin) */

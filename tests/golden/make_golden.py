@@ -117,6 +117,21 @@ def main():
                          ref_bf16=dict(full=rl2(yb, y), resid=rl2(yb - x, y - x)))
         print(name, "reference bf16-autocast vs fp32:", out[name]["ref_bf16"])
 
+    # ---- BASELINE configs[3]: Uformer-B built for 256x256 run on a 512x512 image in ONE whole-image forward (the reference has
+    # no tiling: test/test_sidd.py:79-108 pads to a square multiple of 128 and calls the model once).  Weights: the
+    # gain-0.5 set (trained-denoiser-like residual branch).  The input is re-derivable: torch.rand under seed 512 (not stored).
+    net = m.Uformer(**cfgb)
+    st = randomize_state(net.state_dict(), 1234, 0.5)
+    net.load_state_dict(st, strict=True)
+    net.eval()
+    x512 = torch.rand(1, 3, 512, 512, generator=torch.Generator().manual_seed(512))
+    y512 = net(x512)
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        yb = net(x512).float()
+    out["uformer_b_512_g05"] = dict(kind="model", cfg=cfgb, seed=1234, gain=0.5, x_seed=512, x_shape=(1, 3, 512, 512), y=y512,
+                                    checksum=state_checksum(st), ref_bf16=dict(full=rl2(yb, y512), resid=rl2(yb - x512, y512 - x512)))
+    print("uformer_b_512_g05 reference bf16-autocast vs fp32:", out["uformer_b_512_g05"]["ref_bf16"])
+
     only = os.environ.get("GOLDEN_ONLY")
     for k, v in out.items():
         if only and not k.startswith(only):

@@ -13,7 +13,10 @@ TOL_BF16 = 1e-2
 
 
 def load_golden(name):
-    return torch.load(os.path.join(GOLDEN, name + ".pt"), weights_only=False)
+    g = torch.load(os.path.join(GOLDEN, name + ".pt"), weights_only=False)
+    if "x" not in g and "x_seed" in g:                    # large inputs are re-derived from their seed instead of stored
+        g["x"] = torch.rand(*g["x_shape"], generator=torch.Generator().manual_seed(g["x_seed"]))
+    return g
 
 
 def golden_names(kind):

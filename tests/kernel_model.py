@@ -94,24 +94,44 @@ def wmsa(x, p, *, H, W, shift, windowed, resid, mask=None, out=None):
     return y
 
 
-def leff(x, p, *, B, H, W, resid, out=None):
+def leff(x, p, *, B, H, W, resid, out=None, out_dtype=None):
     assert x.dtype == BF
     C, hid = x.shape[-1], p["hidden"]
     xf = x.float().reshape(B * H * W, C)
-    if p.get("ln_w") is not None:
-        xf = F.layer_norm(xf, (C,), p["ln_w"], p["ln_b"], p.get("ln_eps", 1e-5))
-    nch1 = min(hid, 256 if C == 256 else 128)                     # lw_nch_ares
-    assert nch1 == _lib.load().lw_nch_ares(C, hid)
-    w1 = packing.unpack_kmajor(p["w1_img"], hid, C, nch1, "nk")
-    h1 = _q(F.gelu(_q(xf) @ w1.t() + p["b1"]))                    # bf16 round trip through HBM
+    if "w1f_img" in p:
+        # single-kernel contract (lw_leff_fwd): LayerNorm folded into linear1; the raw bf16 x is the GEMM operand
+        assert _lib.load().lw_leff_fused_supported(C, hid)
+        sl = p["slice"]
+        assert sl == _lib.load().lw_leff_slice(C)
+        w1g = packing.unpack_kmajor_sw(p["w1f_img"], hid, C, sl, 2 * min(C, 64))
+        acc = xf @ w1g.t()
+        if p["has_ln"]:
+            mean = xf.mean(1, keepdim=True)
+            rstd = torch.rsqrt(((xf - mean) ** 2).mean(1, keepdim=True) + p.get("ln_eps", 1e-5))
+            pre = rstd * acc - (rstd * mean) * p["cs"] + p["b1f"]
+        else:
+            pre = acc + p["b1f"]
+        h1 = _q(F.gelu(pre))                                       # bf16 in shared memory
+        w2 = packing.unpack_kmajor_sw(p["w2f_img"], C, hid, C, 2 * sl)
+        t = p["taps"].permute(1, 0, 2).reshape(10, hid)               # [NS][10][sl] -> (10, hidden)
+        wd_t, bd_t = t[:9], t[9]
+    else:
+        if p.get("ln_w") is not None:
+            xf = F.layer_norm(xf, (C,), p["ln_w"], p["ln_b"], p.get("ln_eps", 1e-5))
+        nch1 = min(hid, 256 if C == 256 else 128)                     # lw_nch_ares
+        assert nch1 == _lib.load().lw_nch_ares(C, hid)
+        w1 = packing.unpack_kmajor(p["w1_img"], hid, C, nch1, "nk")
+        h1 = _q(F.gelu(_q(xf) @ w1.t() + p["b1"]))                    # bf16 round trip through HBM
+        w2 = packing.unpack_kmajor(p["w2_img"], C, hid, min(C, 128), "kn")
+        wd_t, bd_t = p["wd"], p["bd"]
     m = h1.view(B, H, W, hid).permute(0, 3, 1, 2)
-    wd = p["wd"].t().reshape(hid, 1, 3, 3)                        # taps (9, hidden), tap = ky*3+kx
-    h2 = _q(F.gelu(F.conv2d(m, wd, p["bd"], padding=1, groups=hid))).permute(0, 2, 3, 1).reshape(B * H * W, hid)
-    w2 = packing.unpack_kmajor(p["w2_img"], C, hid, min(C, 128), "kn")
-    y = (h2 @ w2.t() + p["b2"]).view(x.shape)
+    wd = wd_t.t().reshape(hid, 1, 3, 3)                           # taps (9, hidden), tap = ky*3+kx
+    h2 = _q(F.gelu(F.conv2d(m, wd, bd_t, padding=1, groups=hid))).permute(0, 2, 3, 1).reshape(B * H * W, hid)
+    y = _q(h2 @ w2.t() + p["b2"]).view(x.shape)                  # the branch is rounded to bf16 before the residual add
     if resid is not None:
         y = y + resid.float()
-    y = y.to(BF)
+    odt = out.dtype if out is not None else (out_dtype or BF)
+    y = y.to(odt)
     if out is not None:
         out.copy_(y)
         return out

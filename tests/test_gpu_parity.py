@@ -274,3 +274,56 @@ def test_fp32_residual_precision_mode(name):
     _check(y_32, g["y"], name + " fp32-residual", tol=tol_full)
     _check(y_32 - g["x"], g["y"] - g["x"], name + " fp32-residual residual-branch", tol=tol_resid)
     assert e_32 < e_bf
+
+
+@pytest.mark.parametrize("dim,H,B", [(32, 16, 2), (64, 24, 1), (128, 16, 2), (16, 8, 3), (256, 16, 1)])
+def test_leff_fused_strides_and_fp32_residual_stream(dim, H, B):
+    """Single-kernel LeFF (lw_leff_fwd): x / out as column slices of a wider buffer (skip-concat fusion, model.py:1288-1300)
+    and the fp32 residual-stream mode (fp32 resid in, fp32 out) against the oracle; the block's norm2 is folded in."""
+    import uformer_b200 as U
+    from uformer_b200 import ops
+    from oracle import lewin_oracle as O
+    from paramgen import randomize_state
+    torch.manual_seed(dim + H)
+    blk = U.LeWinTransformerBlock(dim, (16, 16), max(1, dim // 32), win_size=8).eval()
+    st = randomize_state(blk.state_dict(), 21)
+    blk.load_state_dict(st)
+    blk = blk.to(DEV)
+    pm = blk.mlp.packed(blk.norm2)
+    assert "w1f_img" in pm                                   # the fused path is the one under test
+    x = torch.randn(B, H * H, dim).to(torch.bfloat16)
+    r32 = torch.randn(B, H * H, dim)                         # an fp32 residual stream that is NOT the bf16 operand
+    z = O.layer_norm(x.float(), st["norm2.weight"], st["norm2.bias"])
+    branch = O.leff(z, st, "mlp.")
+    wide_in = torch.full((B, H * H, 3 * dim), 3.0, dtype=torch.bfloat16, device=DEV)
+    wide_in[:, :, dim:2 * dim] = x.to(DEV)
+    wide_out = torch.full((B, H * H, 2 * dim), 7.0, dtype=torch.bfloat16, device=DEV)
+    with torch.no_grad():
+        xin = wide_in[:, :, dim:2 * dim]
+        ops.leff(xin, pm, B=B, H=H, W=H, resid=xin, out=wide_out[:, :, dim:])
+        y32 = ops.leff(x.to(DEV), pm, B=B, H=H, W=H, resid=r32.to(DEV), out_dtype=torch.float32)
+    torch.cuda.synchronize()
+    assert torch.all(wide_out[:, :, :dim] == 7.0)            # left half untouched
+    _check(wide_out[:, :, dim:].float().cpu(), x.float() + branch, f"fused leff strided C={dim}")
+    assert y32.dtype == torch.float32
+    _check(y32.cpu() - r32, branch, f"fused leff fp32 residual stream C={dim} (branch)")
+    assert ((y32.cpu() - r32 - branch).abs().max() / branch.abs().max()) < 2e-2
+
+
+def test_launch_on_non_current_device():
+    """tensors on cuda:1 while cuda:0 is current must launch on cuda:1 (device guard around every launch)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import uformer_b200 as U
+    from oracle import lewin_oracle as O
+    from paramgen import randomize_state
+    torch.cuda.set_device(0)
+    blk = U.LeWinTransformerBlock(64, (16, 16), 2, win_size=8, shift_size=4, modulator=True).eval()
+    st = randomize_state(blk.state_dict(), 5)
+    blk.load_state_dict(st)
+    x = torch.randn(2, 256, 64).to(torch.bfloat16)
+    with torch.no_grad():
+        y = blk.to("cuda:1")(x.to("cuda:1"))
+    torch.cuda.synchronize("cuda:1")
+    assert y.device.index == 1 and torch.cuda.current_device() == 0
+    _check(y.float().cpu(), O.lewin_block(x.float(), st, "", 2, 8, 4), "block on cuda:1 with cuda:0 current")

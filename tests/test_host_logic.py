@@ -134,14 +134,21 @@ def test_batched_prepack_is_bit_identical_to_lazy_packing():
                 dict(img_size=128, embed_dim=32, depths=[1, 2, 1, 1, 1, 1, 1, 2, 1], win_size=8, modulator=True)]:
         net = uformer_b200.Uformer(**cfg)
         net.load_state_dict(randomize_state(net.state_dict(), 11))
-        mods = [m for m in net.modules() if hasattr(m, "packed")]
-        lazy = [{k: (v.clone() if torch.is_tensor(v) else v) for k, v in m.packed().items()} for m in mods]
+        calls = []                                                        # (module, cache, packed-call)
+        for m in net.modules():
+            if isinstance(m, M.LeWinTransformerBlock):
+                calls += [(m, m._cache, m.packed), (m.attn, m.attn._cache, m.attn.packed),
+                          (m.mlp, m.mlp._cache_ln, lambda mm=m: mm.mlp.packed(mm.norm2))]
+            elif isinstance(m, (M.Downsample, M.Upsample)):
+                calls.append((m, m._cache, m.packed))
+        lazy = [{k: (v.clone() if torch.is_tensor(v) else v) for k, v in call().items()} for _, _, call in calls]
+        assert any("w1f_img" in d for d in lazy) and (cfg["embed_dim"] == 16 or any("w1_img" in d for d in lazy))   # both LeFF paths
         M.invalidate_packed()
         assert prepack(net) == sum(cfg["depths"]) + 8
-        for m, want in zip(mods, lazy):
-            key_before = m._cache._entry[0]
-            got = m.packed()
-            assert m._cache._entry[0] == key_before                      # cache hit: nothing was rebuilt
+        for (m, cache, call), want in zip(calls, lazy):
+            key_before = cache._entry[0]
+            got = call()
+            assert cache._entry[0] == key_before                          # cache hit: nothing was rebuilt
             assert set(got) == set(want), type(m)
             for k, v in want.items():
                 if torch.is_tensor(v):
@@ -190,3 +197,18 @@ def test_alignment_validation_without_gpu():
     d.p, d.g, d.m, d.v, d.n, d.step, d.beta1, d.beta2 = 0x20000, 0x20004, 0x20000, 0x20000, 64, 1, 0.9, 0.999
     assert lib.lw_adamw_step(ctypes.byref(d), None) == -5
     assert _lib.LW_ERRORS[-5] == "LW_ERR_ALIGN"
+
+
+def test_torch_cuda_attribute_chains_exist():
+    """The launch plumbing (ops._launch, bench.py, tools/) only runs on a GPU box; a typo in a torch.cuda.* name there costs a
+    whole GPU call.  Static check: every torch.cuda.<name> the repo mentions exists in the installed torch."""
+    import glob
+    import re
+    files = glob.glob(os.path.join(ROOT, "uformer_b200", "*.py")) + glob.glob(os.path.join(ROOT, "tools", "*.py")) + [
+        os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")]
+    bad = []
+    for f in files:
+        for m in re.finditer(r"torch\.cuda\.([A-Za-z_]+)", open(f).read()):
+            if not hasattr(torch.cuda, m.group(1)):
+                bad.append((os.path.basename(f), m.group(0)))
+    assert not bad, bad

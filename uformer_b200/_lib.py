@@ -37,6 +37,14 @@ class Leff2Args(C.Structure):
                 ("C", C.c_int32), ("hidden", C.c_int32)]
 
 
+class LeffArgs(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("out", C.c_void_p), ("resid", C.c_void_p), ("w1_img", C.c_void_p), ("b1f", C.c_void_p),
+                ("cs", C.c_void_p), ("taps", C.c_void_p), ("w2_img", C.c_void_p), ("b2", C.c_void_p),
+                ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32), ("hidden", C.c_int32),
+                ("x_stride", C.c_int32), ("resid_stride", C.c_int32), ("out_stride", C.c_int32), ("resid_fp32", C.c_int32),
+                ("out_fp32", C.c_int32), ("has_ln", C.c_int32), ("ln_eps", C.c_float)]
+
+
 class DownArgs(C.Structure):
     _fields_ = [("x", C.c_void_p), ("out", C.c_void_p), ("w_img", C.c_void_p), ("bias", C.c_void_p), ("B", C.c_int32),
                 ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32), ("Cout", C.c_int32)]
@@ -56,7 +64,7 @@ class AdamWArgs(C.Structure):
 CHARBONNIER_PARTIALS = 1024      # LW_CHARBONNIER_PARTIALS
 
 # every symbol include/lewin_b200.h declares
-EXPORTS = ["lw_abi_version", "lw_last_cuda_error", "lw_check_device", "lw_nch_ares", "lw_wmsa_fwd", "lw_leff1_fwd", "lw_leff2_fwd",
+EXPORTS = ["lw_abi_version", "lw_last_cuda_error", "lw_check_device", "lw_nch_ares", "lw_wmsa_fwd", "lw_leff1_fwd", "lw_leff2_fwd", "lw_leff_fwd", "lw_leff_fused_supported", "lw_leff_slice",
            "lw_downsample_fwd", "lw_upsample_fwd", "lw_input_proj_fwd", "lw_output_proj_fwd", "lw_charbonnier_fwd_bwd", "lw_adamw_step"]
 
 _lib = None
@@ -75,7 +83,11 @@ def load():
     lib.lw_check_device.restype = C.c_int
     lib.lw_nch_ares.restype = C.c_int
     lib.lw_nch_ares.argtypes = [C.c_int, C.c_int]
-    for name, argt in [("lw_wmsa_fwd", WmsaArgs), ("lw_leff1_fwd", Leff1Args), ("lw_leff2_fwd", Leff2Args),
+    lib.lw_leff_fused_supported.restype = C.c_int
+    lib.lw_leff_fused_supported.argtypes = [C.c_int, C.c_int]
+    lib.lw_leff_slice.restype = C.c_int
+    lib.lw_leff_slice.argtypes = [C.c_int]
+    for name, argt in [("lw_wmsa_fwd", WmsaArgs), ("lw_leff1_fwd", Leff1Args), ("lw_leff2_fwd", Leff2Args), ("lw_leff_fwd", LeffArgs),
                        ("lw_downsample_fwd", DownArgs), ("lw_upsample_fwd", UpArgs)]:
         fn = getattr(lib, name)
         fn.restype = C.c_int

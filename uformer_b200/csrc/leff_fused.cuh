@@ -1,0 +1,540 @@
+// leff_fused.cuh — LeFF in ONE kernel (model.py:666-685 with norm2 of :987 folded in):
+//   out = resid + GELU( dwconv3x3( GELU( LN(x) W1^T + b1 ) ) + bd ) W2^T + b2
+// The 4C-wide hidden map never exists in HBM: it lives, 64 channels at a time, in shared memory.
+//
+// PERSISTENT kernel, one CTA per SM, 8 x 16 spatial output tiles (128 tokens) walked round-robin.  Per tile:
+//   TMA      the 10 x 18 halo'd block of RAW input tokens lands with one cp.async.bulk.tensor box per 64-channel
+//            k-block (4-D tensor map (C, W, H, B), out-of-image coordinates are zero-filled by the hardware) directly
+//            in the K-major swizzled layout tcgen05 consumes: 180 rows, row = halo token.
+//   stats    two warps compute the LayerNorm statistics of the 180 rows from shared memory.  LayerNorm itself is
+//            FOLDED into GEMM-1: W1' = W1 diag(gamma) (host packing), so
+//              LN(x) W1^T + b1 = rstd * (x W1'^T) - rstd*mu * colsum(W1') + (b1 + W1 beta)
+//            and the raw tile is the A operand as it landed (no normalise-and-rewrite pass; also one bf16 rounding less).
+//   GEMM-1   per 64-channel hidden slice j: D1_j[192 x 64] = X[192 x C] W1'_j^T as one M=128 + one M=64 tcgen05.mma chain
+//            (192 = 180 halo rows rounded up), accumulators double-buffered in TMEM.
+//   E1       4 epilogue warps: D1 (16x256b TMEM fragments) -> LN fold + bias -> GELU -> bf16 -> stmatrix into the halo
+//            tile [192 tokens][64 ch] (zero for out-of-image tokens = the conv's zero padding of h1, model.py:659).
+//   conv     8 warps: depthwise 3x3 + bias + GELU on the halo tile (one warp per channel octet, lanes = 16 columns x
+//            2 row halves sliding down their column, packed FFMA2) -> bf16 A operand of GEMM-2.
+//   GEMM-2   D2[128 x C] += A2_j[128 x 64] W2_j^T, accumulator double-buffered in TMEM across tiles.
+//   E2       (the E1 warps, one tile behind) D2 + b2 -> staging -> coalesced store with the residual added.
+// Every stage is double-buffered and mbarrier-linked, so GEMM-1(j+1), E1(j), conv(j-1), GEMM-2(j-2) run concurrently and
+// the pipeline does not drain between tiles.
+#pragma once
+#include <cuda.h>
+#include "lewin_common.cuh"
+#include "leff2.cuh"
+
+namespace lw {
+
+constexpr int kLFThreads = 512;
+constexpr int kLFConv = 256;
+
+struct LeffFArgs {
+  int B, H, W, hidden;
+  const uint8_t* w1_img;   // [hidden/SL][KB1][SL rows x SW bytes] bf16, gamma folded, swizzle SW = 2*min(C,64)
+  const float* b1f;        // (hidden)  b1 + W1 beta
+  const float* cs;         // (hidden)  row sums of the bf16-rounded W1' (mean correction of the folded LayerNorm)
+  const float* taps;       // [hidden/SL][10][SL] fp32: 9 depthwise taps (tap = ky*3+kx) + conv bias per slice
+  const uint8_t* w2_img;   // [hidden/SL][C rows x 2*SL bytes] bf16, swizzle 2*SL
+  const float* b2;         // (C)
+  const void* resid;       // (B*H*W rows, stride resid_stride) bf16 or fp32, or null
+  void* out;               // (B*H*W rows, stride out_stride) bf16 or fp32
+  int resid_stride, out_stride, resid_fp32, out_fp32;
+  int has_ln;
+  float ln_eps;
+  int tiles_x, tiles_y, n_tiles;
+};
+
+template <int C>
+struct LeffFCfg {
+  static constexpr int SL = (C <= 128) ? 64 : 32;           // hidden channels per slice (smem / TMEM budget at C = 256)
+  static constexpr int SWH = SL * 2;                        // row bytes / swizzle span of the halo tile, A2 and W2 chunks
+  static constexpr int CB = C < 64 ? C : 64;               // channels per k-block
+  static constexpr int SW = CB * 2;                         // bytes per A / W1 row inside a k-block = swizzle span
+  static constexpr int KB1 = (C + 63) / 64;
+  static constexpr int KS1 = CB / 16;
+  static constexpr int A1_ROWS = 192;
+  static constexpr int A1_KB_BYTES = A1_ROWS * SW;
+  static constexpr int A1_BYTES = KB1 * A1_KB_BYTES;
+  static constexpr int NA1 = (C <= 64) ? 2 : 1;             // input tiles in flight
+  static constexpr int X_BOX_BYTES = 180 * SW;              // one TMA box (one k-block)
+  static constexpr int W1_CHUNK = KB1 * SL * SW;
+  static constexpr int W2_CHUNK = C * SWH;
+  static constexpr int STAGES = 3;
+  static constexpr int HALO_BYTES = 192 * SWH;
+  static constexpr int A2_BYTES = 128 * SWH;
+  static constexpr int NTAP = 4;
+  static constexpr int TAP_BYTES = 10 * SL * 4;
+  static constexpr int STAGE_PITCH = 80;                    // E2 staging: 32 bf16 columns + 16 B pad
+  static constexpr int S_A1 = 0;
+  static constexpr int S_HALO = (NA1 * A1_BYTES + 1023) / 1024 * 1024;
+  static constexpr int S_A2 = S_HALO + 2 * HALO_BYTES;
+  static constexpr int S_RING = S_A2 + 2 * A2_BYTES;
+  static constexpr int S_STAGE = S_RING + STAGES * kStageBytes;
+  static constexpr int S_TAPS = S_STAGE + 128 * STAGE_PITCH;          // NTAP x [10][SL] fp32
+  static constexpr int S_B1 = S_TAPS + NTAP * TAP_BYTES;              // b1f[hidden], cs[hidden], hidden <= 1024
+  static constexpr int S_B2 = S_B1 + 2 * 1024 * 4;                    // b2[C]
+  static constexpr int S_STATS = S_B2 + 1024;                         // [2][192] float2
+  static constexpr int S_MISC = S_STATS + 2 * 192 * 8;
+  static constexpr int SMEM_BYTES = S_MISC + 2048 + 1024;
+  static constexpr int T_D1 = 0;                            // 2 x (SL cols M=128 part | SL cols M=64 part)
+  static constexpr int T_D2 = 4 * SL;                       // ND2 x C columns
+  static constexpr int ND2 = (4 * SL + 2 * C <= 512) ? 2 : 1;
+  static constexpr int T_ALLOC = 512;
+  static_assert(C <= 256 && C % 16 == 0, "fused LeFF: C in {16,32,64,128,256}");
+  static_assert(W1_CHUNK <= kStageBytes && W2_CHUNK <= kStageBytes, "ring stage");
+  static_assert(S_RING % 1024 == 0 && S_A2 % 1024 == 0 && S_HALO % 1024 == 0, "operand alignment");
+  static_assert(T_D2 + ND2 * C <= 512, "TMEM budget");
+  static_assert(SMEM_BYTES <= 232448, "smem budget");
+};
+
+struct LeffFMisc {
+  uint64_t bar_full[4], bar_empty[4];
+  uint64_t bar_x_full[2], bar_x_empty[2];
+  uint64_t bar_st_full[2], bar_st_empty[2];
+  uint64_t bar_d1_full[2], bar_d1_empty[2];
+  uint64_t bar_h_full[2], bar_h_empty[2];
+  uint64_t bar_a2_full[2], bar_a2_empty[2];
+  uint64_t bar_d2_full[2], bar_d2_empty[2];
+  uint64_t bar_tap_full[4], bar_tap_empty[4];
+  uint32_t tmem_base;
+  int row_out[128];
+};
+static_assert(sizeof(LeffFMisc) <= 2048, "misc too large");
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst_smem, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst_smem),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void lf_e_bar() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
+
+// E2 copy-out: staged [128 rows][32 cols] bf16 tile -> out rows (bf16 or fp32), residual (bf16 or fp32) added in fp32.
+// 128 threads; 4 threads per row (8 columns each).
+__device__ __forceinline__ void lf_store_rows(uint32_t stage_s, const int* row_out, const LeffFArgs& a, int col0, int et) {
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const int i = et + p * 128;
+    const int row = i >> 2, vec = i & 3;
+    const int tok = row_out[row];
+    if (tok < 0) continue;
+    float f[8];
+    unpack8(lds128(stage_s + row * 80 + vec * 16), f);
+    const int c = col0 + vec * 8;
+    if (a.resid != nullptr) {
+      if (a.resid_fp32) {
+        const float* rp = reinterpret_cast<const float*>(a.resid) + (size_t)tok * a.resid_stride + c;
+        const float4 r0 = __ldg(reinterpret_cast<const float4*>(rp)), r1 = __ldg(reinterpret_cast<const float4*>(rp + 4));
+        f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w; f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
+      } else {
+        float r[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(a.resid) + (size_t)tok * a.resid_stride + c)), r);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] += r[k];
+      }
+    }
+    if (a.out_fp32) {
+      float* op = reinterpret_cast<float*>(a.out) + (size_t)tok * a.out_stride + c;
+      *reinterpret_cast<float4*>(op) = make_float4(f[0], f[1], f[2], f[3]);
+      *reinterpret_cast<float4*>(op + 4) = make_float4(f[4], f[5], f[6], f[7]);
+    } else {
+      *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(a.out) + (size_t)tok * a.out_stride + c) = pack8(f);
+    }
+  }
+}
+
+template <int C>
+__global__ void __launch_bounds__(kLFThreads, 1) leff_fused_kernel(const __grid_constant__ CUtensorMap xmap, const LeffFArgs a) {
+  using Cfg = LeffFCfg<C>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  LeffFMisc& ms = *reinterpret_cast<LeffFMisc*>(smem + Cfg::S_MISC);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int SL = Cfg::SL;
+  const int NS = a.hidden / SL;
+  const int my_tiles = ((int)blockIdx.x < a.n_tiles) ? (a.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int total = my_tiles * NS;                    // hidden slices this CTA walks
+
+  if (tid == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(smem_u32(&ms.bar_full[s]), 1); mbar_init(smem_u32(&ms.bar_empty[s]), 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&ms.bar_x_full[i]), 1);  mbar_init(smem_u32(&ms.bar_x_empty[i]), 3);      // GEMM-1 commit + 2 stats warps
+      mbar_init(smem_u32(&ms.bar_st_full[i]), 2); mbar_init(smem_u32(&ms.bar_st_empty[i]), 4);     // one lane per warp
+      mbar_init(smem_u32(&ms.bar_d1_full[i]), 1); mbar_init(smem_u32(&ms.bar_d1_empty[i]), 128);
+      mbar_init(smem_u32(&ms.bar_h_full[i]), 128); mbar_init(smem_u32(&ms.bar_h_empty[i]), kLFConv);
+      mbar_init(smem_u32(&ms.bar_a2_full[i]), kLFConv); mbar_init(smem_u32(&ms.bar_a2_empty[i]), 1);
+      mbar_init(smem_u32(&ms.bar_d2_full[i]), 1); mbar_init(smem_u32(&ms.bar_d2_empty[i]), 128);
+    }
+    for (int i = 0; i < Cfg::NTAP; ++i) { mbar_init(smem_u32(&ms.bar_tap_full[i]), 1); mbar_init(smem_u32(&ms.bar_tap_empty[i]), kLFConv); }
+    fence_mbar_init();
+    tma_prefetch_desc(&xmap);
+  }
+  if (warp == 12) tmem_alloc(smem_u32(&ms.tmem_base), Cfg::T_ALLOC);
+  // resident per-channel tables: b1f, cs, b2; the never-loaded A rows 180..191 are zeroed once
+  {
+    for (int i = tid; i < a.hidden; i += kLFThreads) {
+      reinterpret_cast<float*>(smem + Cfg::S_B1)[i] = __ldg(a.b1f + i);
+      reinterpret_cast<float*>(smem + Cfg::S_B1)[a.hidden + i] = __ldg(a.cs + i);
+    }
+    for (int i = tid; i < C; i += kLFThreads) reinterpret_cast<float*>(smem + Cfg::S_B2)[i] = __ldg(a.b2 + i);
+    constexpr int PAD_WORDS = 12 * Cfg::SW / 4;
+    for (int i = tid; i < Cfg::NA1 * Cfg::KB1 * PAD_WORDS; i += kLFThreads) {
+      const int buf = i / PAD_WORDS, w = i % PAD_WORDS;
+      reinterpret_cast<uint32_t*>(smem + Cfg::S_A1 + buf * Cfg::A1_KB_BYTES + 180 * Cfg::SW)[w] = 0u;
+    }
+    fence_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = ms.tmem_base;
+  const int wg = warp >> 2;
+
+  auto tile_of = [&](int it) { return (int)blockIdx.x + it * (int)gridDim.x; };
+
+  if (wg == 3) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    if (warp == 12) {
+      // ============================== producer: input tiles (TMA boxes) + weight ring ==============================
+      if (lane == 0) {
+        Ring ring{smem_u32(smem + Cfg::S_RING), smem_u32(&ms.bar_full[0]), smem_u32(&ms.bar_empty[0]), Cfg::STAGES, 0};
+        auto load_x = [&](int it) {
+          const int ab = it % Cfg::NA1, use = it / Cfg::NA1;
+          mbar_wait(smem_u32(&ms.bar_x_empty[ab]), (use & 1) ^ 1);
+          const int tile = tile_of(it);
+          const int tx = tile % a.tiles_x, ty = (tile / a.tiles_x) % a.tiles_y, b = tile / (a.tiles_x * a.tiles_y);
+          const uint32_t bar = smem_u32(&ms.bar_x_full[ab]);
+          mbar_expect_tx(bar, Cfg::KB1 * Cfg::X_BOX_BYTES);
+#pragma unroll
+          for (int kb = 0; kb < Cfg::KB1; ++kb)
+            tma_load_4d(smem_u32(smem + Cfg::S_A1 + ab * Cfg::A1_BYTES + kb * Cfg::A1_KB_BYTES), &xmap, kb * 64, tx * 16 - 1, ty * 8 - 1, b, bar);
+        };
+        if (my_tiles > 0) load_x(0);
+        for (int k = 0; k < total + 2; ++k) {
+          if (k < total) {
+            const int j = k % NS, it = k / NS;
+            if (j == 0) {
+              if (Cfg::NA1 == 2) { if (it + 1 < my_tiles) load_x(it + 1); }
+              else if (it > 0) load_x(it);
+            }
+            {   // depthwise taps + conv bias of this slice (consumed by the conv warps two pipeline slots later)
+              const int tbuf = k % Cfg::NTAP;
+              mbar_wait(smem_u32(&ms.bar_tap_empty[tbuf]), ((k / Cfg::NTAP) & 1) ^ 1);
+              mbar_expect_tx(smem_u32(&ms.bar_tap_full[tbuf]), Cfg::TAP_BYTES);
+              bulk_g2s(smem_u32(smem + Cfg::S_TAPS + tbuf * Cfg::TAP_BYTES), a.taps + (size_t)j * 10 * SL, Cfg::TAP_BYTES, smem_u32(&ms.bar_tap_full[tbuf]));
+            }
+            ring.load(a.w1_img + (size_t)j * Cfg::W1_CHUNK, Cfg::W1_CHUNK);
+          }
+          if (k >= 2) ring.load(a.w2_img + (size_t)((k - 2) % NS) * Cfg::W2_CHUNK, Cfg::W2_CHUNK);
+        }
+      }
+    } else if (warp == 13) {
+      // ============================== issuer (warp-uniform; one elected lane issues) ==============================
+      Ring ring{smem_u32(smem + Cfg::S_RING), smem_u32(&ms.bar_full[0]), smem_u32(&ms.bar_empty[0]), Cfg::STAGES, 0};
+      constexpr uint32_t idesc_g1a = make_idesc_bf16(128, SL), idesc_g1b = make_idesc_bf16(64, SL), idesc_g2 = make_idesc_bf16(128, C);
+      for (int k = 0; k < total + 2; ++k) {
+        if (k < total) {
+          // ---- GEMM-1 of slice k: D1[k&1] = X W1'_j^T ----
+          const int j = k % NS, it = k / NS, ab = it % Cfg::NA1, db = k & 1;
+          if (j == 0) { mbar_wait(smem_u32(&ms.bar_x_full[ab]), (it / Cfg::NA1) & 1); }
+          mbar_wait(smem_u32(&ms.bar_d1_empty[db]), ((k >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t wst = ring.acquire();
+          const uint32_t xs = smem_u32(smem + Cfg::S_A1 + ab * Cfg::A1_BYTES);
+          if (elect_one()) {
+#pragma unroll
+            for (int kb = 0; kb < Cfg::KB1; ++kb)
+#pragma unroll
+              for (int ks = 0; ks < Cfg::KS1; ++ks) {
+                const uint64_t bd = kmajor_desc<Cfg::SW>(wst + kb * SL * Cfg::SW + ks * 32);
+                umma_ss(tb + Cfg::T_D1 + db * 2 * SL, kmajor_desc<Cfg::SW>(xs + kb * Cfg::A1_KB_BYTES + ks * 32), bd, idesc_g1a, (kb | ks) != 0);
+                umma_ss(tb + Cfg::T_D1 + db * 2 * SL + SL, kmajor_desc<Cfg::SW>(xs + kb * Cfg::A1_KB_BYTES + 128 * Cfg::SW + ks * 32), bd, idesc_g1b,
+                        (kb | ks) != 0);
+              }
+          }
+          __syncwarp();
+          ring.release();
+          if (elect_one()) {
+            umma_commit(smem_u32(&ms.bar_d1_full[db]));
+            if (j == NS - 1) umma_commit(smem_u32(&ms.bar_x_empty[ab]));
+          }
+          __syncwarp();
+        }
+        if (k >= 2) {
+          // ---- GEMM-2 of slice g = k-2: D2[tile & 1] += A2[g&1] W2_j^T ----
+          const int g = k - 2, j = g % NS, it = g / NS, ob = it % Cfg::ND2, ab2 = g & 1;
+          if (j == 0) { mbar_wait(smem_u32(&ms.bar_d2_empty[ob]), ((it / Cfg::ND2) & 1) ^ 1); }
+          mbar_wait(smem_u32(&ms.bar_a2_full[ab2]), (g >> 1) & 1);
+          tc_fence_after();
+          const uint32_t wst = ring.acquire();
+          if (elect_one()) {
+            const uint64_t ad = kmajor_desc<Cfg::SWH>(smem_u32(smem + Cfg::S_A2 + ab2 * Cfg::A2_BYTES)), bd = kmajor_desc<Cfg::SWH>(wst);
+#pragma unroll
+            for (int ks = 0; ks < SL / 16; ++ks) umma_ss(tb + Cfg::T_D2 + ob * C, ad + 2 * ks, bd + 2 * ks, idesc_g2, (j | ks) != 0);
+          }
+          __syncwarp();
+          ring.release();
+          if (elect_one()) {
+            umma_commit(smem_u32(&ms.bar_a2_empty[ab2]));
+            if (j == NS - 1) umma_commit(smem_u32(&ms.bar_d2_full[ob]));
+          }
+          __syncwarp();
+        }
+      }
+    } else {
+      // ============================== stats warps 14, 15: LayerNorm statistics of the 180 halo rows ==============================
+      const int sw = warp - 14;                            // rows sw*96 .. sw*96+95
+      constexpr int LPR = Cfg::SW / 16;                    // lanes per row inside a k-block (16-byte vectors): 8 / 4 / 2
+      constexpr int RPP = 32 / LPR;                        // rows per pass
+      const int sub = lane % LPR, rin = lane / LPR;
+      for (int it = 0; it < my_tiles; ++it) {
+        const int ab = it % Cfg::NA1, sb = it & 1;
+        const int tile = tile_of(it);
+        const int tx = tile % a.tiles_x, ty = (tile / a.tiles_x) % a.tiles_y;
+        mbar_wait(smem_u32(&ms.bar_st_empty[sb]), ((it >> 1) & 1) ^ 1);
+        mbar_wait(smem_u32(&ms.bar_x_full[ab]), (it / Cfg::NA1) & 1);
+        const uint32_t xs = smem_u32(smem + Cfg::S_A1 + ab * Cfg::A1_BYTES);
+        float2* st = reinterpret_cast<float2*>(smem + Cfg::S_STATS) + sb * 192;
+        for (int r0 = sw * 96; r0 < sw * 96 + 96; r0 += RPP) {
+          const int r = r0 + rin;
+          float v[Cfg::KB1][8];
+#pragma unroll
+          for (int kb = 0; kb < Cfg::KB1; ++kb) unpack8(lds128(xs + kb * Cfg::A1_KB_BYTES + swz<Cfg::SW>(r, sub * 16)), v[kb]);
+          float s = 0.f;
+#pragma unroll
+          for (int kb = 0; kb < Cfg::KB1; ++kb)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s += v[kb][i];
+#pragma unroll
+          for (int o = 1; o < LPR; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+          const float mean = s * (1.0f / C);
+          float q = 0.f;
+#pragma unroll
+          for (int kb = 0; kb < Cfg::KB1; ++kb)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const float d = v[kb][i] - mean; q += d * d; }
+#pragma unroll
+          for (int o = 1; o < LPR; o <<= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+          if (sub == 0) {
+            const int hy = r / 18, hx = r - hy * 18;
+            const int y = ty * 8 - 1 + hy, x = tx * 16 - 1 + hx;
+            const bool valid = (r < 180) && (y >= 0) && (y < a.H) && (x >= 0) && (x < a.W);
+            float rstd = 1.0f, nm = 0.0f;
+            if (a.has_ln) { rstd = rsqrtf(q * (1.0f / C) + a.ln_eps); nm = -mean * rstd; }
+            st[r] = valid ? make_float2(rstd, nm) : make_float2(-1.0f, 0.0f);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(smem_u32(&ms.bar_st_full[sb]));
+          mbar_arrive(smem_u32(&ms.bar_x_empty[ab]));
+        }
+      }
+    }
+  } else if (wg == 2) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    // ============================== E1 / E2 warps 8-11 (TMEM lane quadrant q) ==============================
+    const int q = warp & 3, et = tid - 256;
+    const int t4 = lane >> 2, tq = lane & 3;
+    const int m = lane >> 3, rr = lane & 7;
+    const uint32_t halo0 = smem_u32(smem + Cfg::S_HALO), stage_s = smem_u32(smem + Cfg::S_STAGE);
+    const uint32_t b1_s = smem_u32(smem + Cfg::S_B1), b2_s = smem_u32(smem + Cfg::S_B2), stats_s = smem_u32(smem + Cfg::S_STATS);
+
+    auto epilogue2 = [&](int it) {
+      const int ob = it % Cfg::ND2;
+      const int tile = tile_of(it);
+      {
+        const int tx = tile % a.tiles_x, ty = (tile / a.tiles_x) % a.tiles_y, b = tile / (a.tiles_x * a.tiles_y);
+        const int y = ty * 8 + (et >> 4), x = tx * 16 + (et & 15);
+        ms.row_out[et] = (x < a.W) ? ((b * a.H + y) * a.W + x) : -1;
+      }
+      mbar_wait(smem_u32(&ms.bar_d2_full[ob]), (it / Cfg::ND2) & 1);
+      tc_fence_after();
+      for (int sc = 0; sc < C; sc += 32) {
+        constexpr int NB = (C >= 32) ? 4 : 2;              // C = 16: one 16-column pass
+#pragma unroll
+        for (int hl = 0; hl < 2; ++hl) {
+          const int row16 = q * 32 + hl * 16;
+          uint32_t v[4 * NB];
+          const uint32_t ta = tb + ((uint32_t)row16 << 16) + Cfg::T_D2 + ob * C + sc;
+          if (NB == 4) tmem_ld_16x256b_x4(ta, v); else tmem_ld_16x256b_x2(ta, v);
+          f2 bb[NB];
+#pragma unroll
+          for (int i = 0; i < NB; ++i) { const float2 b2 = lds64f(b2_s + (sc + 8 * i + 2 * tq) * 4); bb[i] = f2_pack(b2.x, b2.y); }
+          tmem_wait_ld();
+          uint32_t pk[2 * NB];
+          frag_bias_act_pack<NB, false>(v, bb, pk);
+          stage_frag<NB>(stage_s, Cfg::STAGE_PITCH, row16, 0, pk);
+        }
+        if (sc + 32 >= C) { tc_fence_before(); mbar_arrive(smem_u32(&ms.bar_d2_empty[ob])); }
+        lf_e_bar();
+        if (C >= 32) lf_store_rows(stage_s, ms.row_out, a, sc, et);
+        else {                                              // C = 16: two 8-column vectors per row
+          for (int i = et; i < 256; i += 128) {
+            const int row = i >> 1, vec = i & 1, tok = ms.row_out[row];
+            if (tok < 0) continue;
+            float f[8];
+            unpack8(lds128(stage_s + row * 80 + vec * 16), f);
+            const int c = vec * 8;
+            if (a.resid != nullptr) {
+              if (a.resid_fp32) {
+                const float* rp = reinterpret_cast<const float*>(a.resid) + (size_t)tok * a.resid_stride + c;
+#pragma unroll
+                for (int k2 = 0; k2 < 8; ++k2) f[k2] += __ldg(rp + k2);
+              } else {
+                float r[8];
+                unpack8(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(a.resid) + (size_t)tok * a.resid_stride + c)), r);
+#pragma unroll
+                for (int k2 = 0; k2 < 8; ++k2) f[k2] += r[k2];
+              }
+            }
+            if (a.out_fp32) {
+              float* op = reinterpret_cast<float*>(a.out) + (size_t)tok * a.out_stride + c;
+#pragma unroll
+              for (int k2 = 0; k2 < 8; ++k2) op[k2] = f[k2];
+            } else {
+              *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(a.out) + (size_t)tok * a.out_stride + c) = pack8(f);
+            }
+          }
+        }
+        lf_e_bar();
+      }
+    };
+
+    for (int k = 0; k < total; ++k) {
+      const int j = k % NS, it = k / NS, db = k & 1, sb = it & 1;
+      if (j == 0) mbar_wait(smem_u32(&ms.bar_st_full[sb]), (it >> 1) & 1);
+      mbar_wait(smem_u32(&ms.bar_h_empty[db]), ((k >> 1) & 1) ^ 1);          // conv finished reading this halo buffer (slice k-2)
+      mbar_wait(smem_u32(&ms.bar_d1_full[db]), (k >> 1) & 1);
+      tc_fence_after();
+      const uint32_t hb = halo0 + db * Cfg::HALO_BYTES;
+      const uint32_t bsl = b1_s + j * SL * 4, csl = b1_s + (a.hidden + j * SL) * 4;
+#pragma unroll 1
+      for (int f = 0; f < 3; ++f) {
+        // fragment f of this quadrant: 16 TMEM lanes x SL columns.  f < 2: rows 32q + 16f of the M=128 part;
+        // f == 2: rows 128 + 16q of the M=64 part (its 64 rows sit 16 per lane quadrant)
+        const uint32_t lanes = (uint32_t)(q * 32 + (f == 1 ? 16 : 0)) << 16;
+        const uint32_t tcol = tb + lanes + Cfg::T_D1 + db * 2 * SL + (f == 2 ? SL : 0);
+        const int row0 = (f < 2) ? q * 32 + f * 16 : 128 + q * 16;
+        const float2 sa = lds64f(stats_s + (sb * 192 + row0 + t4) * 8), sbb = lds64f(stats_s + (sb * 192 + row0 + t4 + 8) * 8);
+        const bool va = sa.x > 0.f, vb = sbb.x > 0.f;
+        const f2 ra = f2_pack(sa.x, sa.x), na = f2_pack(sa.y, sa.y), rb = f2_pack(sbb.x, sbb.x), nb = f2_pack(sbb.y, sbb.y);
+#pragma unroll
+        for (int half = 0; half < SL / 32; ++half) {
+          uint32_t v[16];
+          tmem_ld_16x256b_x4(tcol + half * 32, v);
+          f2 bb[4], cc[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int n = half * 32 + 8 * i + 2 * tq;
+            const float2 b2 = lds64f(bsl + n * 4), c2 = lds64f(csl + n * 4);
+            bb[i] = f2_pack(b2.x, b2.y); cc[i] = f2_pack(c2.x, c2.y);
+          }
+          tmem_wait_ld();
+          uint32_t pk[8];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const f2 d0 = f2_pack(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]));
+            const f2 d1 = f2_pack(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+            const f2 x0 = f2_fma(d0, ra, f2_fma(na, cc[i], bb[i]));
+            const f2 x1 = f2_fma(d1, rb, f2_fma(nb, cc[i], bb[i]));
+            pk[2 * i] = va ? f2_to_bf2(gelu2(x0)) : 0u;
+            pk[2 * i + 1] = vb ? f2_to_bf2(gelu2(x1)) : 0u;
+          }
+          const int row = row0 + (m & 1) * 8 + rr;
+#pragma unroll
+          for (int i2 = 0; i2 < 2; ++i2)
+            stsm_x4(hb + swz<Cfg::SWH>(row, (half * 4 + 2 * i2 + (m >> 1)) * 16), pk[4 * i2], pk[4 * i2 + 1], pk[4 * i2 + 2], pk[4 * i2 + 3]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(smem_u32(&ms.bar_d1_empty[db]));
+      mbar_arrive(smem_u32(&ms.bar_h_full[db]));
+      if (j == NS - 1) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&ms.bar_st_empty[sb]));
+      }
+      // the previous tile's output epilogue runs one or two slices into this tile (its GEMM-2 chain has drained by then)
+      if (it > 0 && j == ((NS > 1 && Cfg::ND2 == 2) ? 1 : 0)) epilogue2(it - 1);
+    }
+    if (my_tiles > 0) epilogue2(my_tiles - 1);
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
+    // ============================== conv warps 0-7 ==============================
+    // SL = 64: warp = channel octet, lanes = 16 columns x 2 row halves, 4 output rows per lane (6 halo rows).
+    // SL = 32: warp = (octet, row half), lanes = 16 columns x 2 row pairs, 2 output rows per lane (4 halo rows).
+    constexpr int NV = SL / 8;                     // octets per slice
+    constexpr int RPL = (SL == 64) ? 4 : 2;        // output rows per lane
+    const int v = warp % NV;
+    const int cx = lane & 15;
+    const int rbase = (SL == 64) ? (lane >> 4) * 4 : (warp / NV) * 4 + (lane >> 4) * 2;     // first output row of this lane
+    const uint32_t halo0 = smem_u32(smem + Cfg::S_HALO), taps0 = smem_u32(smem + Cfg::S_TAPS);
+    for (int k = 0; k < total; ++k) {
+      const int hbi = k & 1, tbuf = k % Cfg::NTAP;
+      const uint32_t sH = halo0 + hbi * Cfg::HALO_BYTES;
+      const uint32_t sW = taps0 + tbuf * Cfg::TAP_BYTES + v * 32;       // tap t at + t * SL * 4
+      constexpr uint32_t tstride = SL * 4;
+      mbar_wait(smem_u32(&ms.bar_tap_full[tbuf]), (k / Cfg::NTAP) & 1);
+      f2 acc[RPL][4];
+      {
+        const float4 b0 = lds128f(sW + 9 * tstride);
+        const float4 b1 = lds128f(sW + 9 * tstride + 16);
+#pragma unroll
+        for (int o = 0; o < RPL; ++o) {
+          acc[o][0] = f2_pack(b0.x, b0.y); acc[o][1] = f2_pack(b0.z, b0.w);
+          acc[o][2] = f2_pack(b1.x, b1.y); acc[o][3] = f2_pack(b1.z, b1.w);
+        }
+      }
+      mbar_wait(smem_u32(&ms.bar_h_full[hbi]), (k >> 1) & 1);
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        f2 h[RPL + 2][4];
+#pragma unroll
+        for (int r = 0; r < RPL + 2; ++r) {
+          const int t = (rbase + r) * 18 + cx + dx;
+          const uint4 raw = lds128(sH + swz<Cfg::SWH>(t, v * 16));
+          h[r][0] = bf2_to_f2(raw.x); h[r][1] = bf2_to_f2(raw.y); h[r][2] = bf2_to_f2(raw.z); h[r][3] = bf2_to_f2(raw.w);
+        }
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          const float4 w0 = lds128f(sW + (ky * 3 + dx) * tstride);        // warp-uniform address: broadcast
+          const float4 w1 = lds128f(sW + (ky * 3 + dx) * tstride + 16);
+          const f2 wa = f2_pack(w0.x, w0.y), wb = f2_pack(w0.z, w0.w), wc = f2_pack(w1.x, w1.y), wdd = f2_pack(w1.z, w1.w);
+#pragma unroll
+          for (int o = 0; o < RPL; ++o) {
+            acc[o][0] = f2_fma(h[o + ky][0], wa, acc[o][0]);
+            acc[o][1] = f2_fma(h[o + ky][1], wb, acc[o][1]);
+            acc[o][2] = f2_fma(h[o + ky][2], wc, acc[o][2]);
+            acc[o][3] = f2_fma(h[o + ky][3], wdd, acc[o][3]);
+          }
+        }
+      }
+      mbar_arrive(smem_u32(&ms.bar_h_empty[hbi]));                 // halo buffer free for E1 of slice k+2
+      mbar_arrive(smem_u32(&ms.bar_tap_empty[tbuf]));
+      mbar_wait(smem_u32(&ms.bar_a2_empty[hbi]), ((k >> 1) & 1) ^ 1);   // GEMM-2 of slice k-2 has consumed this A buffer
+      const uint32_t sA = smem_u32(smem + Cfg::S_A2 + hbi * Cfg::A2_BYTES);
+#pragma unroll
+      for (int o = 0; o < RPL; ++o) {
+        uint4 pk;
+        pk.x = f2_to_bf2(gelu2(acc[o][0]));
+        pk.y = f2_to_bf2(gelu2(acc[o][1]));
+        pk.z = f2_to_bf2(gelu2(acc[o][2]));
+        pk.w = f2_to_bf2(gelu2(acc[o][3]));
+        const int rw = (rbase + o) * 16 + cx;
+        sts128(sA + swz<Cfg::SWH>(rw, v * 16), pk);
+      }
+      fence_async_smem();
+      mbar_arrive(smem_u32(&ms.bar_a2_full[hbi]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 12) tmem_dealloc(tb, Cfg::T_ALLOC);
+}
+
+}  // namespace lw

@@ -6,6 +6,7 @@
 #include "wmsa.cuh"
 #include "leff.cuh"
 #include "leff2.cuh"
+#include "leff_fused.cuh"
 #include "down.cuh"
 #include "proj.cuh"
 #include "train.cuh"
@@ -195,6 +196,87 @@ extern "C" int lw_leff2_fwd(const lw_leff2_args* p, lw_stream_t stream) {
   leff2_kernel<<<grid, kL2Threads, Leff2Cfg::SMEM_BYTES, st>>>(a, pow2_cols(nbuf_d * a.N), tiles, nbuf_d);
   LW_TRY(cudaGetLastError());
   return LW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA tensor maps are encoded by the driver (cuTensorMapEncodeTiled); the entry point is fetched through the runtime so the
+// library links against libcudart only.
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled encode_tiled_fn() {
+  static PFN_encodeTiled fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    return reinterpret_cast<PFN_encodeTiled>(p);
+  }();
+  return fn;
+}
+// bf16 token map (B, H, W, C) with row stride `stride` elements -> 4-D map (C, W, H, B), box (cb, bw, bh, 1), swizzle = 2*cb bytes
+static int make_token_map(CUtensorMap* m, const void* base, int B, int H, int W, int C, int stride, int cb, int bw, int bh) {
+  PFN_encodeTiled enc = encode_tiled_fn();
+  if (!enc) { snprintf(g_err, sizeof(g_err), "cuTensorMapEncodeTiled unavailable"); return LW_ERR_CUDA; }
+  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  const cuuint64_t strides[3] = {(cuuint64_t)stride * 2, (cuuint64_t)stride * 2 * W, (cuuint64_t)stride * 2 * W * H};
+  const cuuint32_t box[4] = {(cuuint32_t)cb, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUtensorMapSwizzle sw = cb * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : cb * 2 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { snprintf(g_err, sizeof(g_err), "cuTensorMapEncodeTiled failed (%d)", (int)r); return LW_ERR_CUDA; }
+  return LW_OK;
+}
+
+extern "C" int lw_leff_fused_supported(int C, int hidden) {
+  return (C == 16 || C == 32 || C == 64 || C == 128 || C == 256) && hidden % 64 == 0 && hidden >= 64 && hidden <= 1024;
+}
+
+extern "C" int lw_leff_slice(int C) { return C <= 128 ? 64 : 32; }
+
+template <int C>
+static int launch_leff_fused(const CUtensorMap& map, const LeffFArgs& a, cudaStream_t st) {
+  using Cfg = LeffFCfg<C>;
+  static bool attr_set = false;     // per-process, per-instantiation (re-setting it is harmless: benign race)
+  if (!attr_set) {
+    LW_TRY(cudaFuncSetAttribute(leff_fused_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int grid = a.n_tiles < sm_count() ? a.n_tiles : sm_count();
+  leff_fused_kernel<C><<<grid, kLFThreads, Cfg::SMEM_BYTES, st>>>(map, a);
+  LW_TRY(cudaGetLastError());
+  return LW_OK;
+}
+
+extern "C" int lw_leff_fwd(const lw_leff_args* p, lw_stream_t stream) {
+  if (!p || !p->x || !p->out || !p->w1_img || !p->b1f || !p->cs || !p->taps || !p->w2_img || !p->b2) return LW_ERR_NULL;
+  if (!lw_leff_fused_supported(p->C, p->hidden)) return LW_ERR_BAD_SHAPE;
+  if (p->B <= 0 || p->H <= 0 || p->W <= 0 || p->H % 8 || p->W % 8) return LW_ERR_BAD_SHAPE;
+  if (p->x_stride < p->C || p->x_stride % 8 || p->out_stride < p->C || p->out_stride % 8) return LW_ERR_BAD_SHAPE;
+  if (p->resid && (p->resid_stride < p->C || p->resid_stride % 8)) return LW_ERR_BAD_SHAPE;
+  if (p->out == p->x) return LW_ERR_BAD_SHAPE;                       // halo rows of x are read after neighbouring tiles were written
+  if ((long long)p->B * p->H * p->W >= (1ll << 31)) return LW_ERR_BAD_SHAPE;
+  if (!all_aligned16(p->x, p->out, p->resid, p->w1_img, p->b1f, p->cs, p->taps, p->w2_img, p->b2)) return LW_ERR_ALIGN;
+  CUtensorMap map;
+  const int cb = p->C < 64 ? p->C : 64;
+  const int rc = make_token_map(&map, p->x, p->B, p->H, p->W, p->C, p->x_stride, cb, 18, 10);
+  if (rc != LW_OK) return rc;
+  LeffFArgs a{};
+  a.B = p->B; a.H = p->H; a.W = p->W; a.hidden = p->hidden;
+  a.w1_img = reinterpret_cast<const uint8_t*>(p->w1_img); a.b1f = p->b1f; a.cs = p->cs; a.taps = p->taps;
+  a.w2_img = reinterpret_cast<const uint8_t*>(p->w2_img); a.b2 = p->b2;
+  a.resid = p->resid; a.out = p->out; a.resid_stride = p->resid_stride; a.out_stride = p->out_stride;
+  a.resid_fp32 = p->resid_fp32; a.out_fp32 = p->out_fp32; a.has_ln = p->has_ln; a.ln_eps = p->ln_eps;
+  a.tiles_x = (p->W + 15) / 16; a.tiles_y = p->H / 8; a.n_tiles = a.tiles_x * a.tiles_y * p->B;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (p->C) {
+    case 16: return launch_leff_fused<16>(map, a, st);
+    case 32: return launch_leff_fused<32>(map, a, st);
+    case 64: return launch_leff_fused<64>(map, a, st);
+    case 128: return launch_leff_fused<128>(map, a, st);
+    case 256: return launch_leff_fused<256>(map, a, st);
+    default: return LW_ERR_BAD_SHAPE;
+  }
 }
 
 extern "C" int lw_downsample_fwd(const lw_down_args* p, lw_stream_t stream) {

@@ -13,6 +13,7 @@ raises ``EngineUnavailable``.
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -215,21 +216,40 @@ class LeFF(nn.Module):
         self.hidden_dim = hidden_dim
         self.eca = nn.Identity()
         self._cache = _PackCache()
+        self._cache_ln = _PackCache()
 
     def pack_sources(self):
         l1, dw, l2 = self.linear1[0], self.dwconv[0], self.linear2[0]
         return [l1.weight, l1.bias, dw.weight, dw.bias, l2.weight, l2.bias]
 
-    def packed(self):
-        srcs = self.pack_sources()
+    def fused(self) -> bool:
+        """True when the single-kernel LeFF (lw_leff_fwd) covers this shape; wider blocks use the two-kernel pair."""
+        if os.environ.get("UFORMER_B200_LEFF", "fused") == "split":        # A/B switch for measurements (tools/, bench.py)
+            return False
+        return bool(_lib.load().lw_leff_fused_supported(self.dim, self.hidden_dim))
+
+    def packed(self, norm: nn.LayerNorm | None = None):
+        """Operand dict for ops.leff.  `norm` is the LayerNorm applied in front (the block's norm2, model.py:987): the fused
+        kernel folds it into linear1 (packing.pack_leff_fused); the two-kernel path passes its affine through."""
+        srcs = self.pack_sources() + ([norm.weight, norm.bias] if norm is not None else [])
+        cache = self._cache if norm is None else self._cache_ln
 
         def build():
-            w1, b1, wdw, bdw, w2, b2 = srcs
+            w1, b1, wdw, bdw, w2, b2 = srcs[:6]
+            eps = norm.eps if norm is not None else 1e-5
+            if self.fused():
+                d = packing.pack_leff_fused(w1, b1, None if norm is None else norm.weight, None if norm is None else norm.bias,
+                                            wdw, bdw, w2, b2, _lib.load().lw_leff_slice(self.dim))
+                d["ln_eps"] = eps
+                return d
             wd, bd = packing.pack_dwconv(wdw, bdw)
-            return dict(w1_img=packing.pack_kmajor(w1, _lib.load().lw_nch_ares(self.dim, self.hidden_dim), "nk"), b1=b1.float().contiguous(),
-                        wd=wd, bd=bd, w2_img=packing.pack_kmajor(w2, min(self.dim, 128), "kn"),
-                        b2=b2.float().contiguous(), hidden=self.hidden_dim)
-        return self._cache.get(srcs, build)
+            d = dict(w1_img=packing.pack_kmajor(w1, _lib.load().lw_nch_ares(self.dim, self.hidden_dim), "nk"), b1=b1.float().contiguous(),
+                     wd=wd, bd=bd, w2_img=packing.pack_kmajor(w2, min(self.dim, 128), "kn"),
+                     b2=b2.float().contiguous(), hidden=self.hidden_dim, ln_eps=eps)
+            if norm is not None:
+                d.update(ln_w=norm.weight.float().contiguous(), ln_b=norm.bias.float().contiguous())
+            return d
+        return cache.get(srcs, build)
 
     def _check_supported(self):
         if self.dim % 16 or self.dim > 512 or self.hidden_dim % 64 or self.dim not in (16, 32, 64, 128, 256, 512):
@@ -401,7 +421,7 @@ class LeWinTransformerBlock(nn.Module):
             a1, a2, m = split(rest)
             pk = self.packed()
             pa = dict(self.attn.packed(), ln_w=pk["ln1_w"], ln_b=pk["ln1_b"], modulator=pk["modulator"], ln_eps=self.norm1.eps)
-            pm = dict(self.mlp.packed(), ln_w=pk["ln2_w"], ln_b=pk["ln2_b"], ln_eps=self.norm2.eps)
+            pm = self.mlp.packed(self.norm2)
             amask = None if m is None else self.input_mask_to_attn_mask(m, H, W, 8)
             if a1 is None:
                 x1 = ops.wmsa(t, pa, H=H, W=W, shift=self.shift_size, windowed=False, resid=t, mask=amask)
@@ -433,12 +453,14 @@ class LeWinTransformerBlock(nn.Module):
         model's parity error.  Inference only; returns fp32."""
         pk = self.packed()
         pa = dict(self.attn.packed(), ln_w=pk["ln1_w"], ln_b=pk["ln1_b"], modulator=pk["modulator"], ln_eps=self.norm1.eps)
-        pm = dict(self.mlp.packed(), ln_w=pk["ln2_w"], ln_b=pk["ln2_b"], ln_eps=self.norm2.eps)
+        pm = self.mlp.packed(self.norm2)
         xb = x.contiguous() if x.dtype == torch.bfloat16 else x.to(torch.bfloat16).contiguous()
         a = ops.wmsa(xb, pa, H=H, W=W, shift=self.shift_size, windowed=False, resid=None)
         x1 = torch.add(x if x.dtype == torch.float32 else x.float(), a)          # fp32 + bf16 -> fp32, one pass
-        f = ops.leff(x1.to(torch.bfloat16), pm, B=B, H=H, W=W, resid=None)
-        return torch.add(x1, f)
+        x1b = x1.to(torch.bfloat16)
+        if self.mlp.fused():                                                      # residual read and output written in fp32 by the kernel
+            return ops.leff(x1b, pm, B=B, H=H, W=W, resid=x1, out_dtype=torch.float32)
+        return torch.add(x1, ops.leff(x1b, pm, B=B, H=H, W=W, resid=None))
 
     def flops(self):
         H, W = self.input_resolution

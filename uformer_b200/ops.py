@@ -28,7 +28,7 @@ def _launch(label: str, flops: float, fn, rc_name: str, device=None):
     if device is not None and device.type == "cuda" and device.index is not None and device.index != torch.cuda.current_device():
         with torch.cuda.device(device):
             return _launch(label, flops, fn, rc_name, None)
-    stream = torch.cuda.currentst.cuda_stream
+    stream = torch.cuda.current_stream().cuda_stream
     if PROFILE is None:
         _lib.check(fn(stream), rc_name)
         return
@@ -78,9 +78,46 @@ def wmsa(x: Tensor, p: dict, *, H: int, W: int, shift: int, windowed: bool, resi
     return out
 
 
-def leff(x: Tensor, p: dict, *, B: int, H: int, W: int, resid: Tensor | None, out: Tensor | None = None) -> Tensor:
-    """(LN) + Linear1 + GELU  ->  dwconv3x3 + GELU + Linear2 (+ residual).  Two launches; the hidden map
-    makes one bf16 round trip through HBM/L2 between them."""
+def _row_stride(t: Tensor, name: str) -> int:
+    """Row stride (elements) of a (B, L, C) / (rows, C) activation that may be a column slice of a wider buffer."""
+    if t.stride(-1) != 1 or (t.dim() == 3 and t.shape[0] > 1 and t.stride(0) != t.shape[1] * t.stride(1)):
+        raise ValueError(f"{name}: rows must be contiguous and uniformly strided")
+    return t.stride(-2)
+
+
+def leff(x: Tensor, p: dict, *, B: int, H: int, W: int, resid: Tensor | None, out: Tensor | None = None, out_dtype=None) -> Tensor:
+    """(LN) + Linear1 + GELU + dwconv3x3 + GELU + Linear2 (+ residual).
+    p from packing.pack_leff_fused (key "w1f_img"): ONE launch (lw_leff_fwd), the hidden map stays on chip; x / resid / out
+    may be column slices of wider buffers, resid / out may be fp32.  Otherwise (C = 512) the two-kernel path: the hidden
+    map makes one bf16 round trip through HBM/L2 between lw_leff1_fwd and lw_leff2_fwd."""
+    if "w1f_img" not in p:
+        return _leff_two_kernels(x, p, B=B, H=H, W=W, resid=resid, out=out)
+    if x.dtype != torch.bfloat16:
+        raise TypeError(f"x must be bfloat16 (got {x.dtype})")
+    _lib.require_device(x.device)
+    Cc, hidden = x.shape[-1], p["hidden"]
+    n_tokens = B * H * W
+    if out is None:
+        out = torch.empty((B, H * W, Cc) if x.dim() == 3 else (n_tokens, Cc), dtype=out_dtype or torch.bfloat16, device=x.device)
+    for t, nm in ((resid, "resid"), (out, "out")):
+        if t is not None and t.dtype not in (torch.bfloat16, torch.float32):
+            raise TypeError(f"{nm} must be bfloat16 or float32")
+    a = _lib.LeffArgs()
+    a.x, a.out, a.resid = _ptr(x), _ptr(out), _ptr(resid)
+    a.w1_img, a.b1f, a.cs, a.taps, a.w2_img, a.b2 = (_ptr(p["w1f_img"]), _ptr(p["b1f"]), _ptr(p["cs"]), _ptr(p["taps"]), _ptr(p["w2f_img"]),
+                                                     _ptr(p["b2"]))
+    a.B, a.H, a.W, a.C, a.hidden = B, H, W, Cc, hidden
+    a.x_stride, a.out_stride = _row_stride(x, "x"), _row_stride(out, "out")
+    a.resid_stride = _row_stride(resid, "resid") if resid is not None else 0
+    a.resid_fp32 = int(resid is not None and resid.dtype == torch.float32)
+    a.out_fp32 = int(out.dtype == torch.float32)
+    a.has_ln, a.ln_eps = int(p["has_ln"]), p.get("ln_eps", 1e-5)
+    lib = _lib.load()
+    _launch(f"leff_C{Cc}_T{n_tokens}", 2.0 * n_tokens * (2 * hidden * Cc + 9 * hidden), lambda st: lib.lw_leff_fwd(C.byref(a), st), "lw_leff_fwd", x.device)
+    return out
+
+
+def _leff_two_kernels(x: Tensor, p: dict, *, B: int, H: int, W: int, resid: Tensor | None, out: Tensor | None = None) -> Tensor:
     _check_act(x, "x")
     Cc, hidden = x.shape[-1], p["hidden"]
     n_tokens = B * H * W

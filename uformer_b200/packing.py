@@ -61,6 +61,66 @@ def unpack_kmajor(img: Tensor, N: int, K: int, nch: int, order: str = "nk") -> T
     return t[:, :K]
 
 
+def _swizzle_perm(nch: int, sw: int, device) -> Tensor:
+    """perm[n, k] = element offset inside a (nch rows x sw bytes) bf16 K-major tile image with SWIZZLE_<sw>B (sw in 32/64/128):
+    the 16-byte chunk index of byte offset `lin = n*sw + 2k` is XOR-ed with bits [7..] of lin (csrc/umma.cuh swz<SW>)."""
+    key = (nch, sw, str(device))
+    perm = _PERMS.get(key)
+    if perm is None:
+        n = torch.arange(nch)[:, None]
+        k = torch.arange(sw // 2)[None, :]
+        lin = n * sw + 2 * k
+        lin = lin ^ (((lin >> 7) & (sw // 16 - 1)) << 4)
+        perm = (lin // 2).to(device)
+        _PERMS[key] = perm
+    return perm
+
+
+def pack_kmajor_sw(w: Tensor, nch: int, sw: int) -> Tensor:
+    """(N, K) -> bf16 images [N/nch][KB][nch * sw/2] with rows of `sw` bytes (sw/2 channels per k-block, K % (sw/2) == 0)."""
+    N, K = w.shape
+    cb = sw // 2
+    assert N % nch == 0 and K % cb == 0, (N, K, nch, sw)
+    KB = K // cb
+    t = w.to(torch.bfloat16).reshape(N // nch, nch, KB, cb).permute(0, 2, 1, 3).reshape(N // nch, KB, nch * cb)
+    img = torch.empty_like(t)
+    img[:, :, _swizzle_perm(nch, sw, w.device).reshape(-1)] = t
+    return img.contiguous()
+
+
+def unpack_kmajor_sw(img: Tensor, N: int, K: int, nch: int, sw: int) -> Tensor:
+    """Inverse of pack_kmajor_sw (testing aid)."""
+    cb = sw // 2
+    KB = K // cb
+    t = img.float()[:, :, _swizzle_perm(nch, sw, img.device).reshape(-1)]
+    return t.reshape(N // nch, KB, nch, cb).permute(0, 2, 1, 3).reshape(N, K)
+
+
+def pack_leff_taps(wdw: Tensor, bdw: Tensor, sl: int) -> Tensor:
+    """Depthwise Conv2d(groups=hidden) weight (hidden,1,3,3) + bias -> [hidden/sl][10][sl] fp32: per hidden slice the 9 taps
+    (tap = ky*3+kx) then the bias, one contiguous bulk-copy chunk per slice."""
+    hid = wdw.shape[0]
+    t = torch.cat([wdw.float().reshape(hid, 9).t(), bdw.float()[None, :]], 0)            # (10, hidden)
+    return t.reshape(10, hid // sl, sl).permute(1, 0, 2).contiguous()
+
+
+def pack_leff_fused(w1: Tensor, b1: Tensor, ln_w, ln_b, wdw: Tensor, bdw: Tensor, w2: Tensor, b2: Tensor, sl: int = 64) -> dict:
+    """Operands of the single-kernel LeFF (csrc/leff_fused.cuh, lw_leff_fwd); `sl` = lw_leff_slice(C) hidden channels per slice.
+    LayerNorm (norm2, model.py:987) is folded into linear1 (model.py:671):
+      LN(x) W1^T + b1 = rstd*(x W1g^T) - rstd*mean*cs + b1f  with  W1g = W1 diag(gamma) rounded to bf16,
+    cs = row sums of that bf16 matrix (so the mean term cancels exactly against what the tensor core accumulates) and
+    b1f = b1 + W1 beta.  Without LayerNorm (LeFF standalone) W1g = W1, b1f = b1."""
+    hid, C = w1.shape
+    w1f, b1f = w1.float(), b1.float()
+    if ln_w is not None:
+        b1f = b1f + (w1f * ln_b.float()[None, :]).sum(1)       # same reduction as prepack.py (bit-identical images)
+        w1f = w1f * ln_w.float()[None, :]
+    w1g = w1f.to(torch.bfloat16)
+    return dict(w1f_img=pack_kmajor_sw(w1g, sl, 2 * min(C, 64)), b1f=b1f.contiguous(), cs=w1g.float().sum(1).contiguous(),
+                taps=pack_leff_taps(wdw, bdw, sl), w2f_img=pack_kmajor_sw(w2, C, 2 * sl), b2=b2.float().contiguous(), hidden=hid,
+                has_ln=ln_w is not None, slice=sl)
+
+
 def pack_qkv(wq: Tensor, bq: Tensor, wkv: Tensor, bkv: Tensor, heads: int, scale: float):
     """LinearProjection weights (model.py:421-447) -> per-head [q_h; k_h; v_h] row blocks.
     The attention scale (model.py:497, q * hd^-0.5) is folded into the q rows and q bias."""

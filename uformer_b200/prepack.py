@@ -59,18 +59,42 @@ def _pack_blocks(blks):
     nchp = min(C, 128)
     wproj_img = packing.pack_kmajor(stack(lambda b: b.attn.proj.weight).view(nb * C, C), nchp, "nk").view(nb, C // nchp, -1, nchp * 64)
     relpos = stack(lambda b: b.attn.relative_position_bias_table).transpose(1, 2).contiguous()          # (nb, heads, 225)
-    # ---- LeFF: linear1 (A-resident, "nk"), depthwise taps, linear2 (A-streamed, "kn") ----
-    nch1 = _lib.load().lw_nch_ares(C, hid)
-    w1_img = packing.pack_kmajor(stack(lambda b: b.mlp.linear1[0].weight).view(nb * hid, C), nch1, "nk").view(nb, hid // nch1, -1, nch1 * 64)
-    w2_nk = packing.pack_kmajor(stack(lambda b: b.mlp.linear2[0].weight).view(nb * C, hid), nchp, "nk").view(nb, C // nchp, -1, nchp * 64)
-    w2_img = w2_nk.permute(0, 2, 1, 3).contiguous()                                     # per block [KB][C/nch][nch*64]
+    # ---- LeFF.  Fused kernel (C <= 128): LayerNorm-folded linear1 in 64-row slices + row sums + folded bias, linear2 k-blocks
+    # (packing.pack_leff_fused).  Two-kernel path: linear1 (A-resident, "nk"), linear2 (A-streamed, "kn"). ----
+    lib = _lib.load()
+    fused = bool(lib.lw_leff_fused_supported(C, hid))
+    w1 = stack(lambda b: b.mlp.linear1[0].weight)                                       # (nb, hid, C)
+    b1 = stack(lambda b: b.mlp.linear1[0].bias)
     wd = stack(lambda b: b.mlp.dwconv[0].weight).view(nb, hid, 9).transpose(1, 2).contiguous()          # (nb, 9, hid)
+    bdw = stack(lambda b: b.mlp.dwconv[0].bias)                                         # (nb, hid)
+    w2 = stack(lambda b: b.mlp.linear2[0].weight)                                       # (nb, C, hid)
+    if fused:
+        gamma, beta = stack(lambda b: b.norm2.weight), stack(lambda b: b.norm2.bias)
+        b1f = (b1 + (w1 * beta[:, None, :]).sum(2)).contiguous()
+        w1g = (w1 * gamma[:, None, :]).to(torch.bfloat16)
+        cs = w1g.float().sum(2).contiguous()
+        sl = lib.lw_leff_slice(C)
+        w1f_img = packing.pack_kmajor_sw(w1g.view(nb * hid, C), sl, 2 * min(C, 64)).view(nb, hid // sl, -1, sl * min(C, 64))
+        w2f_img = packing.pack_kmajor_sw(w2.view(nb * C, hid), C, 2 * sl).view(nb, 1, hid // sl, C * sl)
+        taps = torch.cat([wd, bdw[:, None, :]], 1).view(nb, 10, hid // sl, sl).permute(0, 2, 1, 3).contiguous()      # (nb, NS, 10, sl)
+    else:
+        nch1 = lib.lw_nch_ares(C, hid)
+        w1_img = packing.pack_kmajor(w1.view(nb * hid, C), nch1, "nk").view(nb, hid // nch1, -1, nch1 * 64)
+        w2_nk = packing.pack_kmajor(w2.view(nb * C, hid), nchp, "nk").view(nb, C // nchp, -1, nchp * 64)
+        w2_img = w2_nk.permute(0, 2, 1, 3).contiguous()                                 # per block [KB][C/nch][nch*64]
 
     for i, b in enumerate(blks):
         a, m = b.attn, b.mlp
         a._cache.put(a.pack_sources(), dict(wqkv_img=wqkv_img[i], bqkv=bqkv[i], wproj_img=wproj_img[i],
                                             bproj=a.proj.bias.detach().float().contiguous(), relpos=relpos[i], head_dim=hd))
-        m._cache.put(m.pack_sources(), dict(w1_img=w1_img[i], b1=m.linear1[0].bias.detach().float().contiguous(), wd=wd[i],
-                                            bd=m.dwconv[0].bias.detach().float().contiguous(), w2_img=w2_img[i],
-                                            b2=m.linear2[0].bias.detach().float().contiguous(), hidden=hid))
-        b.packed()                                  # LN affine / modulator: fp32 views of the parameters, no launches
+        bd = m.dwconv[0].bias.detach().float().contiguous()
+        b2 = m.linear2[0].bias.detach().float().contiguous()
+        if fused:
+            d = dict(w1f_img=w1f_img[i], b1f=b1f[i], cs=cs[i], taps=taps[i], w2f_img=w2f_img[i], b2=b2, hidden=hid, has_ln=True,
+                     slice=sl, ln_eps=b.norm2.eps)
+        else:
+            d = dict(w1_img=w1_img[i], b1=m.linear1[0].bias.detach().float().contiguous(), wd=wd[i], bd=bd, w2_img=w2_img[i], b2=b2,
+                     hidden=hid, ln_eps=b.norm2.eps, ln_w=b.norm2.weight.detach().float().contiguous(),
+                     ln_b=b.norm2.bias.detach().float().contiguous())
+        m._cache_ln.put(m.pack_sources() + [b.norm2.weight, b.norm2.bias], d)
+        b.packed()                                  # LN1 affine / modulator: fp32 views of the parameters, no launches
