@@ -27,7 +27,7 @@
 
 namespace lw {
 
-constexpr int kLFThreads = 512;
+constexpr int kLFThreads = 640;       // 8 conv warps | 4 E1/E2 warps | producer, issuer, 2 stats warps | 4 E1/E2 warps
 constexpr int kLFConv = 256;
 
 struct LeffFArgs {
@@ -72,7 +72,7 @@ struct LeffFCfg {
   static constexpr int S_A2 = S_HALO + 2 * HALO_BYTES;
   static constexpr int S_RING = S_A2 + 2 * A2_BYTES;
   static constexpr int S_STAGE = S_RING + STAGES * kStageBytes;
-  static constexpr int S_TAPS = S_STAGE + 128 * STAGE_PITCH;          // NTAP x [10][SL] fp32
+  static constexpr int S_TAPS = S_STAGE + 2 * 128 * STAGE_PITCH;      // (two staging tiles: one per epilogue group)          // NTAP x [10][SL] fp32
   static constexpr int S_B1 = S_TAPS + NTAP * TAP_BYTES;              // b1f[hidden], cs[hidden], hidden <= 1024
   static constexpr int S_B2 = S_B1 + 2 * 1024 * 4;                    // b2[C]
   static constexpr int S_STATS = S_B2 + 1024;                         // [2][192] float2
@@ -99,7 +99,7 @@ struct LeffFMisc {
   uint64_t bar_d2_full[2], bar_d2_empty[2];
   uint64_t bar_tap_full[4], bar_tap_empty[4];
   uint32_t tmem_base;
-  int row_out[128];
+  int row_out[256];
 };
 static_assert(sizeof(LeffFMisc) <= 2048, "misc too large");
 
@@ -112,7 +112,6 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst_smem, const CUtensorMap
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
-__device__ __forceinline__ void lf_e_bar() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
 
 // E2 copy-out: staged [128 rows][32 cols] bf16 tile -> out rows (bf16 or fp32), residual (bf16 or fp32) added in fp32.
 // 128 threads; 4 threads per row (8 columns each).
@@ -164,11 +163,11 @@ __global__ void __launch_bounds__(kLFThreads, 1) leff_fused_kernel(const __grid_
     for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(smem_u32(&ms.bar_full[s]), 1); mbar_init(smem_u32(&ms.bar_empty[s]), 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&ms.bar_x_full[i]), 1);  mbar_init(smem_u32(&ms.bar_x_empty[i]), 3);      // GEMM-1 commit + 2 stats warps
-      mbar_init(smem_u32(&ms.bar_st_full[i]), 2); mbar_init(smem_u32(&ms.bar_st_empty[i]), 4);     // one lane per warp
-      mbar_init(smem_u32(&ms.bar_d1_full[i]), 1); mbar_init(smem_u32(&ms.bar_d1_empty[i]), 128);
-      mbar_init(smem_u32(&ms.bar_h_full[i]), 128); mbar_init(smem_u32(&ms.bar_h_empty[i]), kLFConv);
+      mbar_init(smem_u32(&ms.bar_st_full[i]), 2); mbar_init(smem_u32(&ms.bar_st_empty[i]), 8);     // one lane per warp
+      mbar_init(smem_u32(&ms.bar_d1_full[i]), 1); mbar_init(smem_u32(&ms.bar_d1_empty[i]), 256);
+      mbar_init(smem_u32(&ms.bar_h_full[i]), 256); mbar_init(smem_u32(&ms.bar_h_empty[i]), kLFConv);
       mbar_init(smem_u32(&ms.bar_a2_full[i]), kLFConv); mbar_init(smem_u32(&ms.bar_a2_empty[i]), 1);
-      mbar_init(smem_u32(&ms.bar_d2_full[i]), 1); mbar_init(smem_u32(&ms.bar_d2_empty[i]), 128);
+      mbar_init(smem_u32(&ms.bar_d2_full[i]), 1); mbar_init(smem_u32(&ms.bar_d2_empty[i]), (C >= 64) ? 256 : 128);
     }
     for (int i = 0; i < Cfg::NTAP; ++i) { mbar_init(smem_u32(&ms.bar_tap_full[i]), 1); mbar_init(smem_u32(&ms.bar_tap_empty[i]), kLFConv); }
     fence_mbar_init();
@@ -197,8 +196,10 @@ __global__ void __launch_bounds__(kLFThreads, 1) leff_fused_kernel(const __grid_
 
   auto tile_of = [&](int it) { return (int)blockIdx.x + it * (int)gridDim.x; };
 
+  // Register re-balancing (setmaxnreg moves registers inside the CTA's launch allocation of 640 x 96): control warpgroup
+  // 96 -> 64, the two epilogue warpgroups 96 -> 88, the two conv warpgroups 96 -> 120:  128*(32 + 8 + 8) = 2*128*24.
   if (wg == 3) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     if (warp == 12) {
       // ============================== producer: input tiles (TMA boxes) + weight ring ==============================
       if (lane == 0) {
@@ -300,33 +301,55 @@ __global__ void __launch_bounds__(kLFThreads, 1) leff_fused_kernel(const __grid_
         mbar_wait(smem_u32(&ms.bar_x_full[ab]), (it / Cfg::NA1) & 1);
         const uint32_t xs = smem_u32(smem + Cfg::S_A1 + ab * Cfg::A1_BYTES);
         float2* st = reinterpret_cast<float2*>(smem + Cfg::S_STATS) + sb * 192;
-        for (int r0 = sw * 96; r0 < sw * 96 + 96; r0 += RPP) {
-          const int r = r0 + rin;
-          float v[Cfg::KB1][8];
+        // One pass over the data: sums of d = x - x0 and d^2 with x0 = the row's first element (shifting by a value of the
+        // row keeps E[d^2] - E[d]^2 free of cancellation), four independent partial sums per lane, UN row groups interleaved
+        // (the chain lds -> unpack -> adds -> shuffles is latency-bound for a single warp).
+        constexpr int UN = (RPP <= 4) ? 4 : 2;
+        static_assert(96 % (RPP * UN) == 0, "stats unroll");
+#pragma unroll 1
+        for (int r0 = sw * 96; r0 < sw * 96 + 96; r0 += RPP * UN) {
+          float s1[UN], s2[UN], x0[UN];
 #pragma unroll
-          for (int kb = 0; kb < Cfg::KB1; ++kb) unpack8(lds128(xs + kb * Cfg::A1_KB_BYTES + swz<Cfg::SW>(r, sub * 16)), v[kb]);
-          float s = 0.f;
+          for (int u = 0; u < UN; ++u) {
+            const int r = r0 + u * RPP + rin;
+            float v[Cfg::KB1][8];
 #pragma unroll
-          for (int kb = 0; kb < Cfg::KB1; ++kb)
+            for (int kb = 0; kb < Cfg::KB1; ++kb) unpack8(lds128(xs + kb * Cfg::A1_KB_BYTES + swz<Cfg::SW>(r, sub * 16)), v[kb]);
+            x0[u] = __shfl_sync(0xffffffffu, v[0][0], lane - sub);          // first element of the row (lane with sub == 0)
+            float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) s += v[kb][i];
+            for (int kb = 0; kb < Cfg::KB1; ++kb)
 #pragma unroll
-          for (int o = 1; o < LPR; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-          const float mean = s * (1.0f / C);
-          float q = 0.f;
+              for (int i = 0; i < 8; i += 2) {
+                const float d0 = v[kb][i] - x0[u], d1 = v[kb][i + 1] - x0[u];
+                a0 += d0; a1 += d1;
+                b0 = fmaf(d0, d0, b0); b1 = fmaf(d1, d1, b1);
+              }
+            s1[u] = a0 + a1; s2[u] = b0 + b1;
+          }
 #pragma unroll
-          for (int kb = 0; kb < Cfg::KB1; ++kb)
+          for (int o = 1; o < LPR; o <<= 1)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { const float d = v[kb][i] - mean; q += d * d; }
-#pragma unroll
-          for (int o = 1; o < LPR; o <<= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+            for (int u = 0; u < UN; ++u) {
+              s1[u] += __shfl_xor_sync(0xffffffffu, s1[u], o);
+              s2[u] += __shfl_xor_sync(0xffffffffu, s2[u], o);
+            }
           if (sub == 0) {
-            const int hy = r / 18, hx = r - hy * 18;
-            const int y = ty * 8 - 1 + hy, x = tx * 16 - 1 + hx;
-            const bool valid = (r < 180) && (y >= 0) && (y < a.H) && (x >= 0) && (x < a.W);
-            float rstd = 1.0f, nm = 0.0f;
-            if (a.has_ln) { rstd = rsqrtf(q * (1.0f / C) + a.ln_eps); nm = -mean * rstd; }
-            st[r] = valid ? make_float2(rstd, nm) : make_float2(-1.0f, 0.0f);
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+              const int r = r0 + u * RPP + rin;
+              const int hy = r / 18, hx = r - hy * 18;
+              const int y = ty * 8 - 1 + hy, x = tx * 16 - 1 + hx;
+              const bool valid = (r < 180) && (y >= 0) && (y < a.H) && (x >= 0) && (x < a.W);
+              float rstd = 1.0f, nm = 0.0f;
+              if (a.has_ln) {
+                const float md = s1[u] * (1.0f / C);                        // mean - x0
+                const float var = fmaxf(s2[u] * (1.0f / C) - md * md, 0.f);
+                rstd = rsqrtf(var + a.ln_eps);
+                nm = -(x0[u] + md) * rstd;
+              }
+              st[r] = valid ? make_float2(rstd, nm) : make_float2(-1.0f, 0.0f);
+            }
           }
         }
         __syncwarp();
@@ -336,76 +359,111 @@ __global__ void __launch_bounds__(kLFThreads, 1) leff_fused_kernel(const __grid_
         }
       }
     }
-  } else if (wg == 2) {
+  } else if (wg == 2 || wg == 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
-    // ============================== E1 / E2 warps 8-11 (TMEM lane quadrant q) ==============================
-    const int q = warp & 3, et = tid - 256;
+    // ============================== E1 / E2: two epilogue groups (warps 8-11 and 16-19), TMEM lane quadrant q ==============================
+    // E1: each group takes half of the 32-column pieces of a hidden slice.  E2: each group drains half of the output columns
+    // through its own staging tile (C >= 64; narrower outputs are drained by group 0 alone).
+    const int grp = (wg == 4) ? 1 : 0;
+    const int q = warp & 3, et = tid & 127;
     const int t4 = lane >> 2, tq = lane & 3;
     const int m = lane >> 3, rr = lane & 7;
-    const uint32_t halo0 = smem_u32(smem + Cfg::S_HALO), stage_s = smem_u32(smem + Cfg::S_STAGE);
+    const uint32_t halo0 = smem_u32(smem + Cfg::S_HALO), stage_s = smem_u32(smem + Cfg::S_STAGE) + grp * (128 * Cfg::STAGE_PITCH);
     const uint32_t b1_s = smem_u32(smem + Cfg::S_B1), b2_s = smem_u32(smem + Cfg::S_B2), stats_s = smem_u32(smem + Cfg::S_STATS);
+    auto grp_bar = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory"); };
+    constexpr bool SPLIT_E2 = (C >= 64);
+    constexpr int E2_COLS = SPLIT_E2 ? C / 2 : C;             // output columns this group drains
+    constexpr int E2_PASS = (E2_COLS >= 32) ? 32 : 16;        // columns per staging pass
+    constexpr int VPR = E2_PASS / 8;                          // 16-byte vectors per staged row
+    constexpr int VPT = VPR;                                  // vectors per thread per pass (128 rows x VPR vectors / 128 threads)
+    int* row_out = ms.row_out + grp * 128;
 
     auto epilogue2 = [&](int it) {
+      if (!SPLIT_E2 && grp == 1) return;
       const int ob = it % Cfg::ND2;
       const int tile = tile_of(it);
       {
         const int tx = tile % a.tiles_x, ty = (tile / a.tiles_x) % a.tiles_y, b = tile / (a.tiles_x * a.tiles_y);
         const int y = ty * 8 + (et >> 4), x = tx * 16 + (et & 15);
-        ms.row_out[et] = (x < a.W) ? ((b * a.H + y) * a.W + x) : -1;
+        row_out[et] = (x < a.W) ? ((b * a.H + y) * a.W + x) : -1;
       }
+      grp_bar();
+      // this thread copies out vectors i = et + p*128 of every pass: row i / VPR, vector i % VPR (fixed over the passes)
+      int tok[VPT];
+#pragma unroll
+      for (int p2 = 0; p2 < VPT; ++p2) tok[p2] = row_out[(et + p2 * 128) / VPR];
       mbar_wait(smem_u32(&ms.bar_d2_full[ob]), (it / Cfg::ND2) & 1);
       tc_fence_after();
-      for (int sc = 0; sc < C; sc += 32) {
-        constexpr int NB = (C >= 32) ? 4 : 2;              // C = 16: one 16-column pass
+      const int cbase = grp * (SPLIT_E2 ? C / 2 : 0);
+#pragma unroll 1
+      for (int sc = 0; sc < E2_COLS; sc += E2_PASS) {
+        // residual vectors of this pass: issued first so that their (L2) latency hides under the TMEM read + staging below
+        uint4 rv[VPT][2];
+        if (a.resid != nullptr) {
+#pragma unroll
+          for (int p2 = 0; p2 < VPT; ++p2) {
+            const int c = cbase + sc + ((et + p2 * 128) % VPR) * 8;
+            const size_t off = (size_t)(tok[p2] < 0 ? 0 : tok[p2]) * a.resid_stride + c;
+            if (a.resid_fp32) {
+              rv[p2][0] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(a.resid) + off));
+              rv[p2][1] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(a.resid) + off + 4));
+            } else {
+              rv[p2][0] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(a.resid) + off));
+            }
+          }
+        }
+        constexpr int NB = E2_PASS / 8;
 #pragma unroll
         for (int hl = 0; hl < 2; ++hl) {
           const int row16 = q * 32 + hl * 16;
           uint32_t v[4 * NB];
-          const uint32_t ta = tb + ((uint32_t)row16 << 16) + Cfg::T_D2 + ob * C + sc;
+          const uint32_t ta = tb + ((uint32_t)row16 << 16) + Cfg::T_D2 + ob * C + cbase + sc;
           if (NB == 4) tmem_ld_16x256b_x4(ta, v); else tmem_ld_16x256b_x2(ta, v);
           f2 bb[NB];
 #pragma unroll
-          for (int i = 0; i < NB; ++i) { const float2 b2 = lds64f(b2_s + (sc + 8 * i + 2 * tq) * 4); bb[i] = f2_pack(b2.x, b2.y); }
+          for (int i = 0; i < NB; ++i) { const float2 b2 = lds64f(b2_s + (cbase + sc + 8 * i + 2 * tq) * 4); bb[i] = f2_pack(b2.x, b2.y); }
           tmem_wait_ld();
           uint32_t pk[2 * NB];
           frag_bias_act_pack<NB, false>(v, bb, pk);
           stage_frag<NB>(stage_s, Cfg::STAGE_PITCH, row16, 0, pk);
         }
-        if (sc + 32 >= C) { tc_fence_before(); mbar_arrive(smem_u32(&ms.bar_d2_empty[ob])); }
-        lf_e_bar();
-        if (C >= 32) lf_store_rows(stage_s, ms.row_out, a, sc, et);
-        else {                                              // C = 16: two 8-column vectors per row
-          for (int i = et; i < 256; i += 128) {
-            const int row = i >> 1, vec = i & 1, tok = ms.row_out[row];
-            if (tok < 0) continue;
-            float f[8];
-            unpack8(lds128(stage_s + row * 80 + vec * 16), f);
-            const int c = vec * 8;
-            if (a.resid != nullptr) {
-              if (a.resid_fp32) {
-                const float* rp = reinterpret_cast<const float*>(a.resid) + (size_t)tok * a.resid_stride + c;
+        if (sc + E2_PASS >= E2_COLS) { tc_fence_before(); mbar_arrive(smem_u32(&ms.bar_d2_empty[ob])); }
+        grp_bar();
 #pragma unroll
-                for (int k2 = 0; k2 < 8; ++k2) f[k2] += __ldg(rp + k2);
-              } else {
-                float r[8];
-                unpack8(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(a.resid) + (size_t)tok * a.resid_stride + c)), r);
-#pragma unroll
-                for (int k2 = 0; k2 < 8; ++k2) f[k2] += r[k2];
-              }
-            }
-            if (a.out_fp32) {
-              float* op = reinterpret_cast<float*>(a.out) + (size_t)tok * a.out_stride + c;
-#pragma unroll
-              for (int k2 = 0; k2 < 8; ++k2) op[k2] = f[k2];
+        for (int p2 = 0; p2 < VPT; ++p2) {
+          if (tok[p2] < 0) continue;
+          const int i = et + p2 * 128;
+          const int row = i / VPR, vec = i % VPR;
+          float f[8];
+          unpack8(lds128(stage_s + row * Cfg::STAGE_PITCH + vec * 16), f);
+          const int c = cbase + sc + vec * 8;
+          if (a.resid != nullptr) {
+            if (a.resid_fp32) {
+              const float4 r0 = *reinterpret_cast<const float4*>(&rv[p2][0]), r1 = *reinterpret_cast<const float4*>(&rv[p2][1]);
+              f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w; f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
             } else {
-              *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(a.out) + (size_t)tok * a.out_stride + c) = pack8(f);
+              float r[8];
+              unpack8(rv[p2][0], r);
+#pragma unroll
+              for (int k2 = 0; k2 < 8; ++k2) f[k2] += r[k2];
             }
           }
+          if (a.out_fp32) {
+            float* op = reinterpret_cast<float*>(a.out) + (size_t)tok[p2] * a.out_stride + c;
+            *reinterpret_cast<float4*>(op) = make_float4(f[0], f[1], f[2], f[3]);
+            *reinterpret_cast<float4*>(op + 4) = make_float4(f[4], f[5], f[6], f[7]);
+          } else {
+            *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(a.out) + (size_t)tok[p2] * a.out_stride + c) = pack8(f);
+          }
         }
-        lf_e_bar();
+        grp_bar();
       }
     };
 
+    // E1 pieces of 32 hidden columns (16 TMEM lanes each).  Fragment f < 2: rows 32q + 16f of the M=128 part; f == 2: rows
+    // 128 + 16q of the M=64 part (its 64 rows sit 16 per lane quadrant).  SL = 64: 6 pieces, 3 per group.  SL = 32: 3 pieces:
+    // group g takes fragment g whole and one 16-column half of fragment 2.
+    constexpr int HP = SL / 32;
     for (int k = 0; k < total; ++k) {
       const int j = k % NS, it = k / NS, db = k & 1, sb = it & 1;
       if (j == 0) mbar_wait(smem_u32(&ms.bar_st_full[sb]), (it >> 1) & 1);
@@ -414,43 +472,60 @@ __global__ void __launch_bounds__(kLFThreads, 1) leff_fused_kernel(const __grid_
       tc_fence_after();
       const uint32_t hb = halo0 + db * Cfg::HALO_BYTES;
       const uint32_t bsl = b1_s + j * SL * 4, csl = b1_s + (a.hidden + j * SL) * 4;
-#pragma unroll 1
-      for (int f = 0; f < 3; ++f) {
-        // fragment f of this quadrant: 16 TMEM lanes x SL columns.  f < 2: rows 32q + 16f of the M=128 part;
-        // f == 2: rows 128 + 16q of the M=64 part (its 64 rows sit 16 per lane quadrant)
-        const uint32_t lanes = (uint32_t)(q * 32 + (f == 1 ? 16 : 0)) << 16;
-        const uint32_t tcol = tb + lanes + Cfg::T_D1 + db * 2 * SL + (f == 2 ? SL : 0);
-        const int row0 = (f < 2) ? q * 32 + f * 16 : 128 + q * 16;
+      auto frag_lanes = [&](int f) { return (uint32_t)(q * 32 + (f == 1 ? 16 : 0)) << 16; };
+      auto frag_row0 = [&](int f) { return (f < 2) ? q * 32 + f * 16 : 128 + q * 16; };
+      // one piece: NBP column blocks of 8 starting at column c0 of fragment f (values already in v)
+      auto do_piece = [&](const uint32_t* v, int f, int c0, auto nbp_tag) {
+        constexpr int NBP = decltype(nbp_tag)::value;
+        const int row0 = frag_row0(f);
         const float2 sa = lds64f(stats_s + (sb * 192 + row0 + t4) * 8), sbb = lds64f(stats_s + (sb * 192 + row0 + t4 + 8) * 8);
-        const bool va = sa.x > 0.f, vb = sbb.x > 0.f;
+        // out-of-image / padding rows are zeroed with a bit mask: a select would be compiled into a branch around each GELU
+        // chain and serialise the independent chains of a piece
+        const uint32_t ma = sa.x > 0.f ? 0xffffffffu : 0u, mb = sbb.x > 0.f ? 0xffffffffu : 0u;
         const f2 ra = f2_pack(sa.x, sa.x), na = f2_pack(sa.y, sa.y), rb = f2_pack(sbb.x, sbb.x), nb = f2_pack(sbb.y, sbb.y);
+        uint32_t pk[2 * NBP];
 #pragma unroll
-        for (int half = 0; half < SL / 32; ++half) {
-          uint32_t v[16];
-          tmem_ld_16x256b_x4(tcol + half * 32, v);
-          f2 bb[4], cc[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int n = half * 32 + 8 * i + 2 * tq;
-            const float2 b2 = lds64f(bsl + n * 4), c2 = lds64f(csl + n * 4);
-            bb[i] = f2_pack(b2.x, b2.y); cc[i] = f2_pack(c2.x, c2.y);
-          }
-          tmem_wait_ld();
-          uint32_t pk[8];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const f2 d0 = f2_pack(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]));
-            const f2 d1 = f2_pack(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
-            const f2 x0 = f2_fma(d0, ra, f2_fma(na, cc[i], bb[i]));
-            const f2 x1 = f2_fma(d1, rb, f2_fma(nb, cc[i], bb[i]));
-            pk[2 * i] = va ? f2_to_bf2(gelu2(x0)) : 0u;
-            pk[2 * i + 1] = vb ? f2_to_bf2(gelu2(x1)) : 0u;
-          }
-          const int row = row0 + (m & 1) * 8 + rr;
+        for (int i = 0; i < NBP; ++i) {
+          const int n = c0 + 8 * i + 2 * tq;
+          const float2 b2 = lds64f(bsl + n * 4), c2 = lds64f(csl + n * 4);
+          const f2 bbv = f2_pack(b2.x, b2.y), ccv = f2_pack(c2.x, c2.y);
+          const f2 d0 = f2_pack(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]));
+          const f2 d1 = f2_pack(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+          const f2 x0 = f2_fma(d0, ra, f2_fma(na, ccv, bbv));
+          const f2 x1 = f2_fma(d1, rb, f2_fma(nb, ccv, bbv));
+          pk[2 * i] = f2_to_bf2(gelu2(x0)) & ma;
+          pk[2 * i + 1] = f2_to_bf2(gelu2(x1)) & mb;
+        }
+        const int row = row0 + (m & 1) * 8 + rr;
+        if (NBP == 4) {
 #pragma unroll
           for (int i2 = 0; i2 < 2; ++i2)
-            stsm_x4(hb + swz<Cfg::SWH>(row, (half * 4 + 2 * i2 + (m >> 1)) * 16), pk[4 * i2], pk[4 * i2 + 1], pk[4 * i2 + 2], pk[4 * i2 + 3]);
+            stsm_x4(hb + swz<Cfg::SWH>(row, (c0 / 8 + 2 * i2 + (m >> 1)) * 16), pk[4 * i2], pk[4 * i2 + 1], pk[4 * i2 + 2], pk[4 * i2 + 3]);
+        } else {
+          stsm_x4(hb + swz<Cfg::SWH>(row, (c0 / 8 + (m >> 1)) * 16), pk[0], pk[1], pk[2], pk[3]);
         }
+      };
+      const uint32_t tcol = tb + Cfg::T_D1 + db * 2 * SL;
+      if (SL == 64) {
+        // pieces p = 3*grp .. 3*grp+2 of (f = p / 2, half = p % 2), software-pipelined TMEM loads
+        uint32_t v[2][16];
+        const int p0 = 3 * grp;
+        auto paddr = [&](int p) { const int f = p / HP; return tcol + frag_lanes(f) + (f == 2 ? SL : 0) + (p % HP) * 32; };
+        tmem_ld_16x256b_x4(paddr(p0), v[0]);
+#pragma unroll
+        for (int pi = 0; pi < 3; ++pi) {
+          tmem_wait_ld();
+          if (pi + 1 < 3) tmem_ld_16x256b_x4(paddr(p0 + pi + 1), v[(pi + 1) & 1]);
+          const int p = p0 + pi;
+          do_piece(v[pi & 1], p / HP, (p % HP) * 32, std::integral_constant<int, 4>());
+        }
+      } else {
+        uint32_t v0[16], v1[8];
+        tmem_ld_16x256b_x4(tcol + frag_lanes(grp), v0);                                   // fragment grp, 32 columns
+        tmem_ld_16x256b_x2(tcol + frag_lanes(2) + SL + grp * 16, v1);                     // fragment 2, columns 16*grp .. +16
+        tmem_wait_ld();
+        do_piece(v0, grp, 0, std::integral_constant<int, 4>());
+        do_piece(v1, 2, grp * 16, std::integral_constant<int, 2>());
       }
       tc_fence_before();
       mbar_arrive(smem_u32(&ms.bar_d1_empty[db]));
@@ -464,7 +539,7 @@ __global__ void __launch_bounds__(kLFThreads, 1) leff_fused_kernel(const __grid_
     }
     if (my_tiles > 0) epilogue2(my_tiles - 1);
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
     // ============================== conv warps 0-7 ==============================
     // SL = 64: warp = channel octet, lanes = 16 columns x 2 row halves, 4 output rows per lane (6 halo rows).
     // SL = 32: warp = (octet, row half), lanes = 16 columns x 2 row pairs, 2 output rows per lane (4 halo rows).

@@ -85,14 +85,17 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void fence_mbar_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+// suspend-time hint (ns): a waiting thread may sleep in hardware up to this long per try_wait (it is woken when the phase
+// completes), instead of burning issue slots of the SM sub-partition it shares with the compute warps
+constexpr uint32_t kMbarSuspendHintNs = 20000;
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(kMbarSuspendHintNs)
       : "memory");
   return ok;
 }
@@ -101,7 +104,7 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 24)) { __trap(); }
+    if (++spins > (1u << 18)) { __trap(); }
   }
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
