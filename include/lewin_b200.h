@@ -118,8 +118,8 @@ typedef struct lw_leff_args {
   const void* w1_img;      /* packed bf16 [hidden/SL][KB][SL rows x SW bytes], SW = 2*min(C,64), swizzle SW */
   const float* b1f;        /* (hidden) */
   const float* cs;         /* (hidden) */
-  const float* taps;       /* [hidden/SL][10][SL] fp32 per hidden slice: 9 depthwise taps (tap = ky*3+kx), then the conv bias */
-  const void* w2_img;      /* packed bf16 [hidden/SL][C rows x 2*SL bytes] (K-major, swizzle 2*SL) */
+  const void* taps;        /* [hidden/SL][10][SL] fp16 per hidden slice: 9 depthwise taps (tap = ky*3+kx), then the conv bias */
+  const void* w2_img;      /* packed FP16 [hidden/SL][C rows x 2*SL bytes] (K-major, swizzle 2*SL): the hidden map is fp16 on chip */
   const float* b2;         /* (C) */
   int32_t B, H, W, C, hidden;
   int32_t x_stride, resid_stride, out_stride;   /* elements */

@@ -111,9 +111,11 @@ def leff(x, p, *, B, H, W, resid, out=None, out_dtype=None):
             pre = rstd * acc - (rstd * mean) * p["cs"] + p["b1f"]
         else:
             pre = acc + p["b1f"]
-        h1 = _q(F.gelu(pre))                                       # bf16 in shared memory
+        q16 = lambda t: t.to(torch.float16).float()                # the hidden map is fp16 on chip (E1 -> conv -> GEMM-2)
+        h1 = q16(F.gelu(q16(pre)))
+        assert p["w2f_img"].dtype == torch.float16 and p["taps"].dtype == torch.float16
         w2 = packing.unpack_kmajor_sw(p["w2f_img"], C, hid, C, 2 * sl)
-        t = p["taps"].permute(1, 0, 2).reshape(10, hid)               # [NS][10][sl] -> (10, hidden)
+        t = p["taps"].float().permute(1, 0, 2).reshape(10, hid)       # [NS][10][sl] -> (10, hidden)
         wd_t, bd_t = t[:9], t[9]
     else:
         if p.get("ln_w") is not None:
@@ -126,7 +128,8 @@ def leff(x, p, *, B, H, W, resid, out=None, out_dtype=None):
         wd_t, bd_t = p["wd"], p["bd"]
     m = h1.view(B, H, W, hid).permute(0, 3, 1, 2)
     wd = wd_t.t().reshape(hid, 1, 3, 3)                           # taps (9, hidden), tap = ky*3+kx
-    h2 = _q(F.gelu(F.conv2d(m, wd, bd_t, padding=1, groups=hid))).permute(0, 2, 3, 1).reshape(B * H * W, hid)
+    qh = (lambda t: t.to(torch.float16).float()) if "w1f_img" in p else _q
+    h2 = qh(F.gelu(qh(F.conv2d(m, wd, bd_t, padding=1, groups=hid)))).permute(0, 2, 3, 1).reshape(B * H * W, hid)
     y = _q(h2 @ w2.t() + p["b2"]).view(x.shape)                  # the branch is rounded to bf16 before the residual add
     if resid is not None:
         y = y + resid.float()

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "liblewin_b200.so")
+LIB_PATH = os.environ.get("UFORMER_B200_LIB") or os.path.join(_HERE, "lib", "liblewin_b200.so")    # (override: trace builds, tools/)
 
 LW_ERRORS = {-1: "LW_ERR_BAD_SHAPE", -2: "LW_ERR_NULL", -3: "LW_ERR_CUDA", -4: "LW_ERR_ARCH", -5: "LW_ERR_ALIGN"}
 

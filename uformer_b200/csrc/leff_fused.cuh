@@ -27,16 +27,21 @@
 
 namespace lw {
 
+// per-role timeline slots of CTA 0 (only compiled with -DLW_TRACE): role r owns trace[r*512 ..]
+#define LF_TRACE(role, idx) LW_TRACE_STMT(if (a.trace != nullptr && blockIdx.x == 0 && (idx) < 512) a.trace[(role) * 512 + (idx)] = clock64();)
+
 constexpr int kLFThreads = 640;       // 8 conv warps | 4 E1/E2 warps | producer, issuer, 2 stats warps | 4 E1/E2 warps
 constexpr int kLFConv = 256;
 
 struct LeffFArgs {
+  const bf16* x;           // the tensor-map source again: the LayerNorm statistics are read with plain loads
+  int x_stride;
   int B, H, W, hidden;
   const uint8_t* w1_img;   // [hidden/SL][KB1][SL rows x SW bytes] bf16, gamma folded, swizzle SW = 2*min(C,64)
   const float* b1f;        // (hidden)  b1 + W1 beta
   const float* cs;         // (hidden)  row sums of the bf16-rounded W1' (mean correction of the folded LayerNorm)
-  const float* taps;       // [hidden/SL][10][SL] fp32: 9 depthwise taps (tap = ky*3+kx) + conv bias per slice
-  const uint8_t* w2_img;   // [hidden/SL][C rows x 2*SL bytes] bf16, swizzle 2*SL
+  const uint8_t* taps;     // [hidden/SL][10][SL] f16: 9 depthwise taps (tap = ky*3+kx) + conv bias per slice
+  const uint8_t* w2_img;   // [hidden/SL][C rows x 2*SL bytes] f16, swizzle 2*SL
   const float* b2;         // (C)
   const void* resid;       // (B*H*W rows, stride resid_stride) bf16 or fp32, or null
   void* out;               // (B*H*W rows, stride out_stride) bf16 or fp32
@@ -44,6 +49,7 @@ struct LeffFArgs {
   int has_ln;
   float ln_eps;
   int tiles_x, tiles_y, n_tiles;
+  long long* trace;        // -DLW_TRACE builds: CTA 0 writes per-role clock64 timelines here (tools/leff_fused_trace.py)
 };
 
 template <int C>
@@ -65,7 +71,7 @@ struct LeffFCfg {
   static constexpr int HALO_BYTES = 192 * SWH;
   static constexpr int A2_BYTES = 128 * SWH;
   static constexpr int NTAP = 4;
-  static constexpr int TAP_BYTES = 10 * SL * 4;
+  static constexpr int TAP_BYTES = 10 * SL * 2;             // [10][SL] f16
   static constexpr int STAGE_PITCH = 80;                    // E2 staging: 32 bf16 columns + 16 B pad
   static constexpr int S_A1 = 0;
   static constexpr int S_HALO = (NA1 * A1_BYTES + 1023) / 1024 * 1024;
@@ -162,8 +168,8 @@ __global__ void __launch_bounds__(kLFThreads, 1) leff_fused_kernel(const __grid_
   if (tid == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(smem_u32(&ms.bar_full[s]), 1); mbar_init(smem_u32(&ms.bar_empty[s]), 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(smem_u32(&ms.bar_x_full[i]), 1);  mbar_init(smem_u32(&ms.bar_x_empty[i]), 3);      // GEMM-1 commit + 2 stats warps
-      mbar_init(smem_u32(&ms.bar_st_full[i]), 2); mbar_init(smem_u32(&ms.bar_st_empty[i]), 8);     // one lane per warp
+      mbar_init(smem_u32(&ms.bar_x_full[i]), 1);  mbar_init(smem_u32(&ms.bar_x_empty[i]), 9);      // GEMM-1 commit + 8 epilogue warps (stats)
+      mbar_init(smem_u32(&ms.bar_st_full[i]), 8); mbar_init(smem_u32(&ms.bar_st_empty[i]), 8);     // one lane per epilogue warp
       mbar_init(smem_u32(&ms.bar_d1_full[i]), 1); mbar_init(smem_u32(&ms.bar_d1_empty[i]), 256);
       mbar_init(smem_u32(&ms.bar_h_full[i]), 256); mbar_init(smem_u32(&ms.bar_h_empty[i]), kLFConv);
       mbar_init(smem_u32(&ms.bar_a2_full[i]), kLFConv); mbar_init(smem_u32(&ms.bar_a2_empty[i]), 1);
@@ -211,6 +217,7 @@ __global__ void __launch_bounds__(kLFThreads, 1) leff_fused_kernel(const __grid_
           const int tx = tile % a.tiles_x, ty = (tile / a.tiles_x) % a.tiles_y, b = tile / (a.tiles_x * a.tiles_y);
           const uint32_t bar = smem_u32(&ms.bar_x_full[ab]);
           mbar_expect_tx(bar, Cfg::KB1 * Cfg::X_BOX_BYTES);
+          LF_TRACE(5, it)
 #pragma unroll
           for (int kb = 0; kb < Cfg::KB1; ++kb)
             tma_load_4d(smem_u32(smem + Cfg::S_A1 + ab * Cfg::A1_BYTES + kb * Cfg::A1_KB_BYTES), &xmap, kb * 64, tx * 16 - 1, ty * 8 - 1, b, bar);
@@ -227,7 +234,7 @@ __global__ void __launch_bounds__(kLFThreads, 1) leff_fused_kernel(const __grid_
               const int tbuf = k % Cfg::NTAP;
               mbar_wait(smem_u32(&ms.bar_tap_empty[tbuf]), ((k / Cfg::NTAP) & 1) ^ 1);
               mbar_expect_tx(smem_u32(&ms.bar_tap_full[tbuf]), Cfg::TAP_BYTES);
-              bulk_g2s(smem_u32(smem + Cfg::S_TAPS + tbuf * Cfg::TAP_BYTES), a.taps + (size_t)j * 10 * SL, Cfg::TAP_BYTES, smem_u32(&ms.bar_tap_full[tbuf]));
+              bulk_g2s(smem_u32(smem + Cfg::S_TAPS + tbuf * Cfg::TAP_BYTES), a.taps + (size_t)j * Cfg::TAP_BYTES, Cfg::TAP_BYTES, smem_u32(&ms.bar_tap_full[tbuf]));
             }
             ring.load(a.w1_img + (size_t)j * Cfg::W1_CHUNK, Cfg::W1_CHUNK);
           }
@@ -237,7 +244,7 @@ __global__ void __launch_bounds__(kLFThreads, 1) leff_fused_kernel(const __grid_
     } else if (warp == 13) {
       // ============================== issuer (warp-uniform; one elected lane issues) ==============================
       Ring ring{smem_u32(smem + Cfg::S_RING), smem_u32(&ms.bar_full[0]), smem_u32(&ms.bar_empty[0]), Cfg::STAGES, 0};
-      constexpr uint32_t idesc_g1a = make_idesc_bf16(128, SL), idesc_g1b = make_idesc_bf16(64, SL), idesc_g2 = make_idesc_bf16(128, C);
+      constexpr uint32_t idesc_g1a = make_idesc_bf16(128, SL), idesc_g1b = make_idesc_bf16(64, SL), idesc_g2 = make_idesc_f16(128, C);
       for (int k = 0; k < total + 2; ++k) {
         if (k < total) {
           // ---- GEMM-1 of slice k: D1[k&1] = X W1'_j^T ----
@@ -260,6 +267,7 @@ __global__ void __launch_bounds__(kLFThreads, 1) leff_fused_kernel(const __grid_
           }
           __syncwarp();
           ring.release();
+          if (lane == 0) { LF_TRACE(3, 2 * k) }
           if (elect_one()) {
             umma_commit(smem_u32(&ms.bar_d1_full[db]));
             if (j == NS - 1) umma_commit(smem_u32(&ms.bar_x_empty[ab]));
@@ -280,6 +288,7 @@ __global__ void __launch_bounds__(kLFThreads, 1) leff_fused_kernel(const __grid_
           }
           __syncwarp();
           ring.release();
+          if (lane == 0) { LF_TRACE(3, 2 * (k - 2) + 1) }
           if (elect_one()) {
             umma_commit(smem_u32(&ms.bar_a2_empty[ab2]));
             if (j == NS - 1) umma_commit(smem_u32(&ms.bar_d2_full[ob]));
@@ -287,78 +296,8 @@ __global__ void __launch_bounds__(kLFThreads, 1) leff_fused_kernel(const __grid_
           __syncwarp();
         }
       }
-    } else {
-      // ============================== stats warps 14, 15: LayerNorm statistics of the 180 halo rows ==============================
-      const int sw = warp - 14;                            // rows sw*96 .. sw*96+95
-      constexpr int LPR = Cfg::SW / 16;                    // lanes per row inside a k-block (16-byte vectors): 8 / 4 / 2
-      constexpr int RPP = 32 / LPR;                        // rows per pass
-      const int sub = lane % LPR, rin = lane / LPR;
-      for (int it = 0; it < my_tiles; ++it) {
-        const int ab = it % Cfg::NA1, sb = it & 1;
-        const int tile = tile_of(it);
-        const int tx = tile % a.tiles_x, ty = (tile / a.tiles_x) % a.tiles_y;
-        mbar_wait(smem_u32(&ms.bar_st_empty[sb]), ((it >> 1) & 1) ^ 1);
-        mbar_wait(smem_u32(&ms.bar_x_full[ab]), (it / Cfg::NA1) & 1);
-        const uint32_t xs = smem_u32(smem + Cfg::S_A1 + ab * Cfg::A1_BYTES);
-        float2* st = reinterpret_cast<float2*>(smem + Cfg::S_STATS) + sb * 192;
-        // One pass over the data: sums of d = x - x0 and d^2 with x0 = the row's first element (shifting by a value of the
-        // row keeps E[d^2] - E[d]^2 free of cancellation), four independent partial sums per lane, UN row groups interleaved
-        // (the chain lds -> unpack -> adds -> shuffles is latency-bound for a single warp).
-        constexpr int UN = (RPP <= 4) ? 4 : 2;
-        static_assert(96 % (RPP * UN) == 0, "stats unroll");
-#pragma unroll 1
-        for (int r0 = sw * 96; r0 < sw * 96 + 96; r0 += RPP * UN) {
-          float s1[UN], s2[UN], x0[UN];
-#pragma unroll
-          for (int u = 0; u < UN; ++u) {
-            const int r = r0 + u * RPP + rin;
-            float v[Cfg::KB1][8];
-#pragma unroll
-            for (int kb = 0; kb < Cfg::KB1; ++kb) unpack8(lds128(xs + kb * Cfg::A1_KB_BYTES + swz<Cfg::SW>(r, sub * 16)), v[kb]);
-            x0[u] = __shfl_sync(0xffffffffu, v[0][0], lane - sub);          // first element of the row (lane with sub == 0)
-            float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
-#pragma unroll
-            for (int kb = 0; kb < Cfg::KB1; ++kb)
-#pragma unroll
-              for (int i = 0; i < 8; i += 2) {
-                const float d0 = v[kb][i] - x0[u], d1 = v[kb][i + 1] - x0[u];
-                a0 += d0; a1 += d1;
-                b0 = fmaf(d0, d0, b0); b1 = fmaf(d1, d1, b1);
-              }
-            s1[u] = a0 + a1; s2[u] = b0 + b1;
-          }
-#pragma unroll
-          for (int o = 1; o < LPR; o <<= 1)
-#pragma unroll
-            for (int u = 0; u < UN; ++u) {
-              s1[u] += __shfl_xor_sync(0xffffffffu, s1[u], o);
-              s2[u] += __shfl_xor_sync(0xffffffffu, s2[u], o);
-            }
-          if (sub == 0) {
-#pragma unroll
-            for (int u = 0; u < UN; ++u) {
-              const int r = r0 + u * RPP + rin;
-              const int hy = r / 18, hx = r - hy * 18;
-              const int y = ty * 8 - 1 + hy, x = tx * 16 - 1 + hx;
-              const bool valid = (r < 180) && (y >= 0) && (y < a.H) && (x >= 0) && (x < a.W);
-              float rstd = 1.0f, nm = 0.0f;
-              if (a.has_ln) {
-                const float md = s1[u] * (1.0f / C);                        // mean - x0
-                const float var = fmaxf(s2[u] * (1.0f / C) - md * md, 0.f);
-                rstd = rsqrtf(var + a.ln_eps);
-                nm = -(x0[u] + md) * rstd;
-              }
-              st[r] = valid ? make_float2(rstd, nm) : make_float2(-1.0f, 0.0f);
-            }
-          }
-        }
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(smem_u32(&ms.bar_st_full[sb]));
-          mbar_arrive(smem_u32(&ms.bar_x_empty[ab]));
-        }
-      }
     }
+    // (warps 14, 15 are spares: the LayerNorm statistics are computed by the epilogue warps, see below)
   } else if (wg == 2 || wg == 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
     // ============================== E1 / E2: two epilogue groups (warps 8-11 and 16-19), TMEM lane quadrant q ==============================
@@ -377,11 +316,14 @@ __global__ void __launch_bounds__(kLFThreads, 1) leff_fused_kernel(const __grid_
     constexpr int VPR = E2_PASS / 8;                          // 16-byte vectors per staged row
     constexpr int VPT = VPR;                                  // vectors per thread per pass (128 rows x VPR vectors / 128 threads)
     int* row_out = ms.row_out + grp * 128;
+    GeluH2 gelu;
+    gelu.init();
 
     auto epilogue2 = [&](int it) {
       if (!SPLIT_E2 && grp == 1) return;
       const int ob = it % Cfg::ND2;
       const int tile = tile_of(it);
+      if (grp == 0 && et == 0) { LF_TRACE(6, 3 * it) }
       {
         const int tx = tile % a.tiles_x, ty = (tile / a.tiles_x) % a.tiles_y, b = tile / (a.tiles_x * a.tiles_y);
         const int y = ty * 8 + (et >> 4), x = tx * 16 + (et & 15);
@@ -394,6 +336,7 @@ __global__ void __launch_bounds__(kLFThreads, 1) leff_fused_kernel(const __grid_
       for (int p2 = 0; p2 < VPT; ++p2) tok[p2] = row_out[(et + p2 * 128) / VPR];
       mbar_wait(smem_u32(&ms.bar_d2_full[ob]), (it / Cfg::ND2) & 1);
       tc_fence_after();
+      if (grp == 0 && et == 0) { LF_TRACE(6, 3 * it + 1) }
       const int cbase = grp * (SPLIT_E2 ? C / 2 : 0);
 #pragma unroll 1
       for (int sc = 0; sc < E2_COLS; sc += E2_PASS) {
@@ -458,6 +401,7 @@ __global__ void __launch_bounds__(kLFThreads, 1) leff_fused_kernel(const __grid_
         }
         grp_bar();
       }
+      if (grp == 0 && et == 0) { LF_TRACE(6, 3 * it + 2) }
     };
 
     // E1 pieces of 32 hidden columns (16 TMEM lanes each).  Fragment f < 2: rows 32q + 16f of the M=128 part; f == 2: rows
@@ -466,10 +410,82 @@ __global__ void __launch_bounds__(kLFThreads, 1) leff_fused_kernel(const __grid_
     constexpr int HP = SL / 32;
     for (int k = 0; k < total; ++k) {
       const int j = k % NS, it = k / NS, db = k & 1, sb = it & 1;
-      if (j == 0) mbar_wait(smem_u32(&ms.bar_st_full[sb]), (it >> 1) & 1);
+      if (j == 0) {
+        // ---- LayerNorm statistics of the new tile's 192 rows, 24 rows per epilogue warp, straight from the landed A tile.
+        // One pass: sums of d = x - x0 and d^2 with x0 = the row's first element (shifting by a value of the row keeps
+        // E[d^2] - E[d]^2 free of cancellation).  Row validity (inside the image) is folded in: rstd = -1 marks a row whose
+        // hidden activations must be zero (the conv's zero padding of h1, model.py:659). ----
+        const int ab = it % Cfg::NA1;
+        mbar_wait(smem_u32(&ms.bar_x_full[ab]), (it / Cfg::NA1) & 1);
+        if (q == 0 && lane == 0) { LF_TRACE(4, 2 * it) }
+        constexpr int LPR = Cfg::SW / 16;                    // lanes per row inside a k-block (16-byte vectors): 8 / 4 / 2
+        constexpr int RPP = 32 / LPR;                        // rows per pass: 4 / 8 / 16
+        constexpr int NPASS = (24 + RPP - 1) / RPP;
+        const int sub = lane % LPR, rin = lane / LPR;
+        const int ew = grp * 4 + q;
+        const int tile = tile_of(it);
+        const int tx = tile % a.tiles_x, ty = (tile / a.tiles_x) % a.tiles_y;
+        const uint32_t xs = smem_u32(smem + Cfg::S_A1 + ab * Cfg::A1_BYTES);
+        float2* st = reinterpret_cast<float2*>(smem + Cfg::S_STATS) + sb * 192;
+        float s1[NPASS], s2[NPASS], x0[NPASS];
+#pragma unroll
+        for (int u = 0; u < NPASS; ++u) {
+          const int rl = u * RPP + rin;                      // row inside this warp's 24
+          const int r = ew * 24 + (rl < 24 ? rl : 23);
+          float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+#pragma unroll
+          for (int kb = 0; kb < Cfg::KB1; ++kb) {
+            float v[8];
+            unpack8(lds128(xs + kb * Cfg::A1_KB_BYTES + swz<Cfg::SW>(r, sub * 16)), v);
+            if (kb == 0) x0[u] = __shfl_sync(0xffffffffu, v[0], lane - sub);
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) {
+              const float d0 = v[i] - x0[u], d1 = v[i + 1] - x0[u];
+              a0 += d0; a1 += d1;
+              b0 = fmaf(d0, d0, b0); b1 = fmaf(d1, d1, b1);
+            }
+          }
+          s1[u] = a0 + a1; s2[u] = b0 + b1;
+        }
+#pragma unroll
+        for (int o = 1; o < LPR; o <<= 1)
+#pragma unroll
+          for (int u = 0; u < NPASS; ++u) {
+            s1[u] += __shfl_xor_sync(0xffffffffu, s1[u], o);
+            s2[u] += __shfl_xor_sync(0xffffffffu, s2[u], o);
+          }
+        if (sub == 0) {
+#pragma unroll
+          for (int u = 0; u < NPASS; ++u) {
+            const int rl = u * RPP + rin;
+            if (rl < 24) {
+              const int r = ew * 24 + rl;
+              const int hy = r / 18, hx = r - hy * 18;
+              const int y = ty * 8 - 1 + hy, x = tx * 16 - 1 + hx;
+              const bool valid = (r < 180) && (y >= 0) && (y < a.H) && (x >= 0) && (x < a.W);
+              float rstd = 1.0f, nm = 0.0f;
+              if (a.has_ln) {
+                const float md = s1[u] * (1.0f / C);                        // mean - x0
+                const float var = fmaxf(s2[u] * (1.0f / C) - md * md, 0.f);
+                rstd = rsqrtf(var + a.ln_eps);
+                nm = -(x0[u] + md) * rstd;
+              }
+              st[r] = valid ? make_float2(rstd, nm) : make_float2(-1.0f, 0.0f);
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(smem_u32(&ms.bar_x_empty[ab]));        // this warp is done reading the raw tile
+          mbar_arrive(smem_u32(&ms.bar_st_full[sb]));
+        }
+        mbar_wait(smem_u32(&ms.bar_st_full[sb]), (it >> 1) & 1);             // all eight warps' rows are in
+        if (q == 0 && lane == 0) { LF_TRACE(4, 2 * it + 1) }
+      }
       mbar_wait(smem_u32(&ms.bar_h_empty[db]), ((k >> 1) & 1) ^ 1);          // conv finished reading this halo buffer (slice k-2)
       mbar_wait(smem_u32(&ms.bar_d1_full[db]), (k >> 1) & 1);
       tc_fence_after();
+      if (q == 0 && lane == 0) { LF_TRACE(grp, 2 * k) }
       const uint32_t hb = halo0 + db * Cfg::HALO_BYTES;
       const uint32_t bsl = b1_s + j * SL * 4, csl = b1_s + (a.hidden + j * SL) * 4;
       auto frag_lanes = [&](int f) { return (uint32_t)(q * 32 + (f == 1 ? 16 : 0)) << 16; };
@@ -483,7 +499,7 @@ __global__ void __launch_bounds__(kLFThreads, 1) leff_fused_kernel(const __grid_
         // chain and serialise the independent chains of a piece
         const uint32_t ma = sa.x > 0.f ? 0xffffffffu : 0u, mb = sbb.x > 0.f ? 0xffffffffu : 0u;
         const f2 ra = f2_pack(sa.x, sa.x), na = f2_pack(sa.y, sa.y), rb = f2_pack(sbb.x, sbb.x), nb = f2_pack(sbb.y, sbb.y);
-        uint32_t pk[2 * NBP];
+        uint32_t pk[2 * NBP];                      // f16x2: the hidden map lives in half precision on chip
 #pragma unroll
         for (int i = 0; i < NBP; ++i) {
           const int n = c0 + 8 * i + 2 * tq;
@@ -493,8 +509,8 @@ __global__ void __launch_bounds__(kLFThreads, 1) leff_fused_kernel(const __grid_
           const f2 d1 = f2_pack(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
           const f2 x0 = f2_fma(d0, ra, f2_fma(na, ccv, bbv));
           const f2 x1 = f2_fma(d1, rb, f2_fma(nb, ccv, bbv));
-          pk[2 * i] = f2_to_bf2(gelu2(x0)) & ma;
-          pk[2 * i + 1] = f2_to_bf2(gelu2(x1)) & mb;
+          pk[2 * i] = gelu(h2_from_f2(x0)) & ma;
+          pk[2 * i + 1] = gelu(h2_from_f2(x1)) & mb;
         }
         const int row = row0 + (m & 1) * 8 + rr;
         if (NBP == 4) {
@@ -530,10 +546,7 @@ __global__ void __launch_bounds__(kLFThreads, 1) leff_fused_kernel(const __grid_
       tc_fence_before();
       mbar_arrive(smem_u32(&ms.bar_d1_empty[db]));
       mbar_arrive(smem_u32(&ms.bar_h_full[db]));
-      if (j == NS - 1) {
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&ms.bar_st_empty[sb]));
-      }
+      if (q == 0 && lane == 0) { LF_TRACE(grp, 2 * k + 1) }
       // the previous tile's output epilogue runs one or two slices into this tile (its GEMM-2 chain has drained by then)
       if (it > 0 && j == ((NS > 1 && Cfg::ND2 == 2) ? 1 : 0)) epilogue2(it - 1);
     }
@@ -549,62 +562,61 @@ __global__ void __launch_bounds__(kLFThreads, 1) leff_fused_kernel(const __grid_
     const int cx = lane & 15;
     const int rbase = (SL == 64) ? (lane >> 4) * 4 : (warp / NV) * 4 + (lane >> 4) * 2;     // first output row of this lane
     const uint32_t halo0 = smem_u32(smem + Cfg::S_HALO), taps0 = smem_u32(smem + Cfg::S_TAPS);
+    GeluH2 gelu;
+    gelu.init();
     for (int k = 0; k < total; ++k) {
       const int hbi = k & 1, tbuf = k % Cfg::NTAP;
       const uint32_t sH = halo0 + hbi * Cfg::HALO_BYTES;
-      const uint32_t sW = taps0 + tbuf * Cfg::TAP_BYTES + v * 32;       // tap t at + t * SL * 4
-      constexpr uint32_t tstride = SL * 4;
+      const uint32_t sW = taps0 + tbuf * Cfg::TAP_BYTES + v * 16;       // tap t at + t * SL * 2 (f16x2 per channel pair)
+      constexpr uint32_t tstride = SL * 2;
       mbar_wait(smem_u32(&ms.bar_tap_full[tbuf]), (k / Cfg::NTAP) & 1);
-      f2 acc[RPL][4];
+      h2 acc[RPL][4];                                // half2 accumulators: 2 channels per register
       {
-        const float4 b0 = lds128f(sW + 9 * tstride);
-        const float4 b1 = lds128f(sW + 9 * tstride + 16);
+        const uint4 b0 = lds128(sW + 9 * tstride);
 #pragma unroll
-        for (int o = 0; o < RPL; ++o) {
-          acc[o][0] = f2_pack(b0.x, b0.y); acc[o][1] = f2_pack(b0.z, b0.w);
-          acc[o][2] = f2_pack(b1.x, b1.y); acc[o][3] = f2_pack(b1.z, b1.w);
-        }
+        for (int o = 0; o < RPL; ++o) { acc[o][0] = b0.x; acc[o][1] = b0.y; acc[o][2] = b0.z; acc[o][3] = b0.w; }
       }
       mbar_wait(smem_u32(&ms.bar_h_full[hbi]), (k >> 1) & 1);
+      if (tid == 0) { LF_TRACE(2, 4 * k) }
 #pragma unroll
       for (int dx = 0; dx < 3; ++dx) {
-        f2 h[RPL + 2][4];
+        uint4 h[RPL + 2];
 #pragma unroll
         for (int r = 0; r < RPL + 2; ++r) {
           const int t = (rbase + r) * 18 + cx + dx;
-          const uint4 raw = lds128(sH + swz<Cfg::SWH>(t, v * 16));
-          h[r][0] = bf2_to_f2(raw.x); h[r][1] = bf2_to_f2(raw.y); h[r][2] = bf2_to_f2(raw.z); h[r][3] = bf2_to_f2(raw.w);
+          h[r] = lds128(sH + swz<Cfg::SWH>(t, v * 16));
         }
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
-          const float4 w0 = lds128f(sW + (ky * 3 + dx) * tstride);        // warp-uniform address: broadcast
-          const float4 w1 = lds128f(sW + (ky * 3 + dx) * tstride + 16);
-          const f2 wa = f2_pack(w0.x, w0.y), wb = f2_pack(w0.z, w0.w), wc = f2_pack(w1.x, w1.y), wdd = f2_pack(w1.z, w1.w);
+          const uint4 w = lds128(sW + (ky * 3 + dx) * tstride);            // warp-uniform address: broadcast
 #pragma unroll
           for (int o = 0; o < RPL; ++o) {
-            acc[o][0] = f2_fma(h[o + ky][0], wa, acc[o][0]);
-            acc[o][1] = f2_fma(h[o + ky][1], wb, acc[o][1]);
-            acc[o][2] = f2_fma(h[o + ky][2], wc, acc[o][2]);
-            acc[o][3] = f2_fma(h[o + ky][3], wdd, acc[o][3]);
+            acc[o][0] = h2_fma(h[o + ky].x, w.x, acc[o][0]);
+            acc[o][1] = h2_fma(h[o + ky].y, w.y, acc[o][1]);
+            acc[o][2] = h2_fma(h[o + ky].z, w.z, acc[o][2]);
+            acc[o][3] = h2_fma(h[o + ky].w, w.w, acc[o][3]);
           }
         }
       }
       mbar_arrive(smem_u32(&ms.bar_h_empty[hbi]));                 // halo buffer free for E1 of slice k+2
       mbar_arrive(smem_u32(&ms.bar_tap_empty[tbuf]));
+      if (tid == 0) { LF_TRACE(2, 4 * k + 1) }
       mbar_wait(smem_u32(&ms.bar_a2_empty[hbi]), ((k >> 1) & 1) ^ 1);   // GEMM-2 of slice k-2 has consumed this A buffer
+      if (tid == 0) { LF_TRACE(2, 4 * k + 2) }
       const uint32_t sA = smem_u32(smem + Cfg::S_A2 + hbi * Cfg::A2_BYTES);
 #pragma unroll
       for (int o = 0; o < RPL; ++o) {
         uint4 pk;
-        pk.x = f2_to_bf2(gelu2(acc[o][0]));
-        pk.y = f2_to_bf2(gelu2(acc[o][1]));
-        pk.z = f2_to_bf2(gelu2(acc[o][2]));
-        pk.w = f2_to_bf2(gelu2(acc[o][3]));
+        pk.x = gelu(acc[o][0]);
+        pk.y = gelu(acc[o][1]);
+        pk.z = gelu(acc[o][2]);
+        pk.w = gelu(acc[o][3]);
         const int rw = (rbase + o) * 16 + cx;
         sts128(sA + swz<Cfg::SWH>(rw, v * 16), pk);
       }
       fence_async_smem();
       mbar_arrive(smem_u32(&ms.bar_a2_full[hbi]));
+      if (tid == 0) { LF_TRACE(2, 4 * k + 3) }
     }
   }
   tc_fence_before();

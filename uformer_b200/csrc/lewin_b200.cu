@@ -262,12 +262,18 @@ extern "C" int lw_leff_fwd(const lw_leff_args* p, lw_stream_t stream) {
   const int rc = make_token_map(&map, p->x, p->B, p->H, p->W, p->C, p->x_stride, cb, 18, 10);
   if (rc != LW_OK) return rc;
   LeffFArgs a{};
+  a.x = reinterpret_cast<const bf16*>(p->x); a.x_stride = p->x_stride;
   a.B = p->B; a.H = p->H; a.W = p->W; a.hidden = p->hidden;
-  a.w1_img = reinterpret_cast<const uint8_t*>(p->w1_img); a.b1f = p->b1f; a.cs = p->cs; a.taps = p->taps;
+  a.w1_img = reinterpret_cast<const uint8_t*>(p->w1_img); a.b1f = p->b1f; a.cs = p->cs; a.taps = reinterpret_cast<const uint8_t*>(p->taps);
   a.w2_img = reinterpret_cast<const uint8_t*>(p->w2_img); a.b2 = p->b2;
   a.resid = p->resid; a.out = p->out; a.resid_stride = p->resid_stride; a.out_stride = p->out_stride;
   a.resid_fp32 = p->resid_fp32; a.out_fp32 = p->out_fp32; a.has_ln = p->has_ln; a.ln_eps = p->ln_eps;
   a.tiles_x = (p->W + 15) / 16; a.tiles_y = p->H / 8; a.n_tiles = a.tiles_x * a.tiles_y * p->B;
+  a.trace = nullptr;
+  if (debug_flags() & 16) {   // profiling aid (-DLW_TRACE builds): env LW_TRACE_PTR = device buffer of >= 7*512 int64
+    const char* e = getenv("LW_TRACE_PTR");
+    a.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr;
+  }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (p->C) {
     case 16: return launch_leff_fused<16>(map, a, st);

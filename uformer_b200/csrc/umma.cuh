@@ -76,6 +76,12 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn_m
          (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// the same with FP16 A/B operands (format code 0) and FP32 D
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, bool a_mn_major = false, bool b_mn_major = false) {
+  return (1u << 4) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
+         (static_cast<uint32_t>(M >> 4) << 24);
+}
+
 // ----------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------
@@ -85,10 +91,23 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void fence_mbar_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-// suspend-time hint (ns): a waiting thread may sleep in hardware up to this long per try_wait (it is woken when the phase
-// completes), instead of burning issue slots of the SM sub-partition it shares with the compute warps
-constexpr uint32_t kMbarSuspendHintNs = 20000;
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+// The same with a suspend-time hint (ns): a waiting thread may sleep in hardware up to that long per call (it is woken when
+// the phase completes) instead of burning issue slots of the SM sub-partition it shares with the compute warps.  Measured
+// (tools/leff_fused_trace.py): the hinted form costs several hundred cycles even when the phase has already completed, so it
+// is only used after a plain probe has failed.
+constexpr uint32_t kMbarSuspendHintNs = 20000;
+__device__ __forceinline__ uint32_t mbar_try_wait_sleep(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -99,11 +118,12 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return ok;
 }
-// Spin until the phase with the given parity completes.  Bounded so that a protocol bug traps
-// the kernel (sticky error on the host) instead of wedging the GPU.
+// Wait until the phase with the given parity completes.  Bounded so that a protocol bug traps the kernel (sticky error on
+// the host) instead of wedging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
   uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
+  while (!mbar_try_wait_sleep(bar, parity)) {
     if (++spins > (1u << 18)) { __trap(); }
   }
 }

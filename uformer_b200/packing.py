@@ -76,13 +76,14 @@ def _swizzle_perm(nch: int, sw: int, device) -> Tensor:
     return perm
 
 
-def pack_kmajor_sw(w: Tensor, nch: int, sw: int) -> Tensor:
-    """(N, K) -> bf16 images [N/nch][KB][nch * sw/2] with rows of `sw` bytes (sw/2 channels per k-block, K % (sw/2) == 0)."""
+def pack_kmajor_sw(w: Tensor, nch: int, sw: int, dtype=torch.bfloat16) -> Tensor:
+    """(N, K) -> 16-bit images [N/nch][KB][nch * sw/2] with rows of `sw` bytes (sw/2 channels per k-block, K % (sw/2) == 0);
+    dtype bfloat16 (default) or float16 (operands of a kind::f16 UMMA whose other operand is produced in half precision)."""
     N, K = w.shape
     cb = sw // 2
     assert N % nch == 0 and K % cb == 0, (N, K, nch, sw)
     KB = K // cb
-    t = w.to(torch.bfloat16).reshape(N // nch, nch, KB, cb).permute(0, 2, 1, 3).reshape(N // nch, KB, nch * cb)
+    t = w.to(dtype).reshape(N // nch, nch, KB, cb).permute(0, 2, 1, 3).reshape(N // nch, KB, nch * cb)
     img = torch.empty_like(t)
     img[:, :, _swizzle_perm(nch, sw, w.device).reshape(-1)] = t
     return img.contiguous()
@@ -97,11 +98,13 @@ def unpack_kmajor_sw(img: Tensor, N: int, K: int, nch: int, sw: int) -> Tensor:
 
 
 def pack_leff_taps(wdw: Tensor, bdw: Tensor, sl: int) -> Tensor:
-    """Depthwise Conv2d(groups=hidden) weight (hidden,1,3,3) + bias -> [hidden/sl][10][sl] fp32: per hidden slice the 9 taps
-    (tap = ky*3+kx) then the bias, one contiguous bulk-copy chunk per slice."""
+    """Depthwise Conv2d(groups=hidden) weight (hidden,1,3,3) + bias -> [hidden/sl][10][sl] fp16: per hidden slice the 9 taps
+    (tap = ky*3+kx) then the bias, one contiguous bulk-copy chunk per slice.  fp16: the fused kernel runs the depthwise
+    conv in packed half precision (the hidden map only exists on chip, in fp16 — 3 more mantissa bits than the bf16 map
+    the two-kernel path stores)."""
     hid = wdw.shape[0]
     t = torch.cat([wdw.float().reshape(hid, 9).t(), bdw.float()[None, :]], 0)            # (10, hidden)
-    return t.reshape(10, hid // sl, sl).permute(1, 0, 2).contiguous()
+    return t.reshape(10, hid // sl, sl).permute(1, 0, 2).contiguous().to(torch.float16)
 
 
 def pack_leff_fused(w1: Tensor, b1: Tensor, ln_w, ln_b, wdw: Tensor, bdw: Tensor, w2: Tensor, b2: Tensor, sl: int = 64) -> dict:
@@ -117,7 +120,7 @@ def pack_leff_fused(w1: Tensor, b1: Tensor, ln_w, ln_b, wdw: Tensor, bdw: Tensor
         w1f = w1f * ln_w.float()[None, :]
     w1g = w1f.to(torch.bfloat16)
     return dict(w1f_img=pack_kmajor_sw(w1g, sl, 2 * min(C, 64)), b1f=b1f.contiguous(), cs=w1g.float().sum(1).contiguous(),
-                taps=pack_leff_taps(wdw, bdw, sl), w2f_img=pack_kmajor_sw(w2, C, 2 * sl), b2=b2.float().contiguous(), hidden=hid,
+                taps=pack_leff_taps(wdw, bdw, sl), w2f_img=pack_kmajor_sw(w2, C, 2 * sl, torch.float16), b2=b2.float().contiguous(), hidden=hid,
                 has_ln=ln_w is not None, slice=sl)
 
 
