@@ -115,7 +115,7 @@ typedef struct lw_leff_args {
   const void* x;           /* bf16 (B*H*W rows, C) with row stride x_stride */
   void* out;               /* (B*H*W rows, C) bf16 or fp32, row stride out_stride */
   const void* resid;       /* same shape, bf16 or fp32, row stride resid_stride; or NULL */
-  const void* w1_img;      /* packed bf16 [hidden/SL][KB][SL rows x SW bytes], SW = 2*min(C,64), swizzle SW */
+  const void* w1_img;      /* packed bf16 [hidden/64][KB][64 rows x SW bytes], SW = 2*min(C,64), swizzle SW */
   const float* b1f;        /* (hidden) */
   const float* cs;         /* (hidden) */
   const void* taps;        /* [hidden/SL][10][SL] fp16 per hidden slice: 9 depthwise taps (tap = ky*3+kx), then the conv bias */

@@ -103,7 +103,7 @@ def leff(x, p, *, B, H, W, resid, out=None, out_dtype=None):
         assert _lib.load().lw_leff_fused_supported(C, hid)
         sl = p["slice"]
         assert sl == _lib.load().lw_leff_slice(C)
-        w1g = packing.unpack_kmajor_sw(p["w1f_img"], hid, C, sl, 2 * min(C, 64))
+        w1g = packing.unpack_kmajor_sw(p["w1f_img"], hid, C, 64, 2 * min(C, 64))      # linear1: 64-row units for every C
         acc = xf @ w1g.t()
         if p["has_ln"]:
             mean = xf.mean(1, keepdim=True)

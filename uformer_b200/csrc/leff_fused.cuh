@@ -65,7 +65,13 @@ struct LeffFCfg {
   static constexpr int A1_BYTES = KB1 * A1_KB_BYTES;
   static constexpr int NA1 = (C <= 64) ? 2 : 1;             // input tiles in flight
   static constexpr int X_BOX_BYTES = 180 * SW;              // one TMA box (one k-block)
-  static constexpr int W1_CHUNK = KB1 * SL * SW;
+  // C = 256 (SL = 32): GEMM-1 is issued for PAIRS of slices (N = 64: half as many tcgen05.mma as two N = 32 chains; the
+  // 32-wide MMAs and the weight ring behind them were the bound of that configuration, tools/leff_fused_trace.py), its W1
+  // operand arrives as two ring chunks of two k-blocks each.  Everything downstream stays 32 channels wide.
+  static constexpr bool PAIR = (SL == 32);
+  static constexpr int G1N = PAIR ? 64 : SL;                // N of the GEMM-1 instructions
+  static constexpr int G1_CHUNKS = PAIR ? 2 : 1;            // ring chunks per GEMM-1
+  static constexpr int W1_CHUNK = PAIR ? (KB1 / 2) * 64 * SW : KB1 * SL * SW;
   static constexpr int W2_CHUNK = C * SWH;
   static constexpr int STAGES = 3;
   static constexpr int HALO_BYTES = 192 * SWH;
@@ -84,9 +90,10 @@ struct LeffFCfg {
   static constexpr int S_STATS = S_B2 + 1024;                         // [2][192] float2
   static constexpr int S_MISC = S_STATS + 2 * 192 * 8;
   static constexpr int SMEM_BYTES = S_MISC + 2048 + 1024;
-  static constexpr int T_D1 = 0;                            // 2 x (SL cols M=128 part | SL cols M=64 part)
-  static constexpr int T_D2 = 4 * SL;                       // ND2 x C columns
-  static constexpr int ND2 = (4 * SL + 2 * C <= 512) ? 2 : 1;
+  static constexpr int T_D1 = 0;                            // 2 x (G1N cols M=128 part | G1N cols M=64 part)
+  static constexpr int D1_COLS = 2 * G1N;
+  static constexpr int T_D2 = 2 * D1_COLS;                  // ND2 x C columns
+  static constexpr int ND2 = (T_D2 + 2 * C <= 512) ? 2 : 1;
   static constexpr int T_ALLOC = 512;
   static_assert(C <= 256 && C % 16 == 0, "fused LeFF: C in {16,32,64,128,256}");
   static_assert(W1_CHUNK <= kStageBytes && W2_CHUNK <= kStageBytes, "ring stage");
@@ -170,7 +177,7 @@ __global__ void __launch_bounds__(kLFThreads, 1) leff_fused_kernel(const __grid_
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&ms.bar_x_full[i]), 1);  mbar_init(smem_u32(&ms.bar_x_empty[i]), 9);      // GEMM-1 commit + 8 epilogue warps (stats)
       mbar_init(smem_u32(&ms.bar_st_full[i]), 8); mbar_init(smem_u32(&ms.bar_st_empty[i]), 8);     // one lane per epilogue warp
-      mbar_init(smem_u32(&ms.bar_d1_full[i]), 1); mbar_init(smem_u32(&ms.bar_d1_empty[i]), 256);
+      mbar_init(smem_u32(&ms.bar_d1_full[i]), 1); mbar_init(smem_u32(&ms.bar_d1_empty[i]), Cfg::PAIR ? 512 : 256);
       mbar_init(smem_u32(&ms.bar_h_full[i]), 256); mbar_init(smem_u32(&ms.bar_h_empty[i]), kLFConv);
       mbar_init(smem_u32(&ms.bar_a2_full[i]), kLFConv); mbar_init(smem_u32(&ms.bar_a2_empty[i]), 1);
       mbar_init(smem_u32(&ms.bar_d2_full[i]), 1); mbar_init(smem_u32(&ms.bar_d2_empty[i]), (C >= 64) ? 256 : 128);
@@ -236,7 +243,11 @@ __global__ void __launch_bounds__(kLFThreads, 1) leff_fused_kernel(const __grid_
               mbar_expect_tx(smem_u32(&ms.bar_tap_full[tbuf]), Cfg::TAP_BYTES);
               bulk_g2s(smem_u32(smem + Cfg::S_TAPS + tbuf * Cfg::TAP_BYTES), a.taps + (size_t)j * Cfg::TAP_BYTES, Cfg::TAP_BYTES, smem_u32(&ms.bar_tap_full[tbuf]));
             }
-            ring.load(a.w1_img + (size_t)j * Cfg::W1_CHUNK, Cfg::W1_CHUNK);
+            if (!Cfg::PAIR) ring.load(a.w1_img + (size_t)j * Cfg::W1_CHUNK, Cfg::W1_CHUNK);
+            else if ((k & 1) == 0) {
+              ring.load(a.w1_img + (size_t)j * Cfg::W1_CHUNK, Cfg::W1_CHUNK);              // pair j/2: k-blocks 0-1 ...
+              ring.load(a.w1_img + (size_t)(j + 1) * Cfg::W1_CHUNK, Cfg::W1_CHUNK);        // ... and 2-3
+            }
           }
           if (k >= 2) ring.load(a.w2_img + (size_t)((k - 2) % NS) * Cfg::W2_CHUNK, Cfg::W2_CHUNK);
         }
@@ -244,33 +255,39 @@ __global__ void __launch_bounds__(kLFThreads, 1) leff_fused_kernel(const __grid_
     } else if (warp == 13) {
       // ============================== issuer (warp-uniform; one elected lane issues) ==============================
       Ring ring{smem_u32(smem + Cfg::S_RING), smem_u32(&ms.bar_full[0]), smem_u32(&ms.bar_empty[0]), Cfg::STAGES, 0};
-      constexpr uint32_t idesc_g1a = make_idesc_bf16(128, SL), idesc_g1b = make_idesc_bf16(64, SL), idesc_g2 = make_idesc_f16(128, C);
+      constexpr uint32_t idesc_g1a = make_idesc_bf16(128, Cfg::G1N), idesc_g1b = make_idesc_bf16(64, Cfg::G1N), idesc_g2 = make_idesc_f16(128, C);
       for (int k = 0; k < total + 2; ++k) {
-        if (k < total) {
-          // ---- GEMM-1 of slice k: D1[k&1] = X W1'_j^T ----
-          const int j = k % NS, it = k / NS, ab = it % Cfg::NA1, db = k & 1;
+        if (k < total && (!Cfg::PAIR || (k & 1) == 0)) {
+          // ---- GEMM-1 of slice k (PAIR: of slices k, k+1): D1[buffer] = X W1'^T ----
+          const int j = k % NS, it = k / NS, ab = it % Cfg::NA1;
+          const int db = Cfg::PAIR ? ((k >> 1) & 1) : (k & 1), use = Cfg::PAIR ? (k >> 2) : (k >> 1);
           if (j == 0) { mbar_wait(smem_u32(&ms.bar_x_full[ab]), (it / Cfg::NA1) & 1); }
-          mbar_wait(smem_u32(&ms.bar_d1_empty[db]), ((k >> 1) & 1) ^ 1);
+          mbar_wait(smem_u32(&ms.bar_d1_empty[db]), (use & 1) ^ 1);
           tc_fence_after();
-          const uint32_t wst = ring.acquire();
           const uint32_t xs = smem_u32(smem + Cfg::S_A1 + ab * Cfg::A1_BYTES);
-          if (elect_one()) {
+          constexpr int KBC = Cfg::KB1 / Cfg::G1_CHUNKS;       // k-blocks per ring chunk
 #pragma unroll
-            for (int kb = 0; kb < Cfg::KB1; ++kb)
+          for (int ch = 0; ch < Cfg::G1_CHUNKS; ++ch) {
+            const uint32_t wst = ring.acquire();
+            if (elect_one()) {
 #pragma unroll
-              for (int ks = 0; ks < Cfg::KS1; ++ks) {
-                const uint64_t bd = kmajor_desc<Cfg::SW>(wst + kb * SL * Cfg::SW + ks * 32);
-                umma_ss(tb + Cfg::T_D1 + db * 2 * SL, kmajor_desc<Cfg::SW>(xs + kb * Cfg::A1_KB_BYTES + ks * 32), bd, idesc_g1a, (kb | ks) != 0);
-                umma_ss(tb + Cfg::T_D1 + db * 2 * SL + SL, kmajor_desc<Cfg::SW>(xs + kb * Cfg::A1_KB_BYTES + 128 * Cfg::SW + ks * 32), bd, idesc_g1b,
-                        (kb | ks) != 0);
-              }
+              for (int kb2 = 0; kb2 < KBC; ++kb2)
+#pragma unroll
+                for (int ks = 0; ks < Cfg::KS1; ++ks) {
+                  const int kb = ch * KBC + kb2;
+                  const uint64_t bd = kmajor_desc<Cfg::SW>(wst + kb2 * Cfg::G1N * Cfg::SW + ks * 32);
+                  umma_ss(tb + Cfg::T_D1 + db * Cfg::D1_COLS, kmajor_desc<Cfg::SW>(xs + kb * Cfg::A1_KB_BYTES + ks * 32), bd, idesc_g1a, (kb | ks) != 0);
+                  umma_ss(tb + Cfg::T_D1 + db * Cfg::D1_COLS + Cfg::G1N, kmajor_desc<Cfg::SW>(xs + kb * Cfg::A1_KB_BYTES + 128 * Cfg::SW + ks * 32), bd,
+                          idesc_g1b, (kb | ks) != 0);
+                }
+            }
+            __syncwarp();
+            ring.release();
           }
-          __syncwarp();
-          ring.release();
           if (lane == 0) { LF_TRACE(3, 2 * k) }
           if (elect_one()) {
             umma_commit(smem_u32(&ms.bar_d1_full[db]));
-            if (j == NS - 1) umma_commit(smem_u32(&ms.bar_x_empty[ab]));
+            if (j == NS - (Cfg::PAIR ? 2 : 1)) umma_commit(smem_u32(&ms.bar_x_empty[ab]));
           }
           __syncwarp();
         }
@@ -409,7 +426,8 @@ __global__ void __launch_bounds__(kLFThreads, 1) leff_fused_kernel(const __grid_
     // group g takes fragment g whole and one 16-column half of fragment 2.
     constexpr int HP = SL / 32;
     for (int k = 0; k < total; ++k) {
-      const int j = k % NS, it = k / NS, db = k & 1, sb = it & 1;
+      const int j = k % NS, it = k / NS, db = k & 1, sb = it & 1;                       // db: halo buffer
+      const int d1b = Cfg::PAIR ? ((k >> 1) & 1) : (k & 1), d1use = Cfg::PAIR ? (k >> 2) : (k >> 1);   // D1 accumulator buffer
       if (j == 0) {
         // ---- LayerNorm statistics of the new tile's 192 rows, 24 rows per epilogue warp, straight from the landed A tile.
         // One pass: sums of d = x - x0 and d^2 with x0 = the row's first element (shifting by a value of the row keeps
@@ -483,7 +501,7 @@ __global__ void __launch_bounds__(kLFThreads, 1) leff_fused_kernel(const __grid_
         if (q == 0 && lane == 0) { LF_TRACE(4, 2 * it + 1) }
       }
       mbar_wait(smem_u32(&ms.bar_h_empty[db]), ((k >> 1) & 1) ^ 1);          // conv finished reading this halo buffer (slice k-2)
-      mbar_wait(smem_u32(&ms.bar_d1_full[db]), (k >> 1) & 1);
+      mbar_wait(smem_u32(&ms.bar_d1_full[d1b]), d1use & 1);
       tc_fence_after();
       if (q == 0 && lane == 0) { LF_TRACE(grp, 2 * k) }
       const uint32_t hb = halo0 + db * Cfg::HALO_BYTES;
@@ -521,12 +539,13 @@ __global__ void __launch_bounds__(kLFThreads, 1) leff_fused_kernel(const __grid_
           stsm_x4(hb + swz<Cfg::SWH>(row, (c0 / 8 + (m >> 1)) * 16), pk[0], pk[1], pk[2], pk[3]);
         }
       };
-      const uint32_t tcol = tb + Cfg::T_D1 + db * 2 * SL;
+      // columns of this slice inside the accumulator buffer: M=128 part at +0 (PAIR: + 32*(k&1)), M=64 part G1N further
+      const uint32_t tcol = tb + Cfg::T_D1 + d1b * Cfg::D1_COLS + (Cfg::PAIR ? (k & 1) * SL : 0);
       if (SL == 64) {
         // pieces p = 3*grp .. 3*grp+2 of (f = p / 2, half = p % 2), software-pipelined TMEM loads
         uint32_t v[2][16];
         const int p0 = 3 * grp;
-        auto paddr = [&](int p) { const int f = p / HP; return tcol + frag_lanes(f) + (f == 2 ? SL : 0) + (p % HP) * 32; };
+        auto paddr = [&](int p) { const int f = p / HP; return tcol + frag_lanes(f) + (f == 2 ? Cfg::G1N : 0) + (p % HP) * 32; };
         tmem_ld_16x256b_x4(paddr(p0), v[0]);
 #pragma unroll
         for (int pi = 0; pi < 3; ++pi) {
@@ -538,13 +557,13 @@ __global__ void __launch_bounds__(kLFThreads, 1) leff_fused_kernel(const __grid_
       } else {
         uint32_t v0[16], v1[8];
         tmem_ld_16x256b_x4(tcol + frag_lanes(grp), v0);                                   // fragment grp, 32 columns
-        tmem_ld_16x256b_x2(tcol + frag_lanes(2) + SL + grp * 16, v1);                     // fragment 2, columns 16*grp .. +16
+        tmem_ld_16x256b_x2(tcol + frag_lanes(2) + Cfg::G1N + grp * 16, v1);               // fragment 2, columns 16*grp .. +16
         tmem_wait_ld();
         do_piece(v0, grp, 0, std::integral_constant<int, 4>());
         do_piece(v1, 2, grp * 16, std::integral_constant<int, 2>());
       }
       tc_fence_before();
-      mbar_arrive(smem_u32(&ms.bar_d1_empty[db]));
+      mbar_arrive(smem_u32(&ms.bar_d1_empty[d1b]));
       mbar_arrive(smem_u32(&ms.bar_h_full[db]));
       if (q == 0 && lane == 0) { LF_TRACE(grp, 2 * k + 1) }
       // the previous tile's output epilogue runs one or two slices into this tile (its GEMM-2 chain has drained by then)

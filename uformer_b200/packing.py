@@ -108,7 +108,8 @@ def pack_leff_taps(wdw: Tensor, bdw: Tensor, sl: int) -> Tensor:
 
 
 def pack_leff_fused(w1: Tensor, b1: Tensor, ln_w, ln_b, wdw: Tensor, bdw: Tensor, w2: Tensor, b2: Tensor, sl: int = 64) -> dict:
-    """Operands of the single-kernel LeFF (csrc/leff_fused.cuh, lw_leff_fwd); `sl` = lw_leff_slice(C) hidden channels per slice.
+    """Operands of the single-kernel LeFF (csrc/leff_fused.cuh, lw_leff_fwd); `sl` = lw_leff_slice(C) hidden channels per slice
+    (taps and linear2 are cut with it; linear1 is always cut in 64-row units: at sl = 32 GEMM-1 runs on pairs of slices).
     LayerNorm (norm2, model.py:987) is folded into linear1 (model.py:671):
       LN(x) W1^T + b1 = rstd*(x W1g^T) - rstd*mean*cs + b1f  with  W1g = W1 diag(gamma) rounded to bf16,
     cs = row sums of that bf16 matrix (so the mean term cancels exactly against what the tensor core accumulates) and
@@ -119,7 +120,7 @@ def pack_leff_fused(w1: Tensor, b1: Tensor, ln_w, ln_b, wdw: Tensor, bdw: Tensor
         b1f = b1f + (w1f * ln_b.float()[None, :]).sum(1)       # same reduction as prepack.py (bit-identical images)
         w1f = w1f * ln_w.float()[None, :]
     w1g = w1f.to(torch.bfloat16)
-    return dict(w1f_img=pack_kmajor_sw(w1g, sl, 2 * min(C, 64)), b1f=b1f.contiguous(), cs=w1g.float().sum(1).contiguous(),
+    return dict(w1f_img=pack_kmajor_sw(w1g, 64, 2 * min(C, 64)), b1f=b1f.contiguous(), cs=w1g.float().sum(1).contiguous(),
                 taps=pack_leff_taps(wdw, bdw, sl), w2f_img=pack_kmajor_sw(w2, C, 2 * sl, torch.float16), b2=b2.float().contiguous(), hidden=hid,
                 has_ln=ln_w is not None, slice=sl)
 

@@ -74,7 +74,7 @@ def _pack_blocks(blks):
         w1g = (w1 * gamma[:, None, :]).to(torch.bfloat16)
         cs = w1g.float().sum(2).contiguous()
         sl = lib.lw_leff_slice(C)
-        w1f_img = packing.pack_kmajor_sw(w1g.view(nb * hid, C), sl, 2 * min(C, 64)).view(nb, hid // sl, -1, sl * min(C, 64))
+        w1f_img = packing.pack_kmajor_sw(w1g.view(nb * hid, C), 64, 2 * min(C, 64)).view(nb, hid // 64, -1, 64 * min(C, 64))
         w2f_img = packing.pack_kmajor_sw(w2.view(nb * C, hid), C, 2 * sl, torch.float16).view(nb, 1, hid // sl, C * sl)
         taps = torch.cat([wd, bdw[:, None, :]], 1).view(nb, 10, hid // sl, sl).permute(0, 2, 1, 3).contiguous().to(torch.float16)   # (nb, NS, 10, sl)
     else:
