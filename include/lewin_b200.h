@@ -135,11 +135,12 @@ int lw_leff_slice(int C);
 
 /* ---- Downsample: Conv2d(k4,s2,p1) on the token map as an implicit GEMM (model.py:739-746) */
 typedef struct lw_down_args {
-  const void* x;           /* bf16 (B, H, W, Cin) */
+  const void* x;           /* bf16 (B, H, W, Cin); rows may be x_stride elements apart (a column slice of the skip-concat buffer) */
   void* out;               /* bf16 (B, H/2*W/2, Cout) */
   const void* w_img;       /* packed bf16 [16*Cin/64][Cout/nch][nch x 128B], K index = tap*Cin+ci */
   const float* bias;       /* (Cout) */
   int32_t B, H, W, Cin, Cout;
+  int32_t x_stride;        /* row stride of x in elements; 0 = Cin (contiguous) */
 } lw_down_args;
 int lw_downsample_fwd(const lw_down_args* a, lw_stream_t stream);
 

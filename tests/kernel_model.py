@@ -145,7 +145,7 @@ def downsample(x, p, *, B, H, W):
     Cin, Cout = x.shape[-1], p["cout"]
     wk = packing.unpack_kmajor(p["w_img"], Cout, 16 * Cin, min(Cout, 128), "kn")         # K index = (ky*4+kx)*Cin + ci
     w = wk.view(Cout, 4, 4, Cin).permute(0, 3, 1, 2)
-    o = F.conv2d(x.float().view(B, H, W, Cin).permute(0, 3, 1, 2), w, p["bias"], stride=2, padding=1)
+    o = F.conv2d(x.float().reshape(B, H, W, Cin).permute(0, 3, 1, 2), w, p["bias"], stride=2, padding=1)
     return o.flatten(2).transpose(1, 2).contiguous().to(BF)
 
 

@@ -47,7 +47,7 @@ class LeffArgs(C.Structure):
 
 class DownArgs(C.Structure):
     _fields_ = [("x", C.c_void_p), ("out", C.c_void_p), ("w_img", C.c_void_p), ("bias", C.c_void_p), ("B", C.c_int32),
-                ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32), ("Cout", C.c_int32)]
+                ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32), ("Cout", C.c_int32), ("x_stride", C.c_int32)]
 
 
 class UpArgs(C.Structure):

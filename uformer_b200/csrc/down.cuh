@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(kThreads8, 1) down_kernel(const AStreamArgs a,
         const int rr = (tid >> 3) + 32 * it;
         const int iy = y2[it] + ky, ix = x2[it] + kx;
         const bool ok = base_off[it] >= 0 && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W;
-        const bf16* g = ok ? a.src + ((size_t)(base_off[it] + iy * a.W + ix)) * a.Cin + ci : a.src;
+        const bf16* g = ok ? a.src + ((size_t)(base_off[it] + iy * a.W + ix)) * a.src_stride + ci : a.src;
         cp_async16(dst0 + swz<128>(rr, v * 16), g, ok ? 16u : 0u);
       }
       cp_async_commit();

@@ -250,6 +250,7 @@ struct AStreamArgs {
   int B, H, W;            // geometry of src
   int K;                  // PROD 0: hidden; PROD 1: 16*Cin
   int Cin;                // PROD 1 only
+  int src_stride;         // PROD 1: row stride of src in elements (>= Cin: src may be a column slice of a wider buffer)
   const float* wd;        // PROD 0: (9, K) taps
   const float* bd;        // PROD 0: (K)
   const uint8_t* w_img;   // [K/64][N/nch][nch*128B]

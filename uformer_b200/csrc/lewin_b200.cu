@@ -292,6 +292,8 @@ extern "C" int lw_downsample_fwd(const lw_down_args* p, lw_stream_t stream) {
   if (!all_aligned16(p->x, p->out, p->w_img, p->bias)) return LW_ERR_ALIGN;
   AStreamArgs a{};
   a.src = reinterpret_cast<const bf16*>(p->x); a.B = p->B; a.H = p->H; a.W = p->W; a.K = 16 * p->Cin; a.Cin = p->Cin;
+  a.src_stride = p->x_stride > 0 ? p->x_stride : p->Cin;
+  if (a.src_stride < p->Cin || a.src_stride % 8) return LW_ERR_BAD_SHAPE;
   a.w_img = reinterpret_cast<const uint8_t*>(p->w_img); a.N = p->Cout; a.nch = p->Cout < 128 ? p->Cout : 128;
   a.bias = p->bias; a.out = reinterpret_cast<bf16*>(p->out);
   const int rows = p->B * (p->H / 2) * (p->W / 2);

@@ -95,6 +95,14 @@ def _as_bf16(x):
     return x.to(torch.bfloat16).contiguous(), x.dtype
 
 
+def _as_bf16_rows(x):
+    """Like _as_bf16, but a bf16 column slice of a wider buffer (unit channel stride, uniform row stride) passes through
+    without a copy: the kernels that accept it take the row stride."""
+    if x.dtype == torch.bfloat16 and x.dim() == 3 and x.stride(-1) == 1 and (x.shape[0] == 1 or x.stride(0) == x.shape[1] * x.stride(1)):
+        return x, None
+    return _as_bf16(x)
+
+
 def _run(mod, native, restate, acts):
     """Native forward of `mod`; under autograd the same call is wrapped so that backward recomputes it from `acts`."""
     _lib.require_device(acts[0].device)         # device check first: no CPU fallback, fail loudly
@@ -289,7 +297,7 @@ class Downsample(nn.Module):
         _lib.require_device(x.device)
         B, L, _ = x.shape
         H = int(math.sqrt(L))
-        xb, back = _as_bf16(x)
+        xb, back = _as_bf16_rows(x)
         out = _run(self, lambda t: ops.downsample(t, self.packed(), B=B, H=H, W=H), lambda t: restated.downsample(self, t), [xb])
         return out if back is None else out.to(back)
 

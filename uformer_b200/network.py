@@ -11,16 +11,12 @@ decoder input buffer, the skip is copied once into the right half.
 from __future__ import annotations
 
 import math
-import os
 
 import torch
 import torch.nn as nn
 
 from . import _lib, autograd, ops, restated
 from .modules import Downsample, LeWinTransformerBlock, Upsample, _run
-
-# working-set budget (MB) for the optional images-outer stage schedule (B200 L2 is 126 MB)
-L2_BUDGET_BYTES = int(os.environ.get("UFORMER_B200_L2_BUDGET_MB", str(1 << 20))) << 20     # default: off (measured slower)
 
 _STAGE_NAMES = ["encoderlayer_0", "encoderlayer_1", "encoderlayer_2", "encoderlayer_3", "conv",
                 "decoderlayer_0", "decoderlayer_1", "decoderlayer_2", "decoderlayer_3"]
@@ -46,27 +42,20 @@ class LeWinStage(nn.Module):
     def extra_repr(self):
         return f"dim={self.dim}, input_resolution={self.input_resolution}, depth={self.depth}"
 
-    def forward(self, x, mask=None):
-        """Runs the blocks of this stage.  When the stage's per-batch working set (token map, W-MSA output and the
-        4C-wide LeFF hidden map, ~14*L*C bytes per image in bf16) exceeds the L2 budget, the loop order is
-        images-outer / blocks-inner: each sub-batch of images runs through ALL blocks before the next one starts,
-        so x1 / h1 / the next block's input are produced and consumed while still L2-resident and the scratch
-        buffers are re-used at the same addresses (the reference loops blocks-outer, model.py:1054-1060; the
-        result is identical because no op couples images)."""
-        B, L, C = x.shape
-        per_image = 14 * L * C
-        chunk = max(1, min(B, L2_BUDGET_BYTES // per_image))
-        if chunk >= B or mask is not None or x.dtype != torch.bfloat16 or len(self.blocks) == 0 or autograd.wants_grad(x, *autograd.trainable_tensors(self)):
+    def forward(self, x, mask=None, out=None):
+        """Runs the blocks of this stage (model.py:1054-1060).  `out` (inference only): a bf16 destination for the LAST
+        block's output — a column slice of the skip-concat buffer, so the encoder skip is produced in place
+        (model.py:1288-1300) — honoured when that block's fused LeFF can write strided rows; otherwise the result is copied."""
+        if out is None or len(self.blocks) == 0:
             for blk in self.blocks:
                 x = blk(x, mask)
-            return x
-        out = torch.empty_like(x)
-        for i0 in range(0, B, chunk):
-            y = x[i0:i0 + chunk]
-            for bi, blk in enumerate(self.blocks):
-                last = bi == len(self.blocks) - 1
-                y = blk(y, None, out=out[i0:i0 + chunk] if last else None)
-        return out
+            return x if out is None else out.copy_(x)
+        for blk in self.blocks[:-1]:
+            x = blk(x, mask)
+        last = self.blocks[-1]
+        if x.dtype == torch.bfloat16 and last.mlp.fused() and not last.residual_fp32 and not autograd.wants_grad(x, *autograd.trainable_tensors(self)):
+            return last(x, mask, out=out)
+        return out.copy_(last(x, mask))
 
     def flops(self):
         return sum(b.flops() for b in self.blocks)
@@ -197,21 +186,24 @@ class Uformer(nn.Module):
         return self.output_proj(y, x if self.dd_in == 3 else None)
 
     def _forward_infer(self, x, mask=None):
+        """Inference schedule.  Skip-concat fusion (model.py:1288-1300): each level's (B, L, 2C) decoder-input buffer is allocated
+        up front; the last encoder block of the level writes its output straight into the right half (strided rows out of the
+        fused LeFF kernel), Downsample reads it from there, and the decoder's Upsample later writes the left half in place —
+        torch.cat and the skip copy never run."""
         B = x.shape[0]
         y = self.input_proj(x)
-        skips = []
+        cats = []
         for i in range(4):
-            y = getattr(self, f"encoderlayer_{i}")(y, mask)
-            skips.append(y)
-            y = getattr(self, f"dowsample_{i}")(y)
+            stage = getattr(self, f"encoderlayer_{i}")
+            co = getattr(self, f"upsample_{3 - i}").out_channel          # left half: the transposed-conv output of this level
+            cat = torch.empty((B, y.shape[1], co + stage.dim), dtype=torch.bfloat16, device=y.device)
+            skip = stage(y, mask, out=cat[:, :, co:])
+            cats.append(cat)
+            y = getattr(self, f"dowsample_{i}")(skip)
         y = self.conv(y, mask)
         for j in range(4):
-            up = getattr(self, f"upsample_{j}")
-            skip = skips[3 - j]
-            co = up.out_channel
-            cat = torch.empty((B, skip.shape[1], co + skip.shape[2]), dtype=torch.bfloat16, device=y.device)
-            up(y, out=cat)                      # left half: transposed-conv output, written in place
-            cat[:, :, co:].copy_(skip)          # right half: encoder skip
+            cat = cats[3 - j]
+            getattr(self, f"upsample_{j}")(y, out=cat)                   # left half, written in place
             y = getattr(self, f"decoderlayer_{j}")(cat, mask)
         return self.output_proj(y, x if self.dd_in == 3 else None)
 

@@ -139,12 +139,15 @@ def _leff_two_kernels(x: Tensor, p: dict, *, B: int, H: int, W: int, resid: Tens
 
 
 def downsample(x: Tensor, p: dict, *, B: int, H: int, W: int) -> Tensor:
-    _check_act(x, "x")
+    """x may be a column slice of a wider (B, HW, S) buffer (the encoder skip living in the skip-concat buffer)."""
+    if x.dtype != torch.bfloat16:
+        raise TypeError(f"x must be bfloat16 (got {x.dtype})")
+    _lib.require_device(x.device)
     Cin, Cout = x.shape[-1], p["cout"]
     out = torch.empty((B, (H // 2) * (W // 2), Cout), dtype=torch.bfloat16, device=x.device)
     a = _lib.DownArgs()
     a.x, a.out, a.w_img, a.bias = _ptr(x), _ptr(out), _ptr(p["w_img"]), _ptr(p["bias"])
-    a.B, a.H, a.W, a.Cin, a.Cout = B, H, W, Cin, Cout
+    a.B, a.H, a.W, a.Cin, a.Cout, a.x_stride = B, H, W, Cin, Cout, _row_stride(x, "x")
     _launch(f"down_C{Cin}", 2.0 * B * (H // 2) * (W // 2) * 16 * Cin * Cout, lambda st: _lib.load().lw_downsample_fwd(C.byref(a), st),
             "lw_downsample_fwd", x.device)
     return out
