@@ -309,7 +309,11 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="images per GPU per step (default: 32 for fwd, 8 for train)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="fwd", choices=["fwd", "train"])
+    ap.add_argument("--residual", default=None, choices=["auto", "fp32", "bf16"],
+                    help="residual-stream precision between the kernels of a stage (default: the engine's default, fp32)")
     args = ap.parse_args()
+    if args.residual:
+        os.environ["UFORMER_B200_RESIDUAL"] = args.residual
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -488,7 +492,8 @@ def main():
         "config": {"workload": "Uformer-B 256x256 inference fwd, batch 32 per GPU (BASELINE configs[1])", "global_batch": B * world,
                    "per_gpu_batch": B, "parallelism": f"replicas x{world} (no collective)", "l2": "256MB flush between timed steps",
                    "weights": "synthetic seeded init of the Uformer-B architecture",
-                   "cuda_graph": graphed is not None},
+                   "cuda_graph": graphed is not None,
+                   "residual_stream": os.environ.get("UFORMER_B200_RESIDUAL", "auto") + " (fp32 between the kernels of the >=4-block stages, bf16 elsewhere; bf16 operands, fp32 accumulate)"},
         "e2e": {"value": e2e_val, "unit": "img/s", "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": yh[0].numel() * 4, "pipelined": "2 copy streams, double-buffered",
                 "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline}

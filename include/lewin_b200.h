@@ -39,6 +39,10 @@ const char* lw_last_cuda_error(void);
 /* 0 if the current device is a B200-class (sm_100) part, LW_ERR_ARCH otherwise. */
 int lw_check_device(void);
 
+/* sizeof() of the argument struct `id` as this library was compiled (0 wmsa, 1 leff1, 2 leff2, 3 leff, 4 down, 5 up, 6 adamw):
+ * lets a binding (uformer_b200/_lib.py mirrors the structs with ctypes) verify its layout; -1 for an unknown id. */
+int lw_struct_size(int id);
+
 /* Rows per weight-image chunk the A-resident GEMM kernels (lw_leff1_fwd, lw_upsample_fwd) expect for
  * reduction depth K and output width n_total: the host packer must cut w1_img / w_img with this value. */
 int lw_nch_ares(int K, int n_total);
@@ -70,6 +74,10 @@ typedef struct lw_wmsa_args {
   float ln_eps;
   int32_t dbg;             /* profiling aid (env LW_DEBUG & 16): CTA 0 writes clock64 timestamps to `trace` */
   long long* trace;
+  /* fp32 residual-stream mode (0 / NULL = everything bf16): */
+  int32_t x_fp32;          /* x and resid are fp32 (the residual stream); the GEMM operand is still rounded to bf16 after LayerNorm */
+  int32_t out_fp32;        /* out is fp32 */
+  void* out_b;             /* optional bf16 copy of out (same layout): the GEMM operand of the LeFF kernel that follows */
 } lw_wmsa_args;
 int lw_wmsa_fwd(const lw_wmsa_args* a, lw_stream_t stream);
 
@@ -90,13 +98,14 @@ int lw_leff1_fwd(const lw_leff1_args* a, lw_stream_t stream);
  * the depthwise conv is staged in shared memory (zero padding on h1) and feeds the GEMM directly. */
 typedef struct lw_leff2_args {
   const void* h1;          /* bf16 (B, H, W, hidden) */
-  void* out;               /* bf16 (B, H*W, C) */
-  const void* resid;       /* bf16 (B, H*W, C) or NULL */
+  void* out;               /* bf16 (B, H*W, C) (fp32 if out_fp32) */
+  const void* resid;       /* bf16 (B, H*W, C) (fp32 if resid_fp32) or NULL */
   const float* wd;         /* (9, hidden) fp32 depthwise taps, tap = ky*3+kx */
   const float* bd;         /* (hidden) */
   const void* w2_img;      /* packed bf16 [hidden/64][C/nch][nch x 128B] */
   const float* b2;         /* (C) */
   int32_t B, H, W, C, hidden;
+  int32_t resid_fp32, out_fp32;   /* fp32 residual-stream mode (0 = bf16) */
 } lw_leff2_args;
 int lw_leff2_fwd(const lw_leff2_args* a, lw_stream_t stream);
 

@@ -69,15 +69,12 @@ def build_module(g):
 
 
 def model_tolerances(g):
-    """(full-output, residual-branch) rel-L2 bounds for a whole-model fixture.  north_star's 1e-2 (bf16) applies to the
-    output; the residual branch out - x gets 2x (the identity term hides error).  Fixtures that record the
-    reference's OWN bf16-autocast error (the flagship model with O(1)-activation weights, where that error exceeds 1e-2
-    after 40 blocks) are bounded by 1.25x that error instead: the engine must not be noisier than the reference in bf16."""
-    full, resid = TOL_BF16, 2 * TOL_BF16
-    if "ref_bf16" in g:
-        full = max(full, 1.25 * g["ref_bf16"]["full"])
-        resid = max(resid, 1.25 * g["ref_bf16"]["resid"])
-    return full, resid
+    """(full-output, residual-branch) rel-L2 bounds for a whole-model fixture: north_star's 1e-2 (bf16 arithmetic) on the
+    output; the residual branch out - x gets 2x (the identity term hides error).  No fixture-specific slack: the
+    engine's default precision mode (fp32 residual stream inside a stage) must meet the plain bound on every fixture,
+    including the 40-block flagship with the bench's O(1)-activation weights, where the reference's own bf16-autocast forward
+    is 1.3e-2 away from its fp32 forward (recorded in the fixture as `ref_bf16` for information)."""
+    return TOL_BF16, 2 * TOL_BF16
 
 
 def oracle_run(g, st, x, dtype=torch.float32, mask=None):

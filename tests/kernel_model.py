@@ -47,8 +47,9 @@ def _shift_mask(H, W, shift):
     return torch.where(rw[:, None, :] != rw[:, :, None], -100.0, 0.0)
 
 
-def wmsa(x, p, *, H, W, shift, windowed, resid, mask=None, out=None):
-    assert x.dtype == BF and x.is_contiguous()
+def wmsa(x, p, *, H, W, shift, windowed, resid, mask=None, out=None, out_dtype=None, bf16_copy=False):
+    assert x.dtype in (BF, torch.float32) and x.is_contiguous()
+    assert resid is None or resid.dtype == x.dtype
     C = x.shape[-1]
     hd = p["head_dim"]
     heads = C // hd
@@ -85,13 +86,16 @@ def wmsa(x, p, *, H, W, shift, windowed, resid, mask=None, out=None):
         if shift:
             y = torch.roll(y, (shift, shift), (1, 2))
         y = y.reshape(x.shape)
+    y = _q(y)                                                    # the branch is rounded to bf16 in the staging tile
     if resid is not None:
         y = y + resid.float()
-    y = y.to(BF)
+    odt = out.dtype if out is not None else (out_dtype or BF)
+    yb = y.to(BF) if bf16_copy else None
+    y = y.to(odt)
     if out is not None:
         out.copy_(y)
-        return out
-    return y
+        y = out
+    return (y, yb) if bf16_copy else y
 
 
 def leff(x, p, *, B, H, W, resid, out=None, out_dtype=None):

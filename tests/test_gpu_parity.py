@@ -256,24 +256,30 @@ def test_downsample_linearity_property_full_size():
 
 
 @pytest.mark.parametrize("name", ["uformer_b_256", "uformer_t2_128"])
-def test_fp32_residual_precision_mode(name):
-    """Precision mode (uformer_b200.set_residual_precision): residual stream in fp32 between the same kernels.  Must be at
-    least as accurate as the default path; the CPU contract model predicts 8.0e-3 (flagship) / 5.7e-3 (t2)."""
+def test_residual_precision_modes(name):
+    """uformer_b200.set_residual_precision: fp32 residual stream inside a stage (the default; must meet the plain tolerance)
+    vs the faster bf16 stream (the residual is rounded twice per block: noisier, bounded by 1.5x the tolerance here)."""
     import uformer_b200 as U
     g = load_golden(name)
     net, _ = build_module(g)
     net = net.to(DEV)
     x = g["x"].to(DEV)
     with torch.no_grad():
-        y_bf = net(x).float().cpu()
+        y_auto = net(x).float().cpu()                       # default policy: fp32 stream in the stages of >= 4 blocks
         U.set_residual_precision(net, torch.float32)
         y_32 = net(x).float().cpu()
+        U.set_residual_precision(net, torch.bfloat16)
+        y_bf = net(x).float().cpu()
+        U.set_residual_precision(net, torch.float32)
+        assert torch.equal(net(x).float().cpu(), y_32)
+    print(f"{name}: default (auto) policy {rel_l2(y_auto, g['y']):.3e}")
+    _check(y_auto, g["y"], name + " auto-residual", tol=model_tolerances(g)[0])
     e_bf, e_32 = rel_l2(y_bf, g["y"]), rel_l2(y_32, g["y"])
     print(f"{name}: bf16 residual stream {e_bf:.3e} -> fp32 residual stream {e_32:.3e}")
     tol_full, tol_resid = model_tolerances(g)
     _check(y_32, g["y"], name + " fp32-residual", tol=tol_full)
     _check(y_32 - g["x"], g["y"] - g["x"], name + " fp32-residual residual-branch", tol=tol_resid)
-    assert e_32 < e_bf
+    assert e_32 < e_bf < 1.5 * tol_full
 
 
 @pytest.mark.parametrize("dim,H,B", [(32, 16, 2), (64, 24, 1), (128, 16, 2), (16, 8, 3), (256, 16, 1)])

@@ -63,10 +63,11 @@ def test_c_abi_exports_every_declared_symbol():
     lib = _lib.load()
     for s in declared:
         assert hasattr(lib, s), s
-    assert lib.lw_abi_version() == 2
-    # struct sizes agree with the header layout (pointers 8 B, ints 4 B)
-    assert ctypes.sizeof(_lib.WmsaArgs) == 12 * 8 + 10 * 4 + 8      # 12 pointers, 9 ints + float, trace pointer
-    assert ctypes.sizeof(_lib.Leff2Args) == 7 * 8 + 5 * 4 + 4
+    assert lib.lw_abi_version() == 3
+    # the ctypes mirrors have the compiled structs' sizes (also enforced at load time)
+    for i, st in enumerate([_lib.WmsaArgs, _lib.Leff1Args, _lib.Leff2Args, _lib.LeffArgs, _lib.DownArgs, _lib.UpArgs, _lib.AdamWArgs]):
+        assert lib.lw_struct_size(i) == ctypes.sizeof(st), st.__name__
+    assert lib.lw_struct_size(99) == -1
 
 
 def test_argument_validation_without_gpu():

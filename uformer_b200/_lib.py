@@ -23,7 +23,8 @@ class WmsaArgs(C.Structure):
                 ("modulator", C.c_void_p), ("wqkv_img", C.c_void_p), ("bqkv", C.c_void_p), ("wproj_img", C.c_void_p),
                 ("bproj", C.c_void_p), ("relpos", C.c_void_p), ("mask", C.c_void_p), ("n_mask_windows", C.c_int32),
                 ("n_windows", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32), ("head_dim", C.c_int32),
-                ("shift", C.c_int32), ("windowed", C.c_int32), ("ln_eps", C.c_float), ("dbg", C.c_int32), ("trace", C.c_void_p)]
+                ("shift", C.c_int32), ("windowed", C.c_int32), ("ln_eps", C.c_float), ("dbg", C.c_int32), ("trace", C.c_void_p),
+                ("x_fp32", C.c_int32), ("out_fp32", C.c_int32), ("out_b", C.c_void_p)]
 
 
 class Leff1Args(C.Structure):
@@ -34,7 +35,7 @@ class Leff1Args(C.Structure):
 class Leff2Args(C.Structure):
     _fields_ = [("h1", C.c_void_p), ("out", C.c_void_p), ("resid", C.c_void_p), ("wd", C.c_void_p), ("bd", C.c_void_p),
                 ("w2_img", C.c_void_p), ("b2", C.c_void_p), ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
-                ("C", C.c_int32), ("hidden", C.c_int32)]
+                ("C", C.c_int32), ("hidden", C.c_int32), ("resid_fp32", C.c_int32), ("out_fp32", C.c_int32)]
 
 
 class LeffArgs(C.Structure):
@@ -64,7 +65,7 @@ class AdamWArgs(C.Structure):
 CHARBONNIER_PARTIALS = 1024      # LW_CHARBONNIER_PARTIALS
 
 # every symbol include/lewin_b200.h declares
-EXPORTS = ["lw_abi_version", "lw_last_cuda_error", "lw_check_device", "lw_nch_ares", "lw_wmsa_fwd", "lw_leff1_fwd", "lw_leff2_fwd", "lw_leff_fwd", "lw_leff_fused_supported", "lw_leff_slice",
+EXPORTS = ["lw_abi_version", "lw_struct_size", "lw_last_cuda_error", "lw_check_device", "lw_nch_ares", "lw_wmsa_fwd", "lw_leff1_fwd", "lw_leff2_fwd", "lw_leff_fwd", "lw_leff_fused_supported", "lw_leff_slice",
            "lw_downsample_fwd", "lw_upsample_fwd", "lw_input_proj_fwd", "lw_output_proj_fwd", "lw_charbonnier_fwd_bwd", "lw_adamw_step"]
 
 _lib = None
@@ -81,6 +82,12 @@ def load():
     lib.lw_abi_version.restype = C.c_int
     lib.lw_last_cuda_error.restype = C.c_char_p
     lib.lw_check_device.restype = C.c_int
+    lib.lw_struct_size.restype = C.c_int
+    lib.lw_struct_size.argtypes = [C.c_int]
+    for i, st in enumerate([WmsaArgs, Leff1Args, Leff2Args, LeffArgs, DownArgs, UpArgs, AdamWArgs]):
+        if lib.lw_struct_size(i) != C.sizeof(st):
+            raise EngineUnavailable(f"{LIB_PATH}: argument struct {st.__name__} is {lib.lw_struct_size(i)} bytes in the library, "
+                                    f"{C.sizeof(st)} in the binding (stale build?)")
     lib.lw_nch_ares.restype = C.c_int
     lib.lw_nch_ares.argtypes = [C.c_int, C.c_int]
     lib.lw_leff_fused_supported.restype = C.c_int

@@ -256,8 +256,9 @@ struct AStreamArgs {
   const uint8_t* w_img;   // [K/64][N/nch][nch*128B]
   int N, nch;
   const float* bias;      // (N)
-  const bf16* resid;      // (rows, N) or null
-  bf16* out;              // (rows, N)
+  const bf16* resid;      // (rows, N) or null (fp32 if resid_fp32)
+  bf16* out;              // (rows, N) (fp32 if out_fp32)
+  int resid_fp32, out_fp32;
   int TW, TH;             // PROD 0 tile shape (TW*TH == 128)
   int tiles_x;
   long long* trace;       // profiling aid (LW_DEBUG & 16)

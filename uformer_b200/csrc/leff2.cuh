@@ -287,7 +287,9 @@ __global__ void __launch_bounds__(kL2Threads, 1) leff2_kernel(const AStreamArgs 
           mbar_arrive(smem_u32(&ms.bar_d_empty[buf]));
         }
         l2_epi_bar();
-        store_staged_rows128(stage_s, pitch, sub_log2, ms.row_tok, a.out, a.resid, (size_t)a.N, sc, et);
+        if (a.resid_fp32 | a.out_fp32) store_staged_rows_mixed<128>(stage_s, pitch, sub_log2, smem_u32(ms.row_tok), a.out, a.resid, nullptr, a.resid_fp32 != 0,
+                                                                    a.out_fp32 != 0, (size_t)a.N, sc, et);
+        else store_staged_rows128(stage_s, pitch, sub_log2, ms.row_tok, a.out, a.resid, (size_t)a.N, sc, et);
         l2_epi_bar();
       }
     }

@@ -36,13 +36,26 @@ static bool all_aligned16(P... ps) {
   return ok;
 }
 
-extern "C" int lw_abi_version(void) { return 2; }
+extern "C" int lw_abi_version(void) { return 3; }
 extern "C" const char* lw_last_cuda_error(void) { return g_err; }
 extern "C" int lw_check_device(void) {
   int dev = 0, major = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return LW_ERR_ARCH;
   if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return LW_ERR_ARCH;
   return major == 10 ? LW_OK : LW_ERR_ARCH;
+}
+
+extern "C" int lw_struct_size(int id) {
+  switch (id) {
+    case 0: return (int)sizeof(lw_wmsa_args);
+    case 1: return (int)sizeof(lw_leff1_args);
+    case 2: return (int)sizeof(lw_leff2_args);
+    case 3: return (int)sizeof(lw_leff_args);
+    case 4: return (int)sizeof(lw_down_args);
+    case 5: return (int)sizeof(lw_up_args);
+    case 6: return (int)sizeof(lw_adamw_args);
+    default: return -1;
+  }
 }
 
 static int debug_flags() {
@@ -97,7 +110,7 @@ extern "C" int lw_wmsa_fwd(const lw_wmsa_args* a, lw_stream_t stream) {
     return LW_ERR_BAD_SHAPE;
   }
   if (a->mask && a->n_mask_windows <= 0) return LW_ERR_BAD_SHAPE;
-  if (!all_aligned16(a->x, a->out, a->resid, a->ln_w, a->ln_b, a->modulator, a->wqkv_img, a->wproj_img, a->bproj)) return LW_ERR_ALIGN;
+  if (!all_aligned16(a->x, a->out, a->out_b, a->resid, a->ln_w, a->ln_b, a->modulator, a->wqkv_img, a->wproj_img, a->bproj)) return LW_ERR_ALIGN;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   lw_wmsa_args aa = *a;
   aa.dbg = debug_flags();
@@ -179,6 +192,7 @@ extern "C" int lw_leff2_fwd(const lw_leff2_args* p, lw_stream_t stream) {
   a.wd = p->wd; a.bd = p->bd; a.w_img = reinterpret_cast<const uint8_t*>(p->w2_img);
   a.N = p->C; a.nch = p->C < 128 ? p->C : 128; a.bias = p->b2;
   a.resid = reinterpret_cast<const bf16*>(p->resid); a.out = reinterpret_cast<bf16*>(p->out);
+  a.resid_fp32 = p->resid_fp32; a.out_fp32 = p->out_fp32;
   if (p->H % 8) return LW_ERR_BAD_SHAPE;
   a.dbg = debug_flags();
   if (a.dbg & 16) {

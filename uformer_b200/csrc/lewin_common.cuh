@@ -320,6 +320,78 @@ __device__ __forceinline__ void store_staged_rows_t(uint32_t stage_s, int pitch,
       if (tok[k] >= 0) *reinterpret_cast<uint4*>(out + g[k]) = v[k];
   }
 }
+// Mixed-precision copy-out (fp32 residual-stream mode): residual bf16 or fp32, output bf16 or fp32, optional bf16 copy of
+// the result (the GEMM operand of the kernel that follows).  The branch is rounded to bf16 in the staging tile, the
+// residual sum is formed in fp32.  NT cooperating threads; same row_tok convention as store_staged_rows_t.
+template <int NT, bool RF32>
+__device__ __forceinline__ void store_staged_rows_mixed_t(uint32_t stage_s, int pitch, int ncols_log2, uint32_t row_tok_s, void* __restrict__ out,
+                                                          const void* __restrict__ resid, bf16* __restrict__ out_b, bool out_fp32,
+                                                          size_t row_stride, int col0, int tid) {
+  const int vshift = ncols_log2 - 3;
+  const int total = 128 << vshift;
+  constexpr int ITER = 4;                       // vectors in flight per thread: all loads of a pass are issued before any use
+#pragma unroll 1
+  for (int i0 = tid; i0 < total; i0 += NT * ITER) {
+    int tok[ITER];
+    size_t g[ITER];
+    uint4 sv[ITER], r0[ITER], r1[RF32 ? ITER : 1];
+#pragma unroll
+    for (int k = 0; k < ITER; ++k) {
+      const int i = i0 + k * NT;
+      const bool in = i < total;
+      const int row = (in ? i : 0) >> vshift, vec = (in ? i : 0) & ((1 << vshift) - 1);
+      int t;
+      asm volatile("ld.shared.s32 %0, [%1];" : "=r"(t) : "r"(row_tok_s + row * 4));
+      tok[k] = in ? t : -1;
+      sv[k] = lds128(stage_s + row * pitch + vec * 16);
+      g[k] = (size_t)(tok[k] < 0 ? 0 : tok[k]) * row_stride + col0 + vec * 8;
+    }
+    if (resid != nullptr) {
+#pragma unroll
+      for (int k = 0; k < ITER; ++k) {
+        if (RF32) {
+          r0[k] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(resid) + g[k]));
+          r1[RF32 ? k : 0] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(resid) + g[k] + 4));
+        } else {
+          r0[k] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(resid) + g[k]));
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < ITER; ++k) {
+      if (tok[k] < 0) continue;
+      float f[8];
+      unpack8(sv[k], f);
+      if (resid != nullptr) {
+        if (RF32) {
+          const uint4 a = r0[k], b = r1[RF32 ? k : 0];
+          f[0] += __uint_as_float(a.x); f[1] += __uint_as_float(a.y); f[2] += __uint_as_float(a.z); f[3] += __uint_as_float(a.w);
+          f[4] += __uint_as_float(b.x); f[5] += __uint_as_float(b.y); f[6] += __uint_as_float(b.z); f[7] += __uint_as_float(b.w);
+        } else {
+          float r[8];
+          unpack8(r0[k], r);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] += r[e];
+        }
+      }
+      if (out_fp32) {
+        float* op = reinterpret_cast<float*>(out) + g[k];
+        *reinterpret_cast<float4*>(op) = make_float4(f[0], f[1], f[2], f[3]);
+        *reinterpret_cast<float4*>(op + 4) = make_float4(f[4], f[5], f[6], f[7]);
+      } else {
+        *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(out) + g[k]) = pack8(f);
+      }
+      if (out_b != nullptr) *reinterpret_cast<uint4*>(out_b + g[k]) = pack8(f);
+    }
+  }
+}
+template <int NT>
+__device__ __forceinline__ void store_staged_rows_mixed(uint32_t stage_s, int pitch, int ncols_log2, uint32_t row_tok_s, void* __restrict__ out,
+                                                        const void* __restrict__ resid, bf16* __restrict__ out_b, bool resid_fp32,
+                                                        bool out_fp32, size_t row_stride, int col0, int tid) {
+  if (resid_fp32) store_staged_rows_mixed_t<NT, true>(stage_s, pitch, ncols_log2, row_tok_s, out, resid, out_b, out_fp32, row_stride, col0, tid);
+  else store_staged_rows_mixed_t<NT, false>(stage_s, pitch, ncols_log2, row_tok_s, out, resid, out_b, out_fp32, row_stride, col0, tid);
+}
 // 128-thread variant (dedicated epilogue warps of the persistent kernels)
 __device__ __forceinline__ void store_staged_rows128(uint32_t stage_s, int pitch, int ncols_log2, const int* row_tok,
                                                      bf16* __restrict__ out, const bf16* __restrict__ resid,
@@ -353,8 +425,8 @@ __device__ __forceinline__ void store_staged_rows(uint32_t stage_s, int pitch, i
 // tile row r (-1: row is padding -> zeros).  Executed by the 4 worker warps; warp w stages rows
 // [32w, 32w+32).  Lanes run along channels, so global reads are coalesced 16 B vectors.
 // ----------------------------------------------------------------------------------------------
-template <int C, int NW = 4>
-__device__ __forceinline__ void stage_rows_ln(uint8_t* sX, const bf16* __restrict__ x,
+template <int C, int NW = 4, bool X32 = false>
+__device__ __forceinline__ void stage_rows_ln(uint8_t* sX, const void* __restrict__ xv,
                                               const int* row_tok, const float* __restrict__ ln_w,
                                               const float* __restrict__ ln_b, float eps,
                                               const float* __restrict__ addtab /* [64][C] or null */) {
@@ -368,9 +440,12 @@ __device__ __forceinline__ void stage_rows_ln(uint8_t* sX, const bf16* __restric
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sub = lane % LPT;
   const uint32_t sX_s = smem_u32(sX);
+  const bf16* __restrict__ x = reinterpret_cast<const bf16*>(xv);
+  const float* __restrict__ x32 = reinterpret_cast<const float*>(xv);     // X32: the fp32 residual stream is the input
   for (int p0 = 0; p0 < PASSES; p0 += BATCH) {
     // ---- issue every global load of the batch before touching any (memory-level parallelism) ----
     uint4 raw[BATCH][VPL];
+    uint4 raw2[X32 ? BATCH : 1][X32 ? VPL : 1];
     int toks[BATCH];
 #pragma unroll
     for (int b = 0; b < BATCH; ++b) {
@@ -379,7 +454,12 @@ __device__ __forceinline__ void stage_rows_ln(uint8_t* sX, const bf16* __restric
 #pragma unroll
       for (int j = 0; j < VPL; ++j) {
         const int c0 = j * 256 + sub * 8;
-        raw[b][j] = (toks[b] >= 0) ? __ldg(reinterpret_cast<const uint4*>(x + (size_t)toks[b] * C + c0)) : make_uint4(0, 0, 0, 0);
+        if (X32) {
+          raw[b][j] = (toks[b] >= 0) ? __ldg(reinterpret_cast<const uint4*>(x32 + (size_t)toks[b] * C + c0)) : make_uint4(0, 0, 0, 0);
+          raw2[X32 ? b : 0][X32 ? j : 0] = (toks[b] >= 0) ? __ldg(reinterpret_cast<const uint4*>(x32 + (size_t)toks[b] * C + c0 + 4)) : make_uint4(0, 0, 0, 0);
+        } else {
+          raw[b][j] = (toks[b] >= 0) ? __ldg(reinterpret_cast<const uint4*>(x + (size_t)toks[b] * C + c0)) : make_uint4(0, 0, 0, 0);
+        }
       }
     }
 #pragma unroll
@@ -387,7 +467,15 @@ __device__ __forceinline__ void stage_rows_ln(uint8_t* sX, const bf16* __restric
       const int r = warp * RPW + (p0 + b) * TPP + lane / LPT;
       float v[VPL][8];
 #pragma unroll
-      for (int j = 0; j < VPL; ++j) unpack8(raw[b][j], v[j]);
+      for (int j = 0; j < VPL; ++j) {
+        if (X32) {
+          const uint4 lo = raw[b][j], hi = raw2[X32 ? b : 0][X32 ? j : 0];
+          v[j][0] = __uint_as_float(lo.x); v[j][1] = __uint_as_float(lo.y); v[j][2] = __uint_as_float(lo.z); v[j][3] = __uint_as_float(lo.w);
+          v[j][4] = __uint_as_float(hi.x); v[j][5] = __uint_as_float(hi.y); v[j][6] = __uint_as_float(hi.z); v[j][7] = __uint_as_float(hi.w);
+        } else {
+          unpack8(raw[b][j], v[j]);
+        }
+      }
       if (ln_w != nullptr) {
         float s = 0.f;
 #pragma unroll

@@ -234,7 +234,8 @@ __global__ void __launch_bounds__(kThreads8, (C <= 128) ? 2 : 1) wmsa_kernel(con
     worker_bar8();
     if (tid < 128 && a.shift > 0 && !a.windowed && ms.region[tid] != ms.region[(tid >> 6) * 64]) ms.win_mixed[tid >> 6] = 1;
     // ---- A operand: LN(x) + modulator ----
-    stage_rows_ln<C, 8>(smem + Cfg::S_X, xin, ms.row_tok, a.ln_w, a.ln_b, a.ln_eps, a.modulator);
+    if (a.x_fp32) stage_rows_ln<C, 8, true>(smem + Cfg::S_X, a.x, ms.row_tok, a.ln_w, a.ln_b, a.ln_eps, a.modulator);
+    else stage_rows_ln<C, 8, false>(smem + Cfg::S_X, xin, ms.row_tok, a.ln_w, a.ln_b, a.ln_eps, a.modulator);
     fence_async_smem();
     mbar_arrive(smem_u32(&ms.bar_xn));
 
@@ -395,6 +396,7 @@ __global__ void __launch_bounds__(kThreads8, (C <= 128) ? 2 : 1) wmsa_kernel(con
     // coalesced scatter to the (un-rolled) token positions with the shortcut added on the way ----
     bf16* __restrict__ outp = reinterpret_cast<bf16*>(a.out);
     const bf16* __restrict__ resid = reinterpret_cast<const bf16*>(a.resid);
+    const bool mixed = (a.x_fp32 | a.out_fp32) != 0 || a.out_b != nullptr;        // fp32 residual-stream mode
     constexpr int PITCH = Cfg::NCH * 2 + 16;
     static_assert(128 * PITCH <= Cfg::S_RING, "staging tile must fit in the dead A/QKV region");
     constexpr int NCH_LOG2 = Cfg::NCH == 128 ? 7 : Cfg::NCH == 64 ? 6 : Cfg::NCH == 32 ? 5 : 4;
@@ -423,7 +425,9 @@ __global__ void __launch_bounds__(kThreads8, (C <= 128) ? 2 : 1) wmsa_kernel(con
       tc_fence_before();
       mbar_arrive(smem_u32(&ms.bar_d_empty[buf]));
       worker_bar8();
-      store_staged_rows(stage_s, PITCH, NCH_LOG2, ms.row_tok, outp, resid, (size_t)C, nc * Cfg::NCH, tid, kWorkers8);
+      if (mixed) store_staged_rows_mixed<kWorkers8>(stage_s, PITCH, NCH_LOG2, smem_u32(ms.row_tok), a.out, a.resid, reinterpret_cast<bf16*>(a.out_b), a.x_fp32 != 0,
+                                                     a.out_fp32 != 0, (size_t)C, nc * Cfg::NCH, tid);
+      else store_staged_rows(stage_s, PITCH, NCH_LOG2, ms.row_tok, outp, resid, (size_t)C, nc * Cfg::NCH, tid, kWorkers8);
       worker_bar8();
       LW_TRACE_STMT(if (trw) a.trace[tw++] = clock64();)
     }

@@ -368,7 +368,7 @@ class LeWinTransformerBlock(nn.Module):
         self.norm2 = norm_layer(dim)
         self.mlp = LeFF(dim, int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
         self._cache = _PackCache()
-        self.residual_fp32 = False          # see set_residual_precision()
+        self.residual_fp32 = default_residual_fp32()      # see set_residual_precision()
 
     def extra_repr(self) -> str:
         return (f"dim={self.dim}, input_resolution={self.input_resolution}, num_heads={self.num_heads}, "
@@ -393,8 +393,9 @@ class LeWinTransformerBlock(nn.Module):
         am = m.unsqueeze(2) * m.unsqueeze(1)
         return torch.where(am != 0, torch.full_like(am, -100.0), torch.zeros_like(am))
 
-    def forward(self, x, mask=None, out=None):
-        """`out` (optional, bf16, same shape as x): write the block output there (used by the stage scheduler)."""
+    def forward(self, x, mask=None, out=None, out_dtype=None):
+        """`out` (optional, bf16, same shape as x): write the block output there (used by the stage scheduler).
+        `out_dtype` (fp32 residual-stream mode only): dtype of the returned tensor (fp32 inside a stage, bf16 at its end)."""
         B, L, C = x.shape
         H = W = int(math.sqrt(L))
         if H * W != L or H % 8 or self.win_size != 8:
@@ -408,8 +409,9 @@ class LeWinTransformerBlock(nn.Module):
             raise RuntimeError(f"input mask with a shifted block needs batch 1 (got {B}): the reference's mask sum at "
                                "model.py:942 does not broadcast (B*nW,N,N) + (nW,N,N)")
         _lib.require_device(x.device)
-        if self.residual_fp32 and mask is None and not (self.training and torch.is_grad_enabled()):
-            return self._forward_fp32_residual(x, B, H, W)
+        stochastic = self.training and isinstance(self.drop_path, DropPath) and self.drop_path.drop_prob > 0.0
+        if self.residual_fp32 and not stochastic and not (torch.is_grad_enabled() and autograd.wants_grad(x, *autograd.trainable_tensors(self))):
+            return self._forward_fp32_residual(x, B, H, W, mask, out, out_dtype)      # inference (nothing to differentiate)
         xb, back = _as_bf16(x)
         # stochastic depth (model.py:986-987): the two per-sample factors, drawn in the reference's order
         dp = self.drop_path if isinstance(self.drop_path, DropPath) else None
@@ -454,31 +456,51 @@ class LeWinTransformerBlock(nn.Module):
         return res if back is None else res.to(back)
 
     @torch.no_grad()
-    def _forward_fp32_residual(self, x, B, H, W):
-        """Precision mode (set_residual_precision): the residual stream x -> x1 -> out stays fp32 in HBM; only the two
-        branch inputs are rounded to bf16 (the kernels' operand type).  Same kernels with resid=NULL plus four
-        element-wise passes per block; removes the 80 bf16 roundings of the residual stream that dominate the flagship
-        model's parity error.  Inference only; returns fp32."""
+    def _forward_fp32_residual(self, x, B, H, W, mask=None, out=None, out_dtype=None):
+        """Precision mode (set_residual_precision): the residual stream x -> x1 -> out stays fp32 in HBM, inside the kernels:
+        W-MSA reads the fp32 stream (LayerNorm in fp32, bf16 GEMM operand), adds its branch in fp32 and writes x1 in fp32 plus
+        a bf16 copy (the LeFF kernel's GEMM operand); LeFF adds its branch to the fp32 x1 and writes fp32 (bf16 at the end of
+        a stage).  Removes the 80 bf16 roundings of the residual stream that dominate the flagship model's parity error
+        (DESIGN §2).  Inference only; `x` may be bf16 (first block of a stage) or fp32."""
         pk = self.packed()
         pa = dict(self.attn.packed(), ln_w=pk["ln1_w"], ln_b=pk["ln1_b"], modulator=pk["modulator"], ln_eps=self.norm1.eps)
         pm = self.mlp.packed(self.norm2)
-        xb = x.contiguous() if x.dtype == torch.bfloat16 else x.to(torch.bfloat16).contiguous()
-        a = ops.wmsa(xb, pa, H=H, W=W, shift=self.shift_size, windowed=False, resid=None)
-        x1 = torch.add(x if x.dtype == torch.float32 else x.float(), a)          # fp32 + bf16 -> fp32, one pass
-        x1b = x1.to(torch.bfloat16)
-        if self.mlp.fused():                                                      # residual read and output written in fp32 by the kernel
-            return ops.leff(x1b, pm, B=B, H=H, W=W, resid=x1, out_dtype=torch.float32)
-        return torch.add(x1, ops.leff(x1b, pm, B=B, H=H, W=W, resid=None))
+        if x.dtype not in (torch.bfloat16, torch.float32):
+            x = x.float()
+        x = x.contiguous()
+        amask = None if mask is None else self.input_mask_to_attn_mask(mask, H, W, 8)
+        x1, x1b = ops.wmsa(x, pa, H=H, W=W, shift=self.shift_size, windowed=False, resid=x, mask=amask, out_dtype=torch.float32, bf16_copy=True)
+        odt = out.dtype if out is not None else (out_dtype or torch.float32)
+        if out is not None and not self.mlp.fused() and not out.is_contiguous():
+            return out.copy_(ops.leff(x1b, pm, B=B, H=H, W=W, resid=x1, out_dtype=odt))
+        return ops.leff(x1b, pm, B=B, H=H, W=W, resid=x1, out=out, out_dtype=odt)
 
     def flops(self):
         H, W = self.input_resolution
         return self.dim * H * W + self.attn.flops(H, W) + self.dim * H * W + self.mlp.flops(H, W)
 
 
+def residual_mode() -> str:
+    """UFORMER_B200_RESIDUAL: "auto" (default), "fp32" or "bf16" — precision of the residual stream between the kernels of a
+    stage at inference.  bf16 rounds the residual twice per block (it costs the 40-block flagship ~4e-3 of parity error,
+    DESIGN §2); fp32 keeps it in fp32 in HBM (more bytes per token); auto = fp32 in stages of >= 4 blocks (where the roundings
+    accumulate and the kernels are compute-bound), bf16 in the 1-2-block full-resolution stages (which are HBM-bound)."""
+    m = os.environ.get("UFORMER_B200_RESIDUAL", "auto")
+    if m not in ("auto", "fp32", "bf16"):
+        raise ValueError(f"UFORMER_B200_RESIDUAL={m!r}: expected auto, fp32 or bf16")
+    return m
+
+
+def default_residual_fp32(depth=None) -> bool:
+    """Whether a block constructed now (inside a stage of `depth` blocks; None: standalone) carries an fp32 residual stream."""
+    m = residual_mode()
+    return m == "fp32" or (m == "auto" and (depth is None or depth >= 4))
+
+
 def set_residual_precision(net: nn.Module, dtype=torch.float32):
-    """Select how LeWin blocks under `net` carry the residual stream between kernels at inference: torch.bfloat16 (default,
-    fastest: the residual add is fused into the kernels' epilogues) or torch.float32 (precision mode, see
-    LeWinTransformerBlock._forward_fp32_residual).  Returns the number of blocks switched."""
+    """Select how LeWin blocks under `net` carry the residual stream between kernels at inference: torch.float32 (default:
+    fp32 in HBM inside each stage, read / written by the kernels themselves, see LeWinTransformerBlock._forward_fp32_residual)
+    or torch.bfloat16 (faster, noisier).  Returns the number of blocks switched."""
     if dtype not in (torch.float32, torch.bfloat16):
         raise ValueError("residual precision must be torch.float32 or torch.bfloat16")
     n = 0

@@ -16,7 +16,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, autograd, ops, restated
-from .modules import Downsample, LeWinTransformerBlock, Upsample, _run
+from .modules import Downsample, LeWinTransformerBlock, Upsample, _run, default_residual_fp32
 
 _STAGE_NAMES = ["encoderlayer_0", "encoderlayer_1", "encoderlayer_2", "encoderlayer_3", "conv",
                 "decoderlayer_0", "decoderlayer_1", "decoderlayer_2", "decoderlayer_3"]
@@ -38,6 +38,8 @@ class LeWinStage(nn.Module):
                                   norm_layer=norm_layer, token_projection=token_projection, token_mlp=token_mlp,
                                   modulator=modulator, cross_modulator=cross_modulator)
             for i in range(depth)])
+        for blk in self.blocks:                               # residual-stream precision policy of this stage (modules.residual_mode)
+            blk.residual_fp32 = default_residual_fp32(depth)
 
     def extra_repr(self):
         return f"dim={self.dim}, input_resolution={self.input_resolution}, depth={self.depth}"
@@ -46,14 +48,22 @@ class LeWinStage(nn.Module):
         """Runs the blocks of this stage (model.py:1054-1060).  `out` (inference only): a bf16 destination for the LAST
         block's output — a column slice of the skip-concat buffer, so the encoder skip is produced in place
         (model.py:1288-1300) — honoured when that block's fused LeFF can write strided rows; otherwise the result is copied."""
-        if out is None or len(self.blocks) == 0:
+        n = len(self.blocks)
+        infer = not autograd.wants_grad(x, *autograd.trainable_tensors(self))
+        if n and infer and self.blocks[0].residual_fp32:
+            # fp32 residual-stream mode: bf16 in, fp32 between the blocks of the stage, bf16 out (set_residual_precision)
+            for i, blk in enumerate(self.blocks):
+                last = i == n - 1
+                x = blk(x, mask, out=out if last else None, out_dtype=torch.bfloat16 if last else torch.float32)
+            return x
+        if out is None or n == 0:
             for blk in self.blocks:
                 x = blk(x, mask)
             return x if out is None else out.copy_(x)
         for blk in self.blocks[:-1]:
             x = blk(x, mask)
         last = self.blocks[-1]
-        if x.dtype == torch.bfloat16 and last.mlp.fused() and not last.residual_fp32 and not autograd.wants_grad(x, *autograd.trainable_tensors(self)):
+        if x.dtype == torch.bfloat16 and last.mlp.fused() and infer:
             return last(x, mask, out=out)
         return out.copy_(last(x, mask))
 

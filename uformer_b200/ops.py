@@ -52,17 +52,27 @@ def _check_act(x: Tensor, name: str):
 
 
 def wmsa(x: Tensor, p: dict, *, H: int, W: int, shift: int, windowed: bool, resid: Tensor | None,
-         mask: Tensor | None = None, out: Tensor | None = None) -> Tensor:
+         mask: Tensor | None = None, out: Tensor | None = None, out_dtype=None, bf16_copy: bool = False):
     """Fused (LN) + (roll/partition) + W-MSA + proj + (reverse/unroll) + (residual).
-    p: packed parameter dict from modules._pack_attention (+ optional ln_w/ln_b/modulator)."""
-    _check_act(x, "x")
+    p: packed parameter dict from modules._pack_attention (+ optional ln_w/ln_b/modulator).
+    fp32 residual-stream mode: x (and resid, which must then be x's dtype) may be fp32; out_dtype=torch.float32 writes the
+    sum in fp32; bf16_copy=True additionally returns a bf16 copy of the output (the GEMM operand of the LeFF kernel that
+    follows): the return value is then the pair (out, out_bf16)."""
+    if x.dtype not in (torch.bfloat16, torch.float32):
+        raise TypeError(f"x must be bfloat16 or float32 (got {x.dtype})")
+    if not x.is_contiguous():
+        raise ValueError("x must be contiguous")
+    if resid is not None and resid.dtype != x.dtype:
+        raise TypeError("resid must have x's dtype")
+    _lib.require_device(x.device)
     Cc = x.shape[-1]
     if windowed:
         n_windows = x.shape[0]
     else:
         n_windows = x.shape[0] * (H // 8) * (W // 8)
     if out is None:
-        out = torch.empty_like(x)
+        out = torch.empty(x.shape, dtype=out_dtype or torch.bfloat16, device=x.device)
+    out_b = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device) if bf16_copy else None
     a = _lib.WmsaArgs()
     a.x, a.out, a.resid = _ptr(x), _ptr(out), _ptr(resid)
     a.ln_w, a.ln_b, a.modulator = _ptr(p.get("ln_w")), _ptr(p.get("ln_b")), _ptr(p.get("modulator"))
@@ -73,9 +83,10 @@ def wmsa(x: Tensor, p: dict, *, H: int, W: int, shift: int, windowed: bool, resi
         a.mask, a.n_mask_windows = _ptr(mask), mask.shape[0]
     a.n_windows, a.H, a.W, a.C, a.head_dim = n_windows, H, W, Cc, p["head_dim"]
     a.shift, a.windowed, a.ln_eps = shift, int(windowed), p.get("ln_eps", 1e-5)
+    a.x_fp32, a.out_fp32, a.out_b = int(x.dtype == torch.float32), int(out.dtype == torch.float32), _ptr(out_b)
     ntok = n_windows * 64
     _launch(f"wmsa_C{Cc}_T{ntok}", 2.0 * ntok * (4 * Cc * Cc + 128 * Cc), lambda st: _lib.load().lw_wmsa_fwd(C.byref(a), st), "lw_wmsa_fwd", x.device)
-    return out
+    return (out, out_b) if bf16_copy else out
 
 
 def _row_stride(t: Tensor, name: str) -> int:
@@ -91,7 +102,7 @@ def leff(x: Tensor, p: dict, *, B: int, H: int, W: int, resid: Tensor | None, ou
     may be column slices of wider buffers, resid / out may be fp32.  Otherwise (C = 512) the two-kernel path: the hidden
     map makes one bf16 round trip through HBM/L2 between lw_leff1_fwd and lw_leff2_fwd."""
     if "w1f_img" not in p:
-        return _leff_two_kernels(x, p, B=B, H=H, W=W, resid=resid, out=out)
+        return _leff_two_kernels(x, p, B=B, H=H, W=W, resid=resid, out=out, out_dtype=out_dtype)
     if x.dtype != torch.bfloat16:
         raise TypeError(f"x must be bfloat16 (got {x.dtype})")
     _lib.require_device(x.device)
@@ -117,7 +128,7 @@ def leff(x: Tensor, p: dict, *, B: int, H: int, W: int, resid: Tensor | None, ou
     return out
 
 
-def _leff_two_kernels(x: Tensor, p: dict, *, B: int, H: int, W: int, resid: Tensor | None, out: Tensor | None = None) -> Tensor:
+def _leff_two_kernels(x: Tensor, p: dict, *, B: int, H: int, W: int, resid: Tensor | None, out: Tensor | None = None, out_dtype=None) -> Tensor:
     _check_act(x, "x")
     Cc, hidden = x.shape[-1], p["hidden"]
     n_tokens = B * H * W
@@ -129,9 +140,12 @@ def _leff_two_kernels(x: Tensor, p: dict, *, B: int, H: int, W: int, resid: Tens
     lib = _lib.load()
     _launch(f"leff1_C{Cc}_T{n_tokens}", 2.0 * n_tokens * Cc * hidden, lambda st: lib.lw_leff1_fwd(C.byref(a), st), "lw_leff1_fwd", x.device)
     if out is None:
-        out = torch.empty_like(x)
+        out = torch.empty(x.shape, dtype=out_dtype or torch.bfloat16, device=x.device)
+    if not out.is_contiguous() or (resid is not None and not resid.is_contiguous()):
+        raise ValueError("two-kernel LeFF: out / resid must be contiguous")
     b = _lib.Leff2Args()
     b.h1, b.out, b.resid = _ptr(h1), _ptr(out), _ptr(resid)
+    b.resid_fp32, b.out_fp32 = int(resid is not None and resid.dtype == torch.float32), int(out.dtype == torch.float32)
     b.wd, b.bd, b.w2_img, b.b2 = _ptr(p["wd"]), _ptr(p["bd"]), _ptr(p["w2_img"]), _ptr(p["b2"])
     b.B, b.H, b.W, b.C, b.hidden = B, H, W, Cc, hidden
     _launch(f"leff2_C{Cc}_T{n_tokens}", 2.0 * n_tokens * (hidden * Cc + 9 * hidden), lambda st: lib.lw_leff2_fwd(C.byref(b), st), "lw_leff2_fwd", x.device)
