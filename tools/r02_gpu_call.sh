@@ -1,7 +1,12 @@
 mkdir -p gpurun_out
-timeout 400 python -m pytest tests -m gpu -q -s -p no:cacheprovider > gpurun_out/r02n_gpu_tests.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/r02n_gpu_tests.log
-grep -E "rel_l2|residual stream|auto" gpurun_out/r02n_gpu_tests.log | grep -E "uformer_b_256:|uformer_b_256 |residual stream|auto|uformer_s2" | head -20
-for r in auto fp32 bf16; do
-timeout 200 python bench.py --steps 10 --no-cpu-baseline --residual $r > gpurun_out/r02n_bench_$r.json 2> gpurun_out/r02n_bench_$r.err; echo "bench $r rc=$?"; python -c "
-import json; d=json.load(open('gpurun_out/r02n_bench_$r.json')); print(d['value'], d['e2e']['value'], d['gpu_launches'])"
-done
+timeout 600 python tools/leff_fused_probe.py > gpurun_out/r02o_leff_probe.log 2>&1; echo "probe rc=$?"
+python - <<'PY'
+import json
+for ln in open('gpurun_out/r02o_leff_probe.log'):
+    if ln.startswith('RESULT'):
+        d=json.loads(ln[7:]); print({k:(round(v,4) if isinstance(v,float) else v) for k,v in d.items() if k in ('C','H','B','rel_l2_vs_oracle','fused_us','split_us','strided_out_equal')})
+    else: print(ln.strip()[:300])
+PY
+timeout 120 python tools/leff_fused_trace.py 128 128 8 > gpurun_out/r02o_trace_c128.log 2>&1; echo "trace rc=$?"
+timeout 200 python bench.py --steps 10 --no-cpu-baseline > gpurun_out/r02o_bench.json 2> gpurun_out/r02o_bench.err; echo "bench rc=$?"; python -c "
+import json; d=json.load(open('gpurun_out/r02o_bench.json')); print(d['value'], d['e2e']['value'], d['roofline']['by_kernel_ms'])"

@@ -317,109 +317,17 @@ __global__ void __launch_bounds__(kLFThreads, 1) leff_fused_kernel(const __grid_
     // (warps 14, 15 are spares: the LayerNorm statistics are computed by the epilogue warps, see below)
   } else if (wg == 2 || wg == 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
-    // ============================== E1 / E2: two epilogue groups (warps 8-11 and 16-19), TMEM lane quadrant q ==============================
-    // E1: each group takes half of the 32-column pieces of a hidden slice.  E2: each group drains half of the output columns
-    // through its own staging tile (C >= 64; narrower outputs are drained by group 0 alone).
+    // ============================== E1: two epilogue groups (warps 8-11 and 16-19), TMEM lane quadrant q ==============================
+    // Each group takes half of the 32-column pieces of a hidden slice (and, at a tile's first slice, a share of the
+    // LayerNorm statistics).  The output epilogue E2 runs on the conv warps, which have the slack.
     const int grp = (wg == 4) ? 1 : 0;
     const int q = warp & 3, et = tid & 127;
     const int t4 = lane >> 2, tq = lane & 3;
     const int m = lane >> 3, rr = lane & 7;
-    const uint32_t halo0 = smem_u32(smem + Cfg::S_HALO), stage_s = smem_u32(smem + Cfg::S_STAGE) + grp * (128 * Cfg::STAGE_PITCH);
-    const uint32_t b1_s = smem_u32(smem + Cfg::S_B1), b2_s = smem_u32(smem + Cfg::S_B2), stats_s = smem_u32(smem + Cfg::S_STATS);
-    auto grp_bar = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory"); };
-    constexpr bool SPLIT_E2 = (C >= 64);
-    constexpr int E2_COLS = SPLIT_E2 ? C / 2 : C;             // output columns this group drains
-    constexpr int E2_PASS = (E2_COLS >= 32) ? 32 : 16;        // columns per staging pass
-    constexpr int VPR = E2_PASS / 8;                          // 16-byte vectors per staged row
-    constexpr int VPT = VPR;                                  // vectors per thread per pass (128 rows x VPR vectors / 128 threads)
-    int* row_out = ms.row_out + grp * 128;
+    const uint32_t halo0 = smem_u32(smem + Cfg::S_HALO);
+    const uint32_t b1_s = smem_u32(smem + Cfg::S_B1), stats_s = smem_u32(smem + Cfg::S_STATS);
     GeluH2 gelu;
     gelu.init();
-
-    auto epilogue2 = [&](int it) {
-      if (!SPLIT_E2 && grp == 1) return;
-      const int ob = it % Cfg::ND2;
-      const int tile = tile_of(it);
-      if (grp == 0 && et == 0) { LF_TRACE(6, 3 * it) }
-      {
-        const int tx = tile % a.tiles_x, ty = (tile / a.tiles_x) % a.tiles_y, b = tile / (a.tiles_x * a.tiles_y);
-        const int y = ty * 8 + (et >> 4), x = tx * 16 + (et & 15);
-        row_out[et] = (x < a.W) ? ((b * a.H + y) * a.W + x) : -1;
-      }
-      grp_bar();
-      // this thread copies out vectors i = et + p*128 of every pass: row i / VPR, vector i % VPR (fixed over the passes)
-      int tok[VPT];
-#pragma unroll
-      for (int p2 = 0; p2 < VPT; ++p2) tok[p2] = row_out[(et + p2 * 128) / VPR];
-      mbar_wait(smem_u32(&ms.bar_d2_full[ob]), (it / Cfg::ND2) & 1);
-      tc_fence_after();
-      if (grp == 0 && et == 0) { LF_TRACE(6, 3 * it + 1) }
-      const int cbase = grp * (SPLIT_E2 ? C / 2 : 0);
-#pragma unroll 1
-      for (int sc = 0; sc < E2_COLS; sc += E2_PASS) {
-        // residual vectors of this pass: issued first so that their (L2) latency hides under the TMEM read + staging below
-        uint4 rv[VPT][2];
-        if (a.resid != nullptr) {
-#pragma unroll
-          for (int p2 = 0; p2 < VPT; ++p2) {
-            const int c = cbase + sc + ((et + p2 * 128) % VPR) * 8;
-            const size_t off = (size_t)(tok[p2] < 0 ? 0 : tok[p2]) * a.resid_stride + c;
-            if (a.resid_fp32) {
-              rv[p2][0] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(a.resid) + off));
-              rv[p2][1] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(a.resid) + off + 4));
-            } else {
-              rv[p2][0] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(a.resid) + off));
-            }
-          }
-        }
-        constexpr int NB = E2_PASS / 8;
-#pragma unroll
-        for (int hl = 0; hl < 2; ++hl) {
-          const int row16 = q * 32 + hl * 16;
-          uint32_t v[4 * NB];
-          const uint32_t ta = tb + ((uint32_t)row16 << 16) + Cfg::T_D2 + ob * C + cbase + sc;
-          if (NB == 4) tmem_ld_16x256b_x4(ta, v); else tmem_ld_16x256b_x2(ta, v);
-          f2 bb[NB];
-#pragma unroll
-          for (int i = 0; i < NB; ++i) { const float2 b2 = lds64f(b2_s + (cbase + sc + 8 * i + 2 * tq) * 4); bb[i] = f2_pack(b2.x, b2.y); }
-          tmem_wait_ld();
-          uint32_t pk[2 * NB];
-          frag_bias_act_pack<NB, false>(v, bb, pk);
-          stage_frag<NB>(stage_s, Cfg::STAGE_PITCH, row16, 0, pk);
-        }
-        if (sc + E2_PASS >= E2_COLS) { tc_fence_before(); mbar_arrive(smem_u32(&ms.bar_d2_empty[ob])); }
-        grp_bar();
-#pragma unroll
-        for (int p2 = 0; p2 < VPT; ++p2) {
-          if (tok[p2] < 0) continue;
-          const int i = et + p2 * 128;
-          const int row = i / VPR, vec = i % VPR;
-          float f[8];
-          unpack8(lds128(stage_s + row * Cfg::STAGE_PITCH + vec * 16), f);
-          const int c = cbase + sc + vec * 8;
-          if (a.resid != nullptr) {
-            if (a.resid_fp32) {
-              const float4 r0 = *reinterpret_cast<const float4*>(&rv[p2][0]), r1 = *reinterpret_cast<const float4*>(&rv[p2][1]);
-              f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w; f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
-            } else {
-              float r[8];
-              unpack8(rv[p2][0], r);
-#pragma unroll
-              for (int k2 = 0; k2 < 8; ++k2) f[k2] += r[k2];
-            }
-          }
-          if (a.out_fp32) {
-            float* op = reinterpret_cast<float*>(a.out) + (size_t)tok[p2] * a.out_stride + c;
-            *reinterpret_cast<float4*>(op) = make_float4(f[0], f[1], f[2], f[3]);
-            *reinterpret_cast<float4*>(op + 4) = make_float4(f[4], f[5], f[6], f[7]);
-          } else {
-            *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(a.out) + (size_t)tok[p2] * a.out_stride + c) = pack8(f);
-          }
-        }
-        grp_bar();
-      }
-      if (grp == 0 && et == 0) { LF_TRACE(6, 3 * it + 2) }
-    };
 
     // E1 pieces of 32 hidden columns (16 TMEM lanes each).  Fragment f < 2: rows 32q + 16f of the M=128 part; f == 2: rows
     // 128 + 16q of the M=64 part (its 64 rows sit 16 per lane quadrant).  SL = 64: 6 pieces, 3 per group.  SL = 32: 3 pieces:
@@ -566,10 +474,7 @@ __global__ void __launch_bounds__(kLFThreads, 1) leff_fused_kernel(const __grid_
       mbar_arrive(smem_u32(&ms.bar_d1_empty[d1b]));
       mbar_arrive(smem_u32(&ms.bar_h_full[db]));
       if (q == 0 && lane == 0) { LF_TRACE(grp, 2 * k + 1) }
-      // the previous tile's output epilogue runs one or two slices into this tile (its GEMM-2 chain has drained by then)
-      if (it > 0 && j == ((NS > 1 && Cfg::ND2 == 2) ? 1 : 0)) epilogue2(it - 1);
     }
-    if (my_tiles > 0) epilogue2(my_tiles - 1);
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
     // ============================== conv warps 0-7 ==============================
@@ -583,6 +488,103 @@ __global__ void __launch_bounds__(kLFThreads, 1) leff_fused_kernel(const __grid_
     const uint32_t halo0 = smem_u32(smem + Cfg::S_HALO), taps0 = smem_u32(smem + Cfg::S_TAPS);
     GeluH2 gelu;
     gelu.init();
+    // ---- E2, the output epilogue (D2 + b2 -> staging -> coalesced store with the residual added), also lives on these warps:
+    // two groups of four warps (one per TMEM lane quadrant), each drains half of the output columns through its own staging
+    // tile (C >= 64; narrower outputs are drained by group 0 alone). ----
+    const int grp = warp >> 2, q = warp & 3, et = tid & 127, tq = lane & 3;
+    const uint32_t stage_s = smem_u32(smem + Cfg::S_STAGE) + grp * (128 * Cfg::STAGE_PITCH), b2_s = smem_u32(smem + Cfg::S_B2);
+    auto grp_bar = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory"); };
+    constexpr bool SPLIT_E2 = (C >= 64);
+    constexpr int E2_COLS = SPLIT_E2 ? C / 2 : C;             // output columns this group drains
+    constexpr int E2_PASS = (E2_COLS >= 32) ? 32 : 16;        // columns per staging pass
+    constexpr int VPR = E2_PASS / 8;                          // 16-byte vectors per staged row
+    constexpr int VPT = VPR;                                  // vectors per thread per pass (128 rows x VPR vectors / 128 threads)
+    int* row_out = ms.row_out + grp * 128;
+    auto epilogue2 = [&](int it) {
+      if (!SPLIT_E2 && grp == 1) return;
+      const int ob = it % Cfg::ND2;
+      const int tile = tile_of(it);
+      if (tid == 0) { LF_TRACE(6, 3 * it) }
+      {
+        const int tx = tile % a.tiles_x, ty = (tile / a.tiles_x) % a.tiles_y, b = tile / (a.tiles_x * a.tiles_y);
+        const int y = ty * 8 + (et >> 4), x = tx * 16 + (et & 15);
+        row_out[et] = (x < a.W) ? ((b * a.H + y) * a.W + x) : -1;
+      }
+      grp_bar();
+      // this thread copies out vectors i = et + p*128 of every pass: row i / VPR, vector i % VPR (fixed over the passes)
+      int tok[VPT];
+#pragma unroll
+      for (int p2 = 0; p2 < VPT; ++p2) tok[p2] = row_out[(et + p2 * 128) / VPR];
+      mbar_wait(smem_u32(&ms.bar_d2_full[ob]), (it / Cfg::ND2) & 1);
+      tc_fence_after();
+      if (tid == 0) { LF_TRACE(6, 3 * it + 1) }
+      const int cbase = grp * (SPLIT_E2 ? C / 2 : 0);
+#pragma unroll 1
+      for (int sc = 0; sc < E2_COLS; sc += E2_PASS) {
+        // residual vectors of this pass: issued first so that their (L2) latency hides under the TMEM read + staging below
+        uint4 rv[VPT][2];
+        if (a.resid != nullptr) {
+#pragma unroll
+          for (int p2 = 0; p2 < VPT; ++p2) {
+            const int c = cbase + sc + ((et + p2 * 128) % VPR) * 8;
+            const size_t off = (size_t)(tok[p2] < 0 ? 0 : tok[p2]) * a.resid_stride + c;
+            if (a.resid_fp32) {
+              rv[p2][0] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(a.resid) + off));
+              rv[p2][1] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(a.resid) + off + 4));
+            } else {
+              rv[p2][0] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(a.resid) + off));
+            }
+          }
+        }
+        constexpr int NB = E2_PASS / 8;
+#pragma unroll
+        for (int hl = 0; hl < 2; ++hl) {
+          const int row16 = q * 32 + hl * 16;
+          uint32_t v[4 * NB];
+          const uint32_t ta = tb + ((uint32_t)row16 << 16) + Cfg::T_D2 + ob * C + cbase + sc;
+          if (NB == 4) tmem_ld_16x256b_x4(ta, v); else tmem_ld_16x256b_x2(ta, v);
+          f2 bb[NB];
+#pragma unroll
+          for (int i = 0; i < NB; ++i) { const float2 b2 = lds64f(b2_s + (cbase + sc + 8 * i + 2 * tq) * 4); bb[i] = f2_pack(b2.x, b2.y); }
+          tmem_wait_ld();
+          uint32_t pk[2 * NB];
+          frag_bias_act_pack<NB, false>(v, bb, pk);
+          stage_frag<NB>(stage_s, Cfg::STAGE_PITCH, row16, 0, pk);
+        }
+        if (sc + E2_PASS >= E2_COLS) { tc_fence_before(); mbar_arrive(smem_u32(&ms.bar_d2_empty[ob])); }
+        grp_bar();
+#pragma unroll
+        for (int p2 = 0; p2 < VPT; ++p2) {
+          if (tok[p2] < 0) continue;
+          const int i = et + p2 * 128;
+          const int row = i / VPR, vec = i % VPR;
+          float f[8];
+          unpack8(lds128(stage_s + row * Cfg::STAGE_PITCH + vec * 16), f);
+          const int c = cbase + sc + vec * 8;
+          if (a.resid != nullptr) {
+            if (a.resid_fp32) {
+              const float4 r0 = *reinterpret_cast<const float4*>(&rv[p2][0]), r1 = *reinterpret_cast<const float4*>(&rv[p2][1]);
+              f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w; f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
+            } else {
+              float r[8];
+              unpack8(rv[p2][0], r);
+#pragma unroll
+              for (int k2 = 0; k2 < 8; ++k2) f[k2] += r[k2];
+            }
+          }
+          if (a.out_fp32) {
+            float* op = reinterpret_cast<float*>(a.out) + (size_t)tok[p2] * a.out_stride + c;
+            *reinterpret_cast<float4*>(op) = make_float4(f[0], f[1], f[2], f[3]);
+            *reinterpret_cast<float4*>(op + 4) = make_float4(f[4], f[5], f[6], f[7]);
+          } else {
+            *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(a.out) + (size_t)tok[p2] * a.out_stride + c) = pack8(f);
+          }
+        }
+        grp_bar();
+      }
+      if (tid == 0) { LF_TRACE(6, 3 * it + 2) }
+    };
+
     for (int k = 0; k < total; ++k) {
       const int hbi = k & 1, tbuf = k % Cfg::NTAP;
       const uint32_t sH = halo0 + hbi * Cfg::HALO_BYTES;
@@ -636,7 +638,14 @@ __global__ void __launch_bounds__(kLFThreads, 1) leff_fused_kernel(const __grid_
       fence_async_smem();
       mbar_arrive(smem_u32(&ms.bar_a2_full[hbi]));
       if (tid == 0) { LF_TRACE(2, 4 * k + 3) }
+      // the previous tile's output epilogue runs one or two slices into this tile (its GEMM-2 chain has drained by then;
+      // with a single D2 buffer it must run before this tile's second GEMM-2 can be issued)
+      {
+        const int j = k % NS, it = k / NS;
+        if (it > 0 && j == ((NS > 1 && Cfg::ND2 == 2) ? 1 : 0)) epilogue2(it - 1);
+      }
     }
+    if (my_tiles > 0) epilogue2(my_tiles - 1);
   }
   tc_fence_before();
   __syncthreads();
