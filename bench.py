@@ -309,6 +309,9 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="images per GPU per step (default: 32 for fwd, 8 for train)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="fwd", choices=["fwd", "train"])
+    ap.add_argument("--size", type=int, default=256, choices=[256, 512],
+                    help="image side: 256 (BASELINE configs[1], the headline) or 512 (configs[3]: the model built for 256 run on "
+                         "512x512 images in one whole-image forward, default batch 8)")
     ap.add_argument("--residual", default=None, choices=["auto", "fp32", "bf16"],
                     help="residual-stream precision between the kernels of a stage (default: the engine's default, fp32)")
     args = ap.parse_args()
@@ -345,10 +348,11 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     warm = max(args.warmup, 3)
-    B = args.batch or 32
+    S = args.size
+    B = args.batch or (32 if S == 256 else 8)
     net = build_engine(dev)
     torch.manual_seed(1234 + rank)
-    x_host = torch.rand(B, 3, 256, 256).pin_memory()
+    x_host = torch.rand(B, 3, S, S).pin_memory()
     x_dev = x_host.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
@@ -390,7 +394,7 @@ def main():
     main_s = torch.cuda.current_stream()
     s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
     xd = [torch.empty_like(x_dev) for _ in range(2)]
-    yh = [torch.empty(B, 3, 256, 256).pin_memory() for _ in range(2)]
+    yh = [torch.empty(B, 3, S, S).pin_memory() for _ in range(2)]
     ev_h2d = [torch.cuda.Event() for _ in range(2)]
     ev_comp = [torch.cuda.Event() for _ in range(2)]
     ev_d2h = [torch.cuda.Event() for _ in range(2)]
@@ -465,6 +469,7 @@ def main():
             dist.destroy_process_group()
         return
     peaks = measured_peaks()
+    gflop_img = GFLOP_PER_IMG * (S / 256) ** 2            # every op of the forward is linear in the pixel count
     ms_step = total_ms / args.steps
     value = world * B * args.steps / (total_ms / 1e3)
     e2e_val = world * B * args.steps / (e2e_ms / 1e3)
@@ -483,13 +488,15 @@ def main():
                 "frac": ach / peaks["tf_sustained"], "peak_source": peaks["src"] + " sustained (kernel timed inside a long step)",
                 "traffic": traffic, "traffic_source": traffic_src, "share_of_step": dms / tot_prof, "launches_per_step": dcount,
                 "avg_launch_ms": dms / dcount,
-                "model": {"achieved": GFLOP_PER_IMG * value / world / 1e3, "unit": "TFLOP/s",
-                          "frac": GFLOP_PER_IMG * value / world / 1e3 / peaks["tf_sustained"]},
+                "model": {"achieved": gflop_img * value / world / 1e3, "unit": "TFLOP/s",
+                          "frac": gflop_img * value / world / 1e3 / peaks["tf_sustained"]},
                 "by_kernel_ms": {k: round(v[0], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}}
     line = {
-        "metric": "images/sec Uformer-B 256x256 fwd", "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
+        "metric": f"images/sec Uformer-B {S}x{S} fwd", "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "Uformer-B 256x256 inference fwd, batch 32 per GPU (BASELINE configs[1])", "global_batch": B * world,
+        "config": {"workload": (f"Uformer-B 256x256 inference fwd, batch {B} per GPU (BASELINE configs[1])" if S == 256 else
+                                f"Uformer-B (built for 256x256) on {S}x{S} images, one whole-image forward each, batch {B} per GPU (BASELINE configs[3])"),
+                   "global_batch": B * world,
                    "per_gpu_batch": B, "parallelism": f"replicas x{world} (no collective)", "l2": "256MB flush between timed steps",
                    "weights": "synthetic seeded init of the Uformer-B architecture",
                    "cuda_graph": graphed is not None,
@@ -497,7 +504,7 @@ def main():
         "e2e": {"value": e2e_val, "unit": "img/s", "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": yh[0].numel() * 4, "pipelined": "2 copy streams, double-buffered",
                 "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline}
-    if not args.no_cpu_baseline and world == 1:
+    if not args.no_cpu_baseline and world == 1 and S == 256:
         note("cpu baseline (oracle port on host cores)")
         v, threads, dt = cpu_oracle_rate(4, iters=2)
         line["cpu_baseline"] = {"value": v, "unit": "img/s", "cores": threads, "kind": "port",

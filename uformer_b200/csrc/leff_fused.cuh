@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(kLFThreads, 1) leff_fused_kernel(const __grid_
     // Each group takes half of the 32-column pieces of a hidden slice (and, at a tile's first slice, a share of the
     // LayerNorm statistics).  The output epilogue E2 runs on the conv warps, which have the slack.
     const int grp = (wg == 4) ? 1 : 0;
-    const int q = warp & 3, et = tid & 127;
+    const int q = warp & 3;
     const int t4 = lane >> 2, tq = lane & 3;
     const int m = lane >> 3, rr = lane & 7;
     const uint32_t halo0 = smem_u32(smem + Cfg::S_HALO);
