@@ -51,7 +51,8 @@ int lw_nch_ares(int K, int n_total);
  * and, with ln_w=NULL / resid=NULL / windowed=1, WindowAttention.forward (model.py:494-522).
  *   out = resid + reverse( proj( softmax( q k^T * hd^-1/2 + relpos_bias + mask ) v ) )
  *   q,k,v = Linear( partition( roll( LN(x), -shift ) ) + modulator )
- * Window size is 8x8 (64 tokens); head_dim in {16, 32}; C in {16,...,512}, C % head_dim == 0. */
+ * Window size is 8x8 (64 tokens); head_dim in {16, 32, 64}; C in {16,...,512}, C % head_dim == 0 (head_dim 16: C <= 256;
+ * head_dim 64: C <= 256). */
 typedef struct lw_wmsa_args {
   const void* x;           /* bf16 (B, H*W, C) token map, or (n_windows, 64, C) if windowed */
   void* out;               /* bf16, same layout as x */

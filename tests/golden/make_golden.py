@@ -132,6 +132,15 @@ def main():
                                     checksum=state_checksum(st), ref_bf16=dict(full=rl2(yb, y512), resid=rl2(yb - x512, y512 - x512)))
     print("uformer_b_512_g05 reference bf16-autocast vs fp32:", out["uformer_b_512_g05"]["ref_bf16"])
 
+    # ---- BASELINE configs[4] point: head_dim 64 (embed_dim 64, 2 heads) WindowAttention, own RNG so older fixtures stay reproducible ----
+    gen = torch.Generator().manual_seed(6464)
+    mod = m.WindowAttention(128, win_size=(8, 8), num_heads=2)
+    st = load_random(mod, 16)
+    xw = torch.randn(6, 64, 128, generator=gen)
+    maskw = torch.where(torch.rand(3, 64, 64, generator=gen) > 0.7, torch.tensor(-100.0), torch.tensor(0.0))
+    out["wattn_c128_h2_hd64"] = dict(kind="wattn", dim=128, heads=2, seed=16, x=xw, y=mod(xw), mask=maskw, y_mask=mod(xw, mask=maskw),
+                                     checksum=state_checksum(st))
+
     only = os.environ.get("GOLDEN_ONLY")
     for k, v in out.items():
         if only and not k.startswith(only):

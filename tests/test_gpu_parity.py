@@ -55,6 +55,7 @@ def test_model_golden(name):
 @pytest.mark.parametrize("dim,heads,H,shift,modu,B", [
     (32, 1, 32, 4, False, 3), (64, 2, 16, 0, True, 1), (128, 4, 32, 4, True, 2), (256, 8, 16, 4, True, 2),
     (512, 16, 16, 4, True, 1), (512, 16, 8, 0, False, 3), (16, 1, 16, 4, True, 2), (256, 16, 16, 4, False, 1),
+    (64, 1, 16, 4, True, 2), (128, 2, 16, 0, False, 1), (256, 4, 16, 4, True, 1),          # head_dim 64 (BASELINE configs[4])
 ])
 def test_block_vs_oracle(dim, heads, H, shift, modu, B):
     """Every stage shape of Uformer-B/T (C=16..512, head_dim 16/32), shifted and not, odd window counts."""

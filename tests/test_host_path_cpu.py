@@ -231,9 +231,10 @@ def test_smoke_host_logic_through_contract_model(capsys):
     assert calls["charbonnier"] == 1 and calls["adamw_step"] == 1
 
 
-@pytest.mark.parametrize("dim,heads", [(16, 1), (32, 1), (32, 2), (64, 2), (64, 4), (128, 4), (128, 8), (256, 8), (256, 16), (512, 16)])
+@pytest.mark.parametrize("dim,heads", [(16, 1), (32, 1), (32, 2), (64, 2), (64, 4), (128, 4), (128, 8), (256, 8), (256, 16), (512, 16),
+                                       (64, 1), (128, 2), (256, 4)])
 def test_every_supported_channel_count_through_contract_model(dim, heads):
-    """Operand-image packing for every (C, head_dim in {16, 32}) the kernels are instantiated for: block through the
+    """Operand-image packing for every (C, head_dim in {16, 32, 64}) the kernels are instantiated for: block through the
     contract model (which decodes the images) == oracle on the raw weights."""
     from oracle import lewin_oracle as O
     shift = 4 if dim % 64 == 0 else 0

@@ -124,6 +124,7 @@ extern "C" int lw_wmsa_fwd(const lw_wmsa_args* a, lw_stream_t stream) {
   if (a->C == c && a->head_dim == hd) return launch_wmsa<c, hd>(a, st);
   WMSA_CASE(32, 32) WMSA_CASE(64, 32) WMSA_CASE(128, 32) WMSA_CASE(256, 32) WMSA_CASE(512, 32)
   WMSA_CASE(16, 16) WMSA_CASE(32, 16) WMSA_CASE(64, 16) WMSA_CASE(128, 16) WMSA_CASE(256, 16)
+  WMSA_CASE(64, 64) WMSA_CASE(128, 64) WMSA_CASE(256, 64)
 #undef WMSA_CASE
   return LW_ERR_BAD_SHAPE;
 }

@@ -30,15 +30,19 @@ struct WmsaCfg {
   static constexpr int NC = C / NCH;
   static constexpr int PROJ_CHUNK_BYTES = NCH * 128;
   static constexpr int STAGES = (C >= 512) ? 3 : (C == 128 ? 2 : 4);   // C=128: 2 stages so two CTAs fit per SM
+  static constexpr int STAGE_BYTES = (HD == 64) ? 24576 : kStageBytes; // head_dim 64: a (head, k-block) QKV chunk is 192 rows
   // TMEM columns
   static constexpr int T_OALL = 0;                         // O for all heads, bf16 packed: C/2 cols
   static constexpr int T_WORK = (C / 2 < 32) ? 32 : C / 2; // S / P (128 cols); also D_out buffer 0
-  static constexpr int T_DO = T_WORK + 128;                // D_o, HD cols (<= 32)
+  // head_dim 64: D_qkv is 192 columns wide; aliased onto S (128 columns) it reaches 64 columns further, so D_o sits behind it
+  static constexpr int T_DO = T_WORK + (HD == 64 ? 192 : 128);   // D_o, HD cols
   // C >= 256 (1 CTA/SM anyway): D_qkv gets its own 96 columns so the issuer can run the QKV GEMM of head h+1
-  // underneath the softmax of head h.  C <= 128: D_qkv aliases S so that two CTAs fit in TMEM.
-  static constexpr bool PIPE = (C >= 256);
+  // underneath the softmax of head h.  C <= 128 (and head_dim 64, whose 192 columns do not fit beside the rest): D_qkv
+  // aliases S so that two CTAs fit in TMEM.
+  static constexpr bool PIPE = (C >= 256) && (HD <= 32);
   static constexpr int T_QKV = PIPE ? T_DO + 32 : T_WORK;
-  static constexpr int T_NEED = T_WORK + ((NC > 1 || PIPE) ? 256 : 160);
+  static constexpr int T_NEED = (HD == 64) ? T_WORK + 256 : T_WORK + ((NC > 1 || PIPE) ? 256 : 160);
+  static_assert(T_NEED <= 512, "TMEM budget");
   static constexpr int T_ALLOC = T_NEED <= 256 ? 256 : 512;
   // shared memory map (bytes)
   static constexpr int S_X = 0;
@@ -47,7 +51,7 @@ struct WmsaCfg {
   static constexpr int S_K = S_Q + TILE_B;
   static constexpr int S_V = S_K + TILE_B;
   static constexpr int S_RING = S_V + TILE_B;
-  static constexpr int S_MISC = S_RING + STAGES * kStageBytes;
+  static constexpr int S_MISC = S_RING + STAGES * STAGE_BYTES;
   static constexpr int SMEM_BYTES = S_MISC + 4096 + 1024;  // + slack for 1024 B alignment
 };
 
@@ -56,7 +60,7 @@ struct WmsaMisc {
   int row_tok[128];
   uint8_t region[128];
   int win_mixed[2];
-  float bqkv[2][96];       // q|k|v bias of the current / next head (written one head ahead)
+  float bqkv[2][192];      // q|k|v bias of the current / next head (written one head ahead)
   uint64_t bar_full[4], bar_empty[4];
   uint64_t bar_xn, bar_qkv_full, bar_qkv_staged, bar_s_full, bar_p_ready, bar_o_full, bar_oall;
   uint64_t bar_d_full[2], bar_d_empty[2];
@@ -65,7 +69,7 @@ struct WmsaMisc {
 static_assert(sizeof(WmsaMisc) <= 4096, "misc too large");
 
 template <int C, int HD>
-__global__ void __launch_bounds__(kThreads8, (C <= 128) ? 2 : 1) wmsa_kernel(const lw_wmsa_args a) {
+__global__ void __launch_bounds__(kThreads8, (C <= 128 && HD <= 32) ? 2 : 1) wmsa_kernel(const lw_wmsa_args a) {
   using Cfg = WmsaCfg<C, HD>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -99,7 +103,7 @@ __global__ void __launch_bounds__(kThreads8, (C <= 128) ? 2 : 1) wmsa_kernel(con
   if (warp == 8) {
     // ======================= producer: weight chunk images =======================
     if (lane == 0) {
-      Ring ring{smem_u32(smem + Cfg::S_RING), smem_u32(&ms.bar_full[0]), smem_u32(&ms.bar_empty[0]), Cfg::STAGES, 0};
+      Ring ring{smem_u32(smem + Cfg::S_RING), smem_u32(&ms.bar_full[0]), smem_u32(&ms.bar_empty[0]), Cfg::STAGES, 0, Cfg::STAGE_BYTES};
       const uint8_t* wq = reinterpret_cast<const uint8_t*>(a.wqkv_img);
       for (int h = 0; h < Cfg::NH; ++h)
         for (int kb = 0; kb < Cfg::KB; ++kb)
@@ -112,7 +116,7 @@ __global__ void __launch_bounds__(kThreads8, (C <= 128) ? 2 : 1) wmsa_kernel(con
   } else if (warp == 9) {
     // ======================= issuer: all tcgen05.mma (warp-uniform; one elected lane issues) =======================
     {
-      Ring ring{smem_u32(smem + Cfg::S_RING), smem_u32(&ms.bar_full[0]), smem_u32(&ms.bar_empty[0]), Cfg::STAGES, 0};
+      Ring ring{smem_u32(smem + Cfg::S_RING), smem_u32(&ms.bar_full[0]), smem_u32(&ms.bar_empty[0]), Cfg::STAGES, 0, Cfg::STAGE_BYTES};
       constexpr uint32_t idesc_qkv = make_idesc_bf16(128, Cfg::QKV_N);
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 128);
       constexpr uint32_t idesc_pv = make_idesc_bf16(128, HD, false, true);
@@ -246,7 +250,7 @@ __global__ void __launch_bounds__(kThreads8, (C <= 128) ? 2 : 1) wmsa_kernel(con
     // relative-position index base of this thread's two rows (token i = row & 63: yi = i>>3, xi = i&7)
     const int rp0 = (((r0 & 63) >> 3) + 7) * 15 + (r0 & 7) + 7;
     const int rp1 = (((r1 & 63) >> 3) + 7) * 15 + (r1 & 7) + 7;
-    constexpr int NBH = HD / 8;                      // 8-column blocks per head slice (4 or 2)
+    constexpr int NBH = HD / 8;                      // 8-column blocks per head slice (8, 4 or 2)
 
     LW_TRACE_STMT(const bool trw = (a.dbg & 16) && blockIdx.x == 0 && tid == 0 && a.trace != nullptr; int tw = 0;)
     LW_TRACE_STMT(if (trw) a.trace[tw++] = clock64();)
@@ -261,16 +265,8 @@ __global__ void __launch_bounds__(kThreads8, (C <= 128) ? 2 : 1) wmsa_kernel(con
       tc_fence_after();
       LW_TRACE_STMT(if (trw && h < 4) a.trace[tw++] = clock64();)
       {
-        uint32_t v[3][4 * NBH];
-#pragma unroll
-        for (int part = 0; part < 3; ++part) {
-          if (NBH == 4) tmem_ld_16x256b_x4(tb + tl + Cfg::T_QKV + part * HD, v[part]);
-          else tmem_ld_16x256b_x2(tb + tl + Cfg::T_QKV + part * HD, v[part]);
-        }
-        tmem_wait_ld();
         const int m = lane >> 3, rr = lane & 7;
-#pragma unroll
-        for (int part = 0; part < 3; ++part) {
+        auto qkv_part = [&](const uint32_t* vp, int part) {
           f2 bb[NBH];
 #pragma unroll
           for (int i = 0; i < NBH; ++i) {
@@ -278,12 +274,31 @@ __global__ void __launch_bounds__(kThreads8, (C <= 128) ? 2 : 1) wmsa_kernel(con
             bb[i] = f2_pack(b2.x, b2.y);
           }
           uint32_t pk[2 * NBH];
-          frag_bias_act_pack<NBH, false>(v[part], bb, pk);
+          frag_bias_act_pack<NBH, false>(vp, bb, pk);
           const uint32_t tile_s = (part == 0 ? sQ : part == 1 ? sK : sV);
           const int row = row16 + (m & 1) * 8 + rr;
 #pragma unroll
           for (int i2 = 0; i2 < NBH / 2; ++i2)
             stsm_x4(tile_s + swz<Cfg::SWH>(row, (2 * i2 + (m >> 1)) * 16), pk[4 * i2], pk[4 * i2 + 1], pk[4 * i2 + 2], pk[4 * i2 + 3]);
+        };
+        if (NBH == 8) {                    // head_dim 64: 32 registers per part, one part in flight
+#pragma unroll
+          for (int part = 0; part < 3; ++part) {
+            uint32_t v[4 * NBH];
+            tmem_ld_16x256b_x8(tb + tl + Cfg::T_QKV + part * HD, v);
+            tmem_wait_ld();
+            qkv_part(v, part);
+          }
+        } else {
+          uint32_t v[3][4 * NBH];
+#pragma unroll
+          for (int part = 0; part < 3; ++part) {
+            if (NBH == 4) tmem_ld_16x256b_x4(tb + tl + Cfg::T_QKV + part * HD, v[part]);
+            else tmem_ld_16x256b_x2(tb + tl + Cfg::T_QKV + part * HD, v[part]);
+          }
+          tmem_wait_ld();
+#pragma unroll
+          for (int part = 0; part < 3; ++part) qkv_part(v[part], part);
         }
       }
       fence_async_smem();
@@ -373,7 +388,9 @@ __global__ void __launch_bounds__(kThreads8, (C <= 128) ? 2 : 1) wmsa_kernel(con
       LW_TRACE_STMT(if (trw && h < 4) a.trace[tw++] = clock64();)
       {
         uint32_t v[4 * NBH];
-        if (NBH == 4) tmem_ld_16x256b_x4(tb + tl + Cfg::T_DO, v); else tmem_ld_16x256b_x2(tb + tl + Cfg::T_DO, v);
+        if (NBH == 8) tmem_ld_16x256b_x8(tb + tl + Cfg::T_DO, v);
+        else if (NBH == 4) tmem_ld_16x256b_x4(tb + tl + Cfg::T_DO, v);
+        else tmem_ld_16x256b_x2(tb + tl + Cfg::T_DO, v);
         tmem_wait_ld();
         const float i0 = 1.0f / sum0, i1 = 1.0f / sum1;
         uint32_t pk[2 * NBH];
@@ -382,7 +399,8 @@ __global__ void __launch_bounds__(kThreads8, (C <= 128) ? 2 : 1) wmsa_kernel(con
           pk[2 * i] = pack_bf16(__uint_as_float(v[4 * i]) * i0, __uint_as_float(v[4 * i + 1]) * i0);
           pk[2 * i + 1] = pack_bf16(__uint_as_float(v[4 * i + 2]) * i1, __uint_as_float(v[4 * i + 3]) * i1);
         }
-        if (NBH == 4) tmem_st_16x128b_x4(tb + tl + Cfg::T_OALL + (h * HD) / 2, pk);
+        if (NBH == 8) tmem_st_16x128b_x8(tb + tl + Cfg::T_OALL + (h * HD) / 2, pk);
+        else if (NBH == 4) tmem_st_16x128b_x4(tb + tl + Cfg::T_OALL + (h * HD) / 2, pk);
         else tmem_st_16x128b_x2(tb + tl + Cfg::T_OALL + (h * HD) / 2, pk);
         tmem_wait_st();
       }

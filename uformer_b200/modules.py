@@ -181,7 +181,7 @@ class WindowAttention(nn.Module):
         if tuple(self.win_size) != (8, 8):
             raise NotImplementedError(f"uformer_b200 kernels are specialised for 8x8 windows (got {self.win_size})")
         hd = self.dim // self.num_heads
-        if hd not in (16, 32) or self.dim % hd or self.dim > 512 or (hd == 16 and self.dim > 256):
+        if hd not in (16, 32, 64) or self.dim % hd or self.dim > 512 or (hd in (16, 64) and self.dim > 256):
             raise NotImplementedError(f"unsupported (dim={self.dim}, heads={self.num_heads})")
         if self.attn_drop.p > 0 and self.training or self.proj_drop.p > 0 and self.training:
             raise NotImplementedError("attention/projection dropout is not implemented (p=0 in every Uformer config)")
