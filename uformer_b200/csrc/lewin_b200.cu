@@ -11,6 +11,7 @@
 #include "proj.cuh"
 #include "train.cuh"
 #include <cmath>
+#include <atomic>
 
 using namespace lw;
 
@@ -58,10 +59,29 @@ extern "C" int lw_struct_size(int id) {
   }
 }
 
+// Profiling knobs (env LW_DEBUG, see leff.cuh) exist only in -DLW_TRACE builds (liblewin_b200_trace.so, tools/*_trace.py); the
+// production library never touches the environment on the launch path.
 static int debug_flags() {
-  const char* e = getenv("LW_DEBUG");   // profiling knobs, see leff.cuh (never set in production)
+#ifdef LW_TRACE
+  const char* e = getenv("LW_DEBUG");
   return e ? atoi(e) : 0;
+#else
+  return 0;
+#endif
 }
+
+// Opt a kernel into its dynamic shared-memory size once per device (the attribute is per device and sticky), not per launch.
+#define LW_ENSURE_SMEM(kernel, bytes)                                                                         \
+  do {                                                                                                        \
+    static std::atomic<unsigned long long> _done{0};                                                          \
+    int _dev = 0;                                                                                             \
+    cudaGetDevice(&_dev);                                                                                     \
+    const unsigned long long _bit = 1ull << (_dev & 63);                                                      \
+    if (!(_done.load(std::memory_order_relaxed) & _bit)) {                                                    \
+      LW_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));               \
+      _done.fetch_or(_bit, std::memory_order_relaxed);                                                        \
+    }                                                                                                         \
+  } while (0)
 
 // N-chunk (rows per weight image chunk) of the A-resident kernels; packing.py mirrors this rule.
 extern "C" int lw_nch_ares(int K, int n_total) {
@@ -91,7 +111,7 @@ template <int C, int HD>
 static int launch_wmsa(const lw_wmsa_args* a, cudaStream_t st) {
   using Cfg = WmsaCfg<C, HD>;
   static_assert(Cfg::SMEM_BYTES <= 232448, "smem budget");
-  LW_TRY(cudaFuncSetAttribute(wmsa_kernel<C, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  LW_ENSURE_SMEM((wmsa_kernel<C, HD>), Cfg::SMEM_BYTES);
   const int tiles = (a->n_windows + 1) / 2;
   wmsa_kernel<C, HD><<<tiles, kThreads8, Cfg::SMEM_BYTES, st>>>(*a);
   LW_TRY(cudaGetLastError());
@@ -134,7 +154,7 @@ template <int K, int EPI>
 static int launch_ares(const AResArgs& a, cudaStream_t st) {
   using Cfg = AResCfg<K>;
   static_assert(Cfg::SMEM_BYTES <= 232448, "smem budget");
-  LW_TRY(cudaFuncSetAttribute(ares_kernel<K, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+  LW_ENSURE_SMEM((ares_kernel<K, EPI>), Cfg::SMEM_BYTES);
   const int tiles = (a.n_rows + 127) / 128;
   ares_kernel<K, EPI><<<tiles, kThreads8, Cfg::SMEM_BYTES, st>>>(a);
   LW_TRY(cudaGetLastError());
@@ -206,7 +226,7 @@ extern "C" int lw_leff2_fwd(const lw_leff2_args* p, lw_stream_t stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if ((long long)p->B * p->H * p->W * p->hidden >= (1ll << 32)) return LW_ERR_BAD_SHAPE;   // 32-bit element offsets in the halo prefetch
   const int nbuf_d = (2 * a.N <= 512) ? 2 : 1;                 // double-buffer the TMEM accumulator when it fits
-  LW_TRY(cudaFuncSetAttribute(leff2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Leff2Cfg::SMEM_BYTES));
+  LW_ENSURE_SMEM(leff2_kernel, Leff2Cfg::SMEM_BYTES);
   const int grid = tiles < sm_count() ? tiles : sm_count();    // persistent: one CTA per SM
   leff2_kernel<<<grid, kL2Threads, Leff2Cfg::SMEM_BYTES, st>>>(a, pow2_cols(nbuf_d * a.N), tiles, nbuf_d);
   LW_TRY(cudaGetLastError());
@@ -252,11 +272,7 @@ extern "C" int lw_leff_slice(int C) { return C <= 128 ? 64 : 32; }
 template <int C>
 static int launch_leff_fused(const CUtensorMap& map, const LeffFArgs& a, cudaStream_t st) {
   using Cfg = LeffFCfg<C>;
-  static bool attr_set = false;     // per-process, per-instantiation (re-setting it is harmless: benign race)
-  if (!attr_set) {
-    LW_TRY(cudaFuncSetAttribute(leff_fused_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
+  LW_ENSURE_SMEM(leff_fused_kernel<C>, Cfg::SMEM_BYTES);
   const int grid = a.n_tiles < sm_count() ? a.n_tiles : sm_count();
   leff_fused_kernel<C><<<grid, kLFThreads, Cfg::SMEM_BYTES, st>>>(map, a);
   LW_TRY(cudaGetLastError());
@@ -313,7 +329,7 @@ extern "C" int lw_downsample_fwd(const lw_down_args* p, lw_stream_t stream) {
   a.bias = p->bias; a.out = reinterpret_cast<bf16*>(p->out);
   const int rows = p->B * (p->H / 2) * (p->W / 2);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  LW_TRY(cudaFuncSetAttribute(down_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DownCfg::SMEM_BYTES));
+  LW_ENSURE_SMEM(down_kernel, DownCfg::SMEM_BYTES);
   down_kernel<<<(rows + 127) / 128, kThreads8, DownCfg::SMEM_BYTES, st>>>(a, pow2_cols(a.N));
   LW_TRY(cudaGetLastError());
   return LW_OK;
