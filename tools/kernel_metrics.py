@@ -32,7 +32,10 @@ def main(csv_path, labels_path, out_path):
         d = launches.setdefault(int(r[iid]), {"name": r[ikn]})
         d[r[imn]] = (r[imv], r[imu])
     ordered = [launches[k] for k in sorted(launches)]
-    ours = [d for d in ordered if "lw::" in d["name"]]
+    OURS = ("input_proj_kernel", "output_proj_kernel", "wmsa_kernel", "leff_fused_kernel", "ares_kernel", "leff2_kernel", "down_kernel",
+            "charbonnier", "adamw_kernel")
+    is_ours = lambda n: n.replace("void ", "").replace("lw::", "").startswith(OURS)          # noqa: E731
+    ours = [d for d in ordered if is_ours(d["name"])]
     labels = json.load(open(labels_path))
     # charbonnier / adamw never run in a forward; labels and our kernels are both in launch order
     assert len(ours) == len(labels), (len(ours), len(labels))
@@ -45,7 +48,7 @@ def main(csv_path, labels_path, out_path):
         a["tensor"] += float(d["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"][0])
     out = dict(source=f"ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,sm__pipe_tensor_cycles_active... "
                       f"--clock-control none over one batch-32 forward ({os.path.basename(csv_path)}); cold-cache, serialised launches",
-               lib_sha256_16=lib_hash(), others_aten=[d["name"][:80] for d in ordered if "lw::" not in d["name"]],
+               lib_sha256_16=lib_hash(), others_aten=[d["name"][:80] for d in ordered if not is_ours(d["name"])],
                dram_bytes_per_launch={k: round(v["dram"] / v["n"]) for k, v in agg.items()},
                us_per_launch={k: round(v["us"] / v["n"], 2) for k, v in agg.items()},
                tensor_pipe_pct={k: round(v["tensor"] / v["n"], 2) for k, v in agg.items()},
