@@ -154,12 +154,13 @@ def run_reference_arm(args, rank, world):
     v = nimg / dt
     sample = (f"{nimg} images of the batch-32 step per timed step (fp32 oracle port of model.py's forward, torch CPU ops, "
               f"{threads} of {os.cpu_count()} host threads = best of 16/32/64)")
+    # same metric / unit / config as the GPU arm (the workload is the batch-32 step; each timed step runs a bounded sample of it)
     print(json.dumps({
         "impl": "reference", "metric": "images/sec Uformer-B 256x256 fwd", "value": v, "unit": "img/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": "Uformer-B 256x256 inference fwd (BASELINE configs[1]), CPU port of the reference forward",
-                   "global_batch": nimg},
+        "config": {"workload": "Uformer-B 256x256 inference fwd, batch 32 per GPU (BASELINE configs[1])", "global_batch": 32 * max(1, args.gpus),
+                   "per_gpu_batch": 32, "sample_images_per_step": nimg, "implementation": "CPU port of the reference forward (oracle/)"},
         "cpu_baseline": {"value": v, "unit": "img/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
