@@ -82,10 +82,11 @@ typedef struct lw_wmsa_args {
 } lw_wmsa_args;
 int lw_wmsa_fwd(const lw_wmsa_args* a, lw_stream_t stream);
 
-/* ---- LeFF part 1: h1 = GELU( LN(x) W1^T + b1 )  (model.py:671 with norm2 of :987 folded in) */
+/* ---- LeFF part 1 (two-kernel path, C = 512): h1 = GELU( LN(x) W1^T + b1 )  (model.py:671 with norm2 of :987 folded in).
+ * h1 is written in HALF precision (fp16): it is an internal buffer between the two kernels. */
 typedef struct lw_leff1_args {
   const void* x;           /* bf16 (n_tokens, C) */
-  void* h1;                /* bf16 (n_tokens, 4C) */
+  void* h1;                /* fp16 (n_tokens, 4C) */
   const float* ln_w;       /* NULL: no LayerNorm (LeFF standalone) */
   const float* ln_b;
   const void* w1_img;      /* packed bf16 [hidden/nch][KB][nch x 128B] */
@@ -98,12 +99,11 @@ int lw_leff1_fwd(const lw_leff1_args* a, lw_stream_t stream);
 /* ---- LeFF part 2: out = resid + GELU( dwconv3x3(h1) + bd ) W2^T + b2  (model.py:674-682);
  * the depthwise conv is staged in shared memory (zero padding on h1) and feeds the GEMM directly. */
 typedef struct lw_leff2_args {
-  const void* h1;          /* bf16 (B, H, W, hidden) */
+  const void* h1;          /* fp16 (B, H, W, hidden), as written by lw_leff1_fwd */
   void* out;               /* bf16 (B, H*W, C) (fp32 if out_fp32) */
   const void* resid;       /* bf16 (B, H*W, C) (fp32 if resid_fp32) or NULL */
-  const float* wd;         /* (9, hidden) fp32 depthwise taps, tap = ky*3+kx */
-  const float* bd;         /* (hidden) */
-  const void* w2_img;      /* packed bf16 [hidden/64][C/nch][nch x 128B] */
+  const void* taps;        /* fp16 (10, hidden): 9 depthwise taps (tap = ky*3+kx), then the conv bias */
+  const void* w2_img;      /* packed FP16 [hidden/64][C/nch][nch x 128B] */
   const float* b2;         /* (C) */
   int32_t B, H, W, C, hidden;
   int32_t resid_fp32, out_fp32;   /* fp32 residual-stream mode (0 = bf16) */

@@ -127,12 +127,14 @@ def leff(x, p, *, B, H, W, resid, out=None, out_dtype=None):
         nch1 = min(hid, 256 if C == 256 else 128)                     # lw_nch_ares
         assert nch1 == _lib.load().lw_nch_ares(C, hid)
         w1 = packing.unpack_kmajor(p["w1_img"], hid, C, nch1, "nk")
-        h1 = _q(F.gelu(_q(xf) @ w1.t() + p["b1"]))                    # bf16 round trip through HBM
+        q16 = lambda t: t.to(torch.float16).float()
+        h1 = q16(F.gelu(q16(_q(xf) @ w1.t() + p["b1"])))              # fp16 round trip through HBM
+        assert p["w2_img"].dtype == torch.float16 and p["taps16"].dtype == torch.float16
         w2 = packing.unpack_kmajor(p["w2_img"], C, hid, min(C, 128), "kn")
-        wd_t, bd_t = p["wd"], p["bd"]
+        wd_t, bd_t = p["taps16"].float()[:9], p["taps16"].float()[9]
     m = h1.view(B, H, W, hid).permute(0, 3, 1, 2)
     wd = wd_t.t().reshape(hid, 1, 3, 3)                           # taps (9, hidden), tap = ky*3+kx
-    qh = (lambda t: t.to(torch.float16).float()) if "w1f_img" in p else _q
+    qh = lambda t: t.to(torch.float16).float()                      # both LeFF paths keep the hidden map in half precision
     h2 = qh(F.gelu(qh(F.conv2d(m, wd, bd_t, padding=1, groups=hid)))).permute(0, 2, 3, 1).reshape(B * H * W, hid)
     y = _q(h2 @ w2.t() + p["b2"]).view(x.shape)                  # the branch is rounded to bf16 before the residual add
     if resid is not None:

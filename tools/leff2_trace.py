@@ -7,6 +7,7 @@ from uformer_b200 import ops
 from paramgen import randomize_state
 dev = torch.device("cuda:0")
 C, H = int(sys.argv[1]), int(sys.argv[2])
+os.environ['UFORMER_B200_LEFF'] = 'split'          # this tool traces the two-kernel path (C = 512, or forced)
 m = U.LeFF(C, 4 * C).eval(); m.load_state_dict(randomize_state(m.state_dict(), 1)); m = m.to(dev)
 x = torch.randn(32, H * H, C, device=dev).to(torch.bfloat16)
 buf = torch.zeros(2048, dtype=torch.int64, device=dev)
@@ -17,12 +18,12 @@ os.environ["LW_TRACE_PTR"] = str(buf.data_ptr()); os.environ["LW_DEBUG"] = "16"
 # only the leff2 launch should trace: leff1 also honours dbg&16 but writes a different layout -> run leff2 alone via ops
 p = m.packed()
 import ctypes as Cx
-h1 = torch.randn(32 * H * H, 4 * C, device=dev).to(torch.bfloat16)
+h1 = torch.randn(32 * H * H, 4 * C, device=dev).to(torch.float16)
 out = torch.empty_like(x)
 from uformer_b200 import _lib
 b = _lib.Leff2Args()
 b.h1, b.out, b.resid = h1.data_ptr(), out.data_ptr(), x.data_ptr()
-b.wd, b.bd, b.w2_img, b.b2 = p["wd"].data_ptr(), p["bd"].data_ptr(), p["w2_img"].data_ptr(), p["b2"].data_ptr()
+b.taps, b.w2_img, b.b2 = p["taps16"].data_ptr(), p["w2_img"].data_ptr(), p["b2"].data_ptr()
 b.B, b.H, b.W, b.C, b.hidden = 32, H, H, C, 4 * C
 _lib.check(_lib.load().lw_leff2_fwd(Cx.byref(b), torch.cuda.current_stream().cuda_stream), "leff2")
 torch.cuda.synchronize()

@@ -33,7 +33,7 @@ class Leff1Args(C.Structure):
 
 
 class Leff2Args(C.Structure):
-    _fields_ = [("h1", C.c_void_p), ("out", C.c_void_p), ("resid", C.c_void_p), ("wd", C.c_void_p), ("bd", C.c_void_p),
+    _fields_ = [("h1", C.c_void_p), ("out", C.c_void_p), ("resid", C.c_void_p), ("taps", C.c_void_p),
                 ("w2_img", C.c_void_p), ("b2", C.c_void_p), ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
                 ("C", C.c_int32), ("hidden", C.c_int32), ("resid_fp32", C.c_int32), ("out_fp32", C.c_int32)]
 

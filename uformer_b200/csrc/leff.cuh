@@ -62,7 +62,7 @@ static_assert(sizeof(GemmMisc) <= 1024, "misc too large");
 // (two 16-lane fragments) and columns half*8NB .. +8NB.  tcol = TMEM address of the sub-chunk's first column,
 // ncol = its global N index.
 template <int NB, int EPI>
-__device__ __forceinline__ void ares_phase_a(const AResArgs& a, uint32_t tcol, int ncol, uint32_t bias_s, uint32_t stage_s, int pitch) {
+__device__ __forceinline__ void ares_phase_a(const AResArgs& a, uint32_t tcol, int ncol, uint32_t bias_s, uint32_t stage_s, int pitch, const GeluH2& gelu) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = warp & 3, half = warp >> 2, tq = lane & 3;
   constexpr int CPH = 8 * NB;
@@ -83,7 +83,8 @@ __device__ __forceinline__ void ares_phase_a(const AResArgs& a, uint32_t tcol, i
 #pragma unroll
   for (int hl = 0; hl < 2; ++hl) {
     uint32_t pk[2 * NB];
-    frag_bias_act_pack<NB, EPI == 0>(v[hl], bb, pk);
+    if (EPI == 0) frag_bias_gelu_h2<NB>(v[hl], bb, pk, gelu);          // LeFF hidden map: fp16 in HBM (internal buffer)
+    else frag_bias_act_pack<NB, false>(v[hl], bb, pk);
     stage_frag<NB>(stage_s, pitch, q * 32 + hl * 16, 0, pk);       // the column half owns a private staging tile
   }
 }
@@ -186,6 +187,8 @@ __global__ void __launch_bounds__(kThreads8, (K <= 128) ? 2 : 1) ares_kernel(con
       }
       worker_bar8();
     }
+    GeluH2 gelu;
+    gelu.init();
     const int sub_cols = a.nch < 128 ? a.nch : 128;          // 128 accumulator columns per pass: 64 per column half
     const int grp = warp >> 2;                               // column half == synchronisation group (128 threads)
     const int cph = sub_cols >> 1;
@@ -205,8 +208,8 @@ __global__ void __launch_bounds__(kThreads8, (K <= 128) ? 2 : 1) ares_kernel(con
         // ---- phase A: TMEM (16x256b fragments) -> (+bias, GELU) -> bf16 -> stmatrix into this column half's private
         // staging tile.  The two halves (warps 0-3 / 4-7) synchronise only among themselves, so one half's
         // copy-out overlaps the other half's GELU math. ----
-        if (sub_cols == 128) ares_phase_a<8, EPI>(a, tb + buf * Cfg::NCH_MAX + sc, nc * a.nch + sc, bias_s, stage_g, pitch_g);
-        else ares_phase_a<4, EPI>(a, tb + buf * Cfg::NCH_MAX + sc, nc * a.nch + sc, bias_s, stage_g, pitch_g);
+        if (sub_cols == 128) ares_phase_a<8, EPI>(a, tb + buf * Cfg::NCH_MAX + sc, nc * a.nch + sc, bias_s, stage_g, pitch_g, gelu);
+        else ares_phase_a<4, EPI>(a, tb + buf * Cfg::NCH_MAX + sc, nc * a.nch + sc, bias_s, stage_g, pitch_g, gelu);
         if (sc + 128 >= a.nch) {            // accumulator fully read: hand the buffer back to the issuer
           tc_fence_before();
           mbar_arrive(smem_u32(&ms.bar_d_empty[buf]));
@@ -246,13 +249,12 @@ __global__ void __launch_bounds__(kThreads8, (K <= 128) ? 2 : 1) ares_kernel(con
 // Arguments of the A-streamed kernels (leff2.cuh: depthwise conv producer; down.cuh: im2col producer)
 // =================================================================================================
 struct AStreamArgs {
-  const bf16* src;        // PROD 0: h1 (B,H,W,K)   PROD 1: x (B,H,W,Cin)
+  const bf16* src;        // PROD 0: h1 (B,H,W,K) — FP16 bits (the LeFF hidden map is half precision)   PROD 1: x (B,H,W,Cin) bf16
   int B, H, W;            // geometry of src
   int K;                  // PROD 0: hidden; PROD 1: 16*Cin
   int Cin;                // PROD 1 only
   int src_stride;         // PROD 1: row stride of src in elements (>= Cin: src may be a column slice of a wider buffer)
-  const float* wd;        // PROD 0: (9, K) taps
-  const float* bd;        // PROD 0: (K)
+  const uint16_t* taps;   // PROD 0: (10, K) fp16: 9 depthwise taps (tap = ky*3+kx), then the conv bias
   const uint8_t* w_img;   // [K/64][N/nch][nch*128B]
   int N, nch;
   const float* bias;      // (N)

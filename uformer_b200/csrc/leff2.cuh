@@ -1,4 +1,5 @@
-// leff2.cuh — LeFF part 2: out = resid + GELU(dwconv3x3(h1) + bd) W2^T + b2   (model.py:674-682)
+// leff2.cuh — LeFF part 2 (C = 512; narrower blocks use leff_fused.cuh): out = resid + GELU(dwconv3x3(h1) + bd) W2^T + b2
+// (model.py:674-682).  h1, the conv arithmetic (HFMA2), the GELU and the GEMM operands are HALF precision (fp16).
 //
 // PERSISTENT kernel: one CTA per SM walks 8 x 16 spatial tiles (128 tokens) round-robin.  512 threads in four
 // warpgroups; setmaxnreg moves registers from the light warpgroups (88) to the conv warpgroups (168):
@@ -27,7 +28,7 @@ struct Leff2Cfg {
   static constexpr int HALO_TOK = 180;                          // 10 x 18
   static constexpr int S_A = 0;                                 // 2 x 16 KB A k-block buffers
   static constexpr int S_HALO = 2 * 16384;                      // 2 x 23552 (180 x 128 B, padded)
-  static constexpr int S_WD = S_HALO + 2 * 23552;               // 2 x (10 x 64 fp32) = 2 x 2560 (+1024 pad)
+  static constexpr int S_WD = S_HALO + 2 * 23552;               // 2 x (10 x 64 fp16) = 2 x 1280 (region sized 2 x 2560 + 1024 pad)
   static constexpr int S_RING = S_WD + 2 * 2560 + 1024;         // = 86016, 1024-aligned
   static constexpr int S_STAGE = S_RING + STAGES * kStageBytes; // epilogue staging tile 128 x 272 B
   static constexpr int S_MISC = S_STAGE + 35840;
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(kL2Threads, 1) leff2_kernel(const AStreamArgs 
   } else if (warp == 9) {
     // ============================== issuer (warp-uniform; one elected lane issues) ==============================
     Ring ring{smem_u32(smem + Cfg::S_RING), smem_u32(&ms.bar_full[0]), smem_u32(&ms.bar_empty[0]), Cfg::STAGES, 0};
-    const uint32_t idesc = make_idesc_bf16(128, a.nch);
+    const uint32_t idesc = make_idesc_f16(128, a.nch);          // fp16 A (conv output) x fp16 W2 image
     const uint32_t ring_base = smem_u32(smem + Cfg::S_RING);
     const uint64_t b_desc0 = kmajor_desc<128>(ring_base);
     int g = 0, j = 0;
@@ -154,8 +155,10 @@ __global__ void __launch_bounds__(kL2Threads, 1) leff2_kernel(const AStreamArgs 
       const int t = idx >> 3, vv = idx & 7;
       pf_soff[i] = (idx < Cfg::HALO_TOK * 8) ? (uint32_t)(t * 128 + ((vv ^ (t & 7)) * 16)) : 0xffffffffu;   // chunk XOR-swizzled by token
     }
-    const int tw_row = tid >> 4, tw_vec = tid & 15;
-    const float* tw_src = (tw_row < 9) ? a.wd + (size_t)tw_row * a.K + tw_vec * 4 : a.bd + tw_vec * 4;
+    const int tw_row = tid >> 3, tw_vec = tid & 7;                   // taps: 10 rows x 8 vectors of 8 halves per 64-channel slice
+    const uint16_t* tw_src = a.taps + (size_t)(tw_row < 10 ? tw_row : 0) * a.K + tw_vec * 8;
+    GeluH2 gelu;
+    gelu.init();
 
     // global element offsets of the halo vectors of a tile (0xffffffff: outside the image -> zero fill)
     auto tile_desc = [&](int tile, uint32_t* goff) {
@@ -179,7 +182,7 @@ __global__ void __launch_bounds__(kL2Threads, 1) leff2_kernel(const AStreamArgs 
           cp_async16(hb + pf_soff[i], ok ? a.src + goff[i] + kb * 64 : a.src, ok ? 16u : 0u);
         }
       }
-      if (tid < 160) cp_async16(wd0 + bufi * 2560 + tid * 16, tw_src + kb * 64, 16u);
+      if (tid < 80) cp_async16(wd0 + bufi * 2560 + tid * 16, tw_src + kb * 64, 16u);
       cp_async_commit();
     };
 
@@ -196,39 +199,32 @@ __global__ void __launch_bounds__(kL2Threads, 1) leff2_kernel(const AStreamArgs 
         else if (next_tile < n_tiles) { tile_desc(next_tile, gnext); prefetch(gnext, 0, (g + 1) & 1); }
         const uint32_t sH = halo0 + ab * 23552;
         const uint32_t sW = wd0 + ab * 2560;
-        // accumulators start at the conv bias of this octet
-        f2 acc[4][4];
+        // accumulators start at the conv bias of this octet; packed-half arithmetic (h1 is fp16: no unpacking, 2 channels per op)
+        h2 acc[4][4];
         {
-          const float4 b0 = lds128f(sW + (9 * 64 + v * 8) * 4);
-          const float4 b1 = lds128f(sW + (9 * 64 + v * 8 + 4) * 4);
+          const uint4 b0 = lds128(sW + (9 * 64 + v * 8) * 2);
 #pragma unroll
-          for (int o = 0; o < 4; ++o) {
-            acc[o][0] = f2_pack(b0.x, b0.y); acc[o][1] = f2_pack(b0.z, b0.w);
-            acc[o][2] = f2_pack(b1.x, b1.y); acc[o][3] = f2_pack(b1.z, b1.w);
-          }
+          for (int o = 0; o < 4; ++o) { acc[o][0] = b0.x; acc[o][1] = b0.y; acc[o][2] = b0.z; acc[o][3] = b0.w; }
         }
         // column by column (dx): pull the 6 halo rows of that column into registers once, then apply the three
         // taps (ky) that touch them; halo row r feeds output row o = r - ky.
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx) {
-          f2 h[6][4];
+          uint4 h[6];
 #pragma unroll
           for (int r = 0; r < 6; ++r) {
             const int t = (hf * 4 + r) * 18 + cx + dx;
-            const uint4 raw = lds128(sH + t * 128 + ((v ^ (t & 7)) * 16));
-            h[r][0] = bf2_to_f2(raw.x); h[r][1] = bf2_to_f2(raw.y); h[r][2] = bf2_to_f2(raw.z); h[r][3] = bf2_to_f2(raw.w);
+            h[r] = lds128(sH + t * 128 + ((v ^ (t & 7)) * 16));
           }
 #pragma unroll
           for (int ky = 0; ky < 3; ++ky) {
-            const float4 w0 = lds128f(sW + ((ky * 3 + dx) * 64 + v * 8) * 4);        // warp-uniform address: broadcast
-            const float4 w1 = lds128f(sW + ((ky * 3 + dx) * 64 + v * 8 + 4) * 4);
-            const f2 wa = f2_pack(w0.x, w0.y), wb = f2_pack(w0.z, w0.w), wc = f2_pack(w1.x, w1.y), wd = f2_pack(w1.z, w1.w);
+            const uint4 w = lds128(sW + ((ky * 3 + dx) * 64 + v * 8) * 2);            // warp-uniform address: broadcast
 #pragma unroll
             for (int o = 0; o < 4; ++o) {
-              acc[o][0] = f2_fma(h[o + ky][0], wa, acc[o][0]);
-              acc[o][1] = f2_fma(h[o + ky][1], wb, acc[o][1]);
-              acc[o][2] = f2_fma(h[o + ky][2], wc, acc[o][2]);
-              acc[o][3] = f2_fma(h[o + ky][3], wd, acc[o][3]);
+              acc[o][0] = h2_fma(h[o + ky].x, w.x, acc[o][0]);
+              acc[o][1] = h2_fma(h[o + ky].y, w.y, acc[o][1]);
+              acc[o][2] = h2_fma(h[o + ky].z, w.z, acc[o][2]);
+              acc[o][3] = h2_fma(h[o + ky].w, w.w, acc[o][3]);
             }
           }
         }
@@ -238,10 +234,10 @@ __global__ void __launch_bounds__(kL2Threads, 1) leff2_kernel(const AStreamArgs 
 #pragma unroll
         for (int o = 0; o < 4; ++o) {
           uint4 pk;
-          pk.x = f2_to_bf2(gelu2(acc[o][0]));
-          pk.y = f2_to_bf2(gelu2(acc[o][1]));
-          pk.z = f2_to_bf2(gelu2(acc[o][2]));
-          pk.w = f2_to_bf2(gelu2(acc[o][3]));
+          pk.x = gelu(acc[o][0]);
+          pk.y = gelu(acc[o][1]);
+          pk.z = gelu(acc[o][2]);
+          pk.w = gelu(acc[o][3]);
           const int rr = (hf * 4 + o) * 16 + cx;
           sts128(sA + swz<128>(rr, v * 16), pk);
         }

@@ -37,7 +37,7 @@ static bool all_aligned16(P... ps) {
   return ok;
 }
 
-extern "C" int lw_abi_version(void) { return 3; }
+extern "C" int lw_abi_version(void) { return 4; }
 extern "C" const char* lw_last_cuda_error(void) { return g_err; }
 extern "C" int lw_check_device(void) {
   int dev = 0, major = 0;
@@ -205,12 +205,12 @@ extern "C" int lw_upsample_fwd(const lw_up_args* p, lw_stream_t stream) {
 
 // ------------------------------------------------------------------------------------------------
 extern "C" int lw_leff2_fwd(const lw_leff2_args* p, lw_stream_t stream) {
-  if (!p || !p->h1 || !p->out || !p->wd || !p->bd || !p->w2_img || !p->b2) return LW_ERR_NULL;
+  if (!p || !p->h1 || !p->out || !p->taps || !p->w2_img || !p->b2) return LW_ERR_NULL;
   if (p->B <= 0 || p->H <= 0 || p->W < 8 || p->hidden % 64 || p->C % 16 || p->C > 512) return LW_ERR_BAD_SHAPE;
-  if (!all_aligned16(p->h1, p->out, p->resid, p->wd, p->bd, p->w2_img, p->b2)) return LW_ERR_ALIGN;
+  if (!all_aligned16(p->h1, p->out, p->resid, p->taps, p->w2_img, p->b2)) return LW_ERR_ALIGN;
   AStreamArgs a{};
   a.src = reinterpret_cast<const bf16*>(p->h1); a.B = p->B; a.H = p->H; a.W = p->W; a.K = p->hidden;
-  a.wd = p->wd; a.bd = p->bd; a.w_img = reinterpret_cast<const uint8_t*>(p->w2_img);
+  a.taps = reinterpret_cast<const uint16_t*>(p->taps); a.w_img = reinterpret_cast<const uint8_t*>(p->w2_img);
   a.N = p->C; a.nch = p->C < 128 ? p->C : 128; a.bias = p->b2;
   a.resid = reinterpret_cast<const bf16*>(p->resid); a.out = reinterpret_cast<bf16*>(p->out);
   a.resid_fp32 = p->resid_fp32; a.out_fp32 = p->out_fp32;

@@ -275,6 +275,19 @@ __device__ __forceinline__ void frag_bias_act_pack(const uint32_t* v, const f2* 
   }
 }
 
+// The same for the LeFF hidden map, which is kept in HALF precision (fp16, 11-bit significand) between linear1 and the
+// depthwise conv: + bias (fp32) -> f16x2 -> packed-half GELU.  Output words are f16x2.
+template <int NB>
+__device__ __forceinline__ void frag_bias_gelu_h2(const uint32_t* v, const f2* bb, uint32_t* pk, const GeluH2& gelu) {
+#pragma unroll
+  for (int i = 0; i < NB; ++i) {
+    const f2 x0 = f2_add(f2_pack(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1])), bb[i]);
+    const f2 x1 = f2_add(f2_pack(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])), bb[i]);
+    pk[2 * i] = gelu(h2_from_f2(x0));
+    pk[2 * i + 1] = gelu(h2_from_f2(x1));
+  }
+}
+
 __device__ __forceinline__ uint4 add_bf16x8(const uint4& a, const uint4& b) {
   float fa[8], fb[8];
   unpack8(a, fa);
@@ -329,7 +342,8 @@ __device__ __forceinline__ void store_staged_rows_mixed_t(uint32_t stage_s, int 
                                                           size_t row_stride, int col0, int tid) {
   const int vshift = ncols_log2 - 3;
   const int total = 128 << vshift;
-  constexpr int ITER = 4;                       // vectors in flight per thread: all loads of a pass are issued before any use
+  constexpr int ITER = (NT == 128) ? 2 : 4;     // vectors in flight per thread (all loads of a pass are issued before any use); the
+                                                // 128-thread callers are the 88-register epilogue warps of the persistent kernels
 #pragma unroll 1
   for (int i0 = tid; i0 < total; i0 += NT * ITER) {
     int tok[ITER];

@@ -250,9 +250,8 @@ class LeFF(nn.Module):
                                             wdw, bdw, w2, b2, _lib.load().lw_leff_slice(self.dim))
                 d["ln_eps"] = eps
                 return d
-            wd, bd = packing.pack_dwconv(wdw, bdw)
             d = dict(w1_img=packing.pack_kmajor(w1, _lib.load().lw_nch_ares(self.dim, self.hidden_dim), "nk"), b1=b1.float().contiguous(),
-                     wd=wd, bd=bd, w2_img=packing.pack_kmajor(w2, min(self.dim, 128), "kn"),
+                     taps16=packing.pack_dwconv16(wdw, bdw), w2_img=packing.pack_kmajor(w2, min(self.dim, 128), "kn", torch.float16),
                      b2=b2.float().contiguous(), hidden=self.hidden_dim, ln_eps=eps)
             if norm is not None:
                 d.update(ln_w=norm.weight.float().contiguous(), ln_b=norm.bias.float().contiguous())

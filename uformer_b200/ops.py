@@ -132,7 +132,7 @@ def _leff_two_kernels(x: Tensor, p: dict, *, B: int, H: int, W: int, resid: Tens
     _check_act(x, "x")
     Cc, hidden = x.shape[-1], p["hidden"]
     n_tokens = B * H * W
-    h1 = torch.empty((n_tokens, hidden), dtype=torch.bfloat16, device=x.device)
+    h1 = torch.empty((n_tokens, hidden), dtype=torch.float16, device=x.device)      # the hidden map is half precision between the two kernels
     a = _lib.Leff1Args()
     a.x, a.h1, a.ln_w, a.ln_b = _ptr(x), _ptr(h1), _ptr(p.get("ln_w")), _ptr(p.get("ln_b"))
     a.w1_img, a.b1 = _ptr(p["w1_img"]), _ptr(p["b1"])
@@ -146,7 +146,7 @@ def _leff_two_kernels(x: Tensor, p: dict, *, B: int, H: int, W: int, resid: Tens
     b = _lib.Leff2Args()
     b.h1, b.out, b.resid = _ptr(h1), _ptr(out), _ptr(resid)
     b.resid_fp32, b.out_fp32 = int(resid is not None and resid.dtype == torch.float32), int(out.dtype == torch.float32)
-    b.wd, b.bd, b.w2_img, b.b2 = _ptr(p["wd"]), _ptr(p["bd"]), _ptr(p["w2_img"]), _ptr(p["b2"])
+    b.taps, b.w2_img, b.b2 = _ptr(p["taps16"]), _ptr(p["w2_img"]), _ptr(p["b2"])
     b.B, b.H, b.W, b.C, b.hidden = B, H, W, Cc, hidden
     _launch(f"leff2_C{Cc}_T{n_tokens}", 2.0 * n_tokens * (hidden * Cc + 9 * hidden), lambda st: lib.lw_leff2_fwd(C.byref(b), st), "lw_leff2_fwd", x.device)
     return out

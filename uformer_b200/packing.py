@@ -33,13 +33,14 @@ def _swizzle128_perm(nch: int, device) -> Tensor:
     return perm
 
 
-def pack_kmajor(w: Tensor, nch: int, order: str = "nk") -> Tensor:
+def pack_kmajor(w: Tensor, nch: int, order: str = "nk", dtype=torch.bfloat16) -> Tensor:
     """(N, K) -> bf16 images.  order "nk": [N/nch][KB][nch*64] (A-resident kernels iterate N outer),
     order "kn": [KB][N/nch][nch*64] (A-streamed kernels iterate K outer)."""
     N, K = w.shape
     assert N % nch == 0, (N, nch)
     KB = (K + 63) // 64
-    wp = w.to(torch.bfloat16)                         # round first: the permutation then moves half the bytes
+    wp = w.to(dtype)                                  # round first: the permutation then moves half the bytes (bf16, or fp16 for
+                                                      # the LeFF linear2 operand, which meets a half-precision hidden map)
     if KB * 64 != K:
         wp = torch.nn.functional.pad(wp, (0, KB * 64 - K))
     perm = _swizzle128_perm(nch, w.device).reshape(-1)
@@ -147,6 +148,12 @@ def pack_dwconv(w: Tensor, b: Tensor):
     """Conv2d(groups=hidden) weight (hidden,1,3,3) -> taps (9, hidden) fp32; bias fp32."""
     hid = w.shape[0]
     return w.float().reshape(hid, 9).t().contiguous(), b.float().contiguous()
+
+
+def pack_dwconv16(w: Tensor, b: Tensor) -> Tensor:
+    """Two-kernel LeFF (lw_leff2_fwd): (10, hidden) fp16 — the 9 taps (tap = ky*3+kx), then the bias row."""
+    wd, bd = pack_dwconv(w, b)
+    return torch.cat([wd, bd[None, :]], 0).to(torch.float16).contiguous()
 
 
 def pack_downsample(w: Tensor, nch: int) -> Tensor:

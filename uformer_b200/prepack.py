@@ -80,7 +80,8 @@ def _pack_blocks(blks):
     else:
         nch1 = lib.lw_nch_ares(C, hid)
         w1_img = packing.pack_kmajor(w1.view(nb * hid, C), nch1, "nk").view(nb, hid // nch1, -1, nch1 * 64)
-        w2_nk = packing.pack_kmajor(w2.view(nb * C, hid), nchp, "nk").view(nb, C // nchp, -1, nchp * 64)
+        w2_nk = packing.pack_kmajor(w2.view(nb * C, hid), nchp, "nk", torch.float16).view(nb, C // nchp, -1, nchp * 64)
+        taps16 = torch.cat([wd, bdw[:, None, :]], 1).to(torch.float16).contiguous()      # (nb, 10, hid)
         w2_img = w2_nk.permute(0, 2, 1, 3).contiguous()                                 # per block [KB][C/nch][nch*64]
 
     for i, b in enumerate(blks):
@@ -93,7 +94,7 @@ def _pack_blocks(blks):
             d = dict(w1f_img=w1f_img[i], b1f=b1f[i], cs=cs[i], taps=taps[i], w2f_img=w2f_img[i], b2=b2, hidden=hid, has_ln=True,
                      slice=sl, ln_eps=b.norm2.eps)
         else:
-            d = dict(w1_img=w1_img[i], b1=m.linear1[0].bias.detach().float().contiguous(), wd=wd[i], bd=bd, w2_img=w2_img[i], b2=b2,
+            d = dict(w1_img=w1_img[i], b1=m.linear1[0].bias.detach().float().contiguous(), taps16=taps16[i], w2_img=w2_img[i], b2=b2,
                      hidden=hid, ln_eps=b.norm2.eps, ln_w=b.norm2.weight.detach().float().contiguous(),
                      ln_b=b.norm2.bias.detach().float().contiguous())
         m._cache_ln.put(m.pack_sources() + [b.norm2.weight, b.norm2.bias], d)
