@@ -13,8 +13,6 @@ the restated statements are replaced by hand-written kernels next round.
 """
 from __future__ import annotations
 
-import os
-
 import torch
 
 Tensor = torch.Tensor
@@ -57,48 +55,6 @@ class NativeFn(torch.autograd.Function):
         return (None, None, None, *res)
 
 
-class BlockFn(torch.autograd.Function):
-    """LeWin block with the explicit backward of uformer_b200/block_bwd.py (opt-in, see use_explicit_block_backward).
-    tensors = [x, (scale1, scale2)?, (mask)?] + parameters in `names` order."""
-
-    @staticmethod
-    def forward(ctx, run_native, blk, layout, names, *tensors):
-        ctx.blk, ctx.layout, ctx.names = blk, layout, names
-        n_act = 1 + (2 if layout[0] else 0) + (1 if layout[1] else 0)
-        ctx.n_act = n_act
-        with torch.no_grad():
-            out = run_native(*tensors[:n_act])
-        ctx.save_for_backward(*tensors[:n_act])
-        return out
-
-    @staticmethod
-    def backward(ctx, g):
-        from . import block_bwd
-        acts = ctx.saved_tensors
-        has_dp, has_mask = ctx.layout
-        x = acts[0]
-        s1, s2 = (acts[1], acts[2]) if has_dp else (None, None)
-        mask = acts[-1] if has_mask else None
-        cd = torch.bfloat16 if autocast_enabled(g.device.type) else torch.float32
-        dx, grads = block_bwd.lewin_block_bwd(ctx.blk, x, g, mask, s1, s2, cd=cd, need_dx=ctx.needs_input_grad[4])
-        need = ctx.needs_input_grad[4 + ctx.n_act:]
-        pg = [grads.get(n) if need[i] else None for i, n in enumerate(ctx.names)]
-        return (None, None, None, None, dx, *([None] * (ctx.n_act - 1)), *pg)
-
-
-_EXPLICIT = [os.environ.get("UFORMER_B200_EXPLICIT_BWD", "0") == "1"]
-
-
-def use_explicit_block_backward(on: bool = True):
-    """Select the explicit block backward (block_bwd.py) instead of autograd over the restated block.  Off by default:
-    the autograd recompute is the path validated on the B200 this round."""
-    _EXPLICIT[0] = bool(on)
-
-
-def explicit_block_backward() -> bool:
-    return _EXPLICIT[0]
-
-
 _AUTOCAST = {"cuda": True, "cpu": False}
 
 
@@ -119,17 +75,6 @@ def trainable_tensors(mod):
             if p is not None and p.requires_grad and id(p) not in seen:
                 seen.add(id(p))
                 out.append(p)
-    return out
-
-
-def named_trainable_tensors(mod):
-    """(dotted name, tensor) pairs in `named_parameters` order; replica-aware like trainable_tensors."""
-    out, seen = [], set()
-    for prefix, m in mod.named_modules():
-        for k, p in list(m._parameters.items()) + list(getattr(m, "_former_parameters", {}).items()):
-            if p is not None and p.requires_grad and id(p) not in seen:
-                seen.add(id(p))
-                out.append(((prefix + "." if prefix else "") + k, p))
     return out
 
 

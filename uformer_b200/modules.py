@@ -445,13 +445,7 @@ class LeWinTransformerBlock(nn.Module):
             a1, a2, m = split(rest)
             return restated.lewin_block(self, t, m, a1, a2)
 
-        res = None
-        if autograd.explicit_block_backward() and torch.is_grad_enabled():
-            named = autograd.named_trainable_tensors(self)
-            if autograd.wants_grad(xb, *[p for _, p in named]):
-                res = autograd.BlockFn.apply(native, self, (has_dp, has_mask), tuple(k for k, _ in named), *acts, *[p for _, p in named])
-        if res is None:
-            res = _run(self, native, restate, acts)
+        res = _run(self, native, restate, acts)
         return res if back is None else res.to(back)
 
     @torch.no_grad()
