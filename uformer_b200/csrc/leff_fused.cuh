@@ -230,9 +230,11 @@ __global__ void __launch_bounds__(kLFThreads, 1) leff_fused_kernel(const __grid_
             tma_load_4d(smem_u32(smem + Cfg::S_A1 + ab * Cfg::A1_BYTES + kb * Cfg::A1_KB_BYTES), &xmap, kb * 64, tx * 16 - 1, ty * 8 - 1, b, bar);
         };
         if (my_tiles > 0) load_x(0);
+        // (slice, tile) counters are advanced incrementally: NS is a runtime value and an integer division per iteration costs
+        // ~25 instructions on warps that issue one instruction every ~8 cycles
+        int j = 0, it = 0, j2 = 0;
         for (int k = 0; k < total + 2; ++k) {
           if (k < total) {
-            const int j = k % NS, it = k / NS;
             if (j == 0) {
               if (Cfg::NA1 == 2) { if (it + 1 < my_tiles) load_x(it + 1); }
               else if (it > 0) load_x(it);
@@ -249,17 +251,19 @@ __global__ void __launch_bounds__(kLFThreads, 1) leff_fused_kernel(const __grid_
               ring.load(a.w1_img + (size_t)(j + 1) * Cfg::W1_CHUNK, Cfg::W1_CHUNK);        // ... and 2-3
             }
           }
-          if (k >= 2) ring.load(a.w2_img + (size_t)((k - 2) % NS) * Cfg::W2_CHUNK, Cfg::W2_CHUNK);
+          if (k >= 2) { ring.load(a.w2_img + (size_t)j2 * Cfg::W2_CHUNK, Cfg::W2_CHUNK); if (++j2 == NS) j2 = 0; }
+          if (k < total && ++j == NS) { j = 0; ++it; }
         }
       }
     } else if (warp == 13) {
       // ============================== issuer (warp-uniform; one elected lane issues) ==============================
       Ring ring{smem_u32(smem + Cfg::S_RING), smem_u32(&ms.bar_full[0]), smem_u32(&ms.bar_empty[0]), Cfg::STAGES, 0};
       constexpr uint32_t idesc_g1a = make_idesc_bf16(128, Cfg::G1N), idesc_g1b = make_idesc_bf16(64, Cfg::G1N), idesc_g2 = make_idesc_f16(128, C);
+      int j1 = 0, it1 = 0, j2 = 0, it2 = 0;                 // (slice, tile) of the GEMM-1 / GEMM-2 being issued
       for (int k = 0; k < total + 2; ++k) {
         if (k < total && (!Cfg::PAIR || (k & 1) == 0)) {
           // ---- GEMM-1 of slice k (PAIR: of slices k, k+1): D1[buffer] = X W1'^T ----
-          const int j = k % NS, it = k / NS, ab = it % Cfg::NA1;
+          const int j = j1, it = it1, ab = it % Cfg::NA1;
           const int db = Cfg::PAIR ? ((k >> 1) & 1) : (k & 1), use = Cfg::PAIR ? (k >> 2) : (k >> 1);
           if (j == 0) { mbar_wait(smem_u32(&ms.bar_x_full[ab]), (it / Cfg::NA1) & 1); }
           mbar_wait(smem_u32(&ms.bar_d1_empty[db]), (use & 1) ^ 1);
@@ -293,7 +297,7 @@ __global__ void __launch_bounds__(kLFThreads, 1) leff_fused_kernel(const __grid_
         }
         if (k >= 2) {
           // ---- GEMM-2 of slice g = k-2: D2[tile & 1] += A2[g&1] W2_j^T ----
-          const int g = k - 2, j = g % NS, it = g / NS, ob = it % Cfg::ND2, ab2 = g & 1;
+          const int g = k - 2, j = j2, it = it2, ob = it % Cfg::ND2, ab2 = g & 1;
           if (j == 0) { mbar_wait(smem_u32(&ms.bar_d2_empty[ob]), ((it / Cfg::ND2) & 1) ^ 1); }
           mbar_wait(smem_u32(&ms.bar_a2_full[ab2]), (g >> 1) & 1);
           tc_fence_after();
@@ -311,7 +315,9 @@ __global__ void __launch_bounds__(kLFThreads, 1) leff_fused_kernel(const __grid_
             if (j == NS - 1) umma_commit(smem_u32(&ms.bar_d2_full[ob]));
           }
           __syncwarp();
+          if (++j2 == NS) { j2 = 0; ++it2; }
         }
+        if (k < total && ++j1 == NS) { j1 = 0; ++it1; }
       }
     }
     // (warps 14, 15 are spares: the LayerNorm statistics are computed by the epilogue warps, see below)
@@ -333,8 +339,9 @@ __global__ void __launch_bounds__(kLFThreads, 1) leff_fused_kernel(const __grid_
     // 128 + 16q of the M=64 part (its 64 rows sit 16 per lane quadrant).  SL = 64: 6 pieces, 3 per group.  SL = 32: 3 pieces:
     // group g takes fragment g whole and one 16-column half of fragment 2.
     constexpr int HP = SL / 32;
-    for (int k = 0; k < total; ++k) {
-      const int j = k % NS, it = k / NS, db = k & 1, sb = it & 1;                       // db: halo buffer
+    int j = 0, it = 0;
+    for (int k = 0; k < total; ++k, j = (j + 1 == NS ? 0 : j + 1), it += (j == 0)) {
+      const int db = k & 1, sb = it & 1;                                              // db: halo buffer
       const int d1b = Cfg::PAIR ? ((k >> 1) & 1) : (k & 1), d1use = Cfg::PAIR ? (k >> 2) : (k >> 1);   // D1 accumulator buffer
       if (j == 0) {
         // ---- LayerNorm statistics of the new tile's 192 rows, 24 rows per epilogue warp, straight from the landed A tile.
@@ -585,6 +592,7 @@ __global__ void __launch_bounds__(kLFThreads, 1) leff_fused_kernel(const __grid_
       if (tid == 0) { LF_TRACE(6, 3 * it + 2) }
     };
 
+    int cj = 0, cit = 0;                                    // (slice, tile) of the conv iteration
     for (int k = 0; k < total; ++k) {
       const int hbi = k & 1, tbuf = k % Cfg::NTAP;
       const uint32_t sH = halo0 + hbi * Cfg::HALO_BYTES;
@@ -640,10 +648,8 @@ __global__ void __launch_bounds__(kLFThreads, 1) leff_fused_kernel(const __grid_
       if (tid == 0) { LF_TRACE(2, 4 * k + 3) }
       // the previous tile's output epilogue runs one or two slices into this tile (its GEMM-2 chain has drained by then;
       // with a single D2 buffer it must run before this tile's second GEMM-2 can be issued)
-      {
-        const int j = k % NS, it = k / NS;
-        if (it > 0 && j == ((NS > 1 && Cfg::ND2 == 2) ? 1 : 0)) epilogue2(it - 1);
-      }
+      if (cit > 0 && cj == ((NS > 1 && Cfg::ND2 == 2) ? 1 : 0)) epilogue2(cit - 1);
+      if (++cj == NS) { cj = 0; ++cit; }
     }
     if (my_tiles > 0) epilogue2(my_tiles - 1);
   }
