@@ -132,15 +132,15 @@ def _trainstep_worker(rank, world, port, out):
     from paramgen import randomize_state
     cfg = dict(img_size=128, embed_dim=16, depths=[1] * 9, win_size=8, modulator=True, drop_path_rate=0.0)
 
-    def build():
+    def build(seed=9):
         net = U.Uformer(**cfg)
-        net.load_state_dict(randomize_state(net.state_dict(), 9), strict=True)
+        net.load_state_dict(randomize_state(net.state_dict(), seed), strict=True)
         return net
     torch.manual_seed(0)
     clean = torch.rand(2, 3, 128, 128)
     noisy = (clean + 0.1 * torch.randn_like(clean)).clamp(0, 1)
     with KM.patched():
-        net = build()
+        net = build(9 + rank)                     # ranks initialise DIFFERENTLY: TrainStep must start everyone from rank 0's weights
         step = TrainStep(net, lr=1e-4, bucket_bytes=1 << 20)
         assert step.world == world and len(step.reducer.buckets) > 2
         for _ in range(2):
@@ -153,9 +153,8 @@ def _trainstep_worker(rank, world, port, out):
         if rank == 0:
             # single-process reference: same two steps on the full batch, no process group involved
             ref = build()
-            rs = TrainStep(ref, lr=1e-4)
-            rs.reducer.remove_hooks()
-            rs.reducer.world = rs.world = 1
+            rs = TrainStep(ref, lr=1e-4, data_parallel=False)
+            assert rs.world == 1
             for _ in range(2):
                 rs(noisy, clean)
             err = ((rs.arena.flat - flat).norm() / rs.arena.flat.norm()).item()
@@ -175,5 +174,5 @@ def test_trainstep_data_parallel_equals_full_batch():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    assert same                      # every rank applied the same update (no weight broadcast needed)
+    assert same                      # rank 0's weights were broadcast at construction and every rank applied the same update
     assert err < 2e-3                # == training on the whole batch (Adam's 1/sqrt(v) amplifies fp32 summation-order noise)

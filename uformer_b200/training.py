@@ -104,10 +104,10 @@ class GradReducer:
     it overlaps the rest of backward).  `finish()` launches whatever did not fire (unused parameters) and waits.
     The division by world size is folded into the optimizer kernel (FlatAdamW.step(grad_scale=1/world))."""
 
-    def __init__(self, arena: FlatArena, process_group=None, bucket_bytes: int = 32 << 20):
+    def __init__(self, arena: FlatArena, process_group=None, bucket_bytes: int = 32 << 20, enabled: bool = True):
         self.arena = arena
         self.group = process_group
-        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.world = dist.get_world_size(process_group) if enabled and dist.is_available() and dist.is_initialized() else 1
         self.buckets = []                # (lo, hi, [param indices])
         lo, members = 0, []
         for i, (p, o) in enumerate(zip(arena.params, arena.offsets)):
@@ -244,15 +244,33 @@ class TrainStep:
     """
 
     def __init__(self, net: nn.Module, lr: float = 2e-4, weight_decay: float = 0.02, betas=(0.9, 0.999), eps: float = 1e-8,
-                 process_group=None, bucket_bytes: int = 32 << 20, criterion: nn.Module | None = None, batched_repack: bool = True):
+                 process_group=None, bucket_bytes: int = 32 << 20, criterion: nn.Module | None = None, batched_repack: bool = True,
+                 data_parallel: bool = True):
+        """data_parallel=False: a purely local step even inside an initialised process group (no all-reduce, no broadcast)."""
         self.net = net
         self.batched_repack = batched_repack
         params = execution_ordered_parameters(net)[::-1]                 # reverse execution order
         self.arena = FlatArena(params)
-        self.reducer = GradReducer(self.arena, process_group, bucket_bytes)
+        self.reducer = GradReducer(self.arena, process_group, bucket_bytes, enabled=data_parallel)
         self.optimizer = FlatAdamW(self.arena, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
         self.criterion = criterion if criterion is not None else CharbonnierLoss()
         self.world = self.reducer.world
+        self.sync_from_rank0()
+
+    def sync_from_rank0(self):
+        """Make every rank start from rank 0's weights and optimizer state (ranks that initialise differently — rank-dependent
+        seeds, a partial checkpoint load — would otherwise silently train diverged replicas: the update is applied locally on
+        every rank from the all-reduced gradient, weights are never re-broadcast).  nn.DataParallel did this every iteration by
+        replicating GPU 0's module (train/train_denoise.py:83)."""
+        if self.world > 1:
+            group = self.reducer.group
+            dist.broadcast(self.arena.flat, src=0, group=group)
+            dist.broadcast(self.optimizer.exp_avg, src=0, group=group)
+            dist.broadcast(self.optimizer.exp_avg_sq, src=0, group=group)
+            steps = torch.tensor([self.optimizer.steps], dtype=torch.int64, device=self.arena.flat.device)
+            dist.broadcast(steps, src=0, group=group)
+            self.optimizer.steps = int(steps.item())
+            modules.invalidate_packed()
 
     def __call__(self, input_: Tensor, target: Tensor) -> Tensor:
         self.net.train()
@@ -274,16 +292,22 @@ class TrainStep:
                     optimizer={k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in self.optimizer.state_dict().items()})
 
     def load_state_dict(self, st):
+        """`st["state_dict"]` may be a reference checkpoint's (keys with the DataParallel `module.` prefix are accepted, like
+        utils/model_utils.py:23-33 does); `st["optimizer"]` (optional) is this class's arena-layout moment dict — the reference's
+        torch.optim.AdamW per-parameter state is a different layout and is not loadable here (resume then restarts the moments)."""
+        sd = {(k[7:] if k.startswith("module.") else k): v for k, v in st["state_dict"].items()}
         with torch.no_grad():
             own = self.net.state_dict()
-            missing = set(own) ^ set(st["state_dict"])
+            missing = set(own) ^ set(sd)
             if missing:
                 raise KeyError(f"checkpoint / model key mismatch: {sorted(missing)[:5]}")
-            for k, v in st["state_dict"].items():
+            for k, v in sd.items():
                 own[k].copy_(v)                                      # in place: the arena views stay intact
-        self.optimizer.load_state_dict(st["optimizer"])
+        if st.get("optimizer") is not None and "exp_avg" in st["optimizer"]:
+            self.optimizer.load_state_dict(st["optimizer"])
         self.arena.zero_grad()
         modules.invalidate_packed()
+        self.sync_from_rank0()
 
 
 __all__ = ["FlatArena", "GradReducer", "FlatAdamW", "CharbonnierLoss", "TrainStep", "mixup",
