@@ -1,9 +1,9 @@
 #!/bin/bash
 # One gpurun call that collects a round's evidence into gpurun_out/ (every stage under its own timeout, later stages
 # still run if an earlier one fails).  Usage on the GPU box:
-#   bash tools/collect_round.sh [tag] [stages]      stages: any of  tests bench b512 wmsa ncu full   (default: all)
+#   bash tools/collect_round.sh [tag] [stages]      stages: any of  tests smoke bench b512 wmsa ncu full   (default: all)
 tag=${1:-rXX}
-stages=${2:-"tests bench b512 wmsa ncu full"}
+stages=${2:-"tests smoke bench b512 wmsa ncu full"}
 out=gpurun_out
 mkdir -p $out
 has() { [[ " $stages " == *" $1 "* ]]; }
@@ -11,6 +11,9 @@ if has tests; then      # the WHOLE gpu suite, no -x
   timeout 500 python -m pytest tests -m gpu -v -s -p no:cacheprovider > $out/${tag}_gpu_tests.log 2>&1
   echo "pytest rc=$?" >> $out/${tag}_gpu_tests.log
   grep -E "passed|failed|error" $out/${tag}_gpu_tests.log | tail -3
+fi
+if has smoke; then      # what the driver runs before the bench
+  timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $out/${tag}_smoke.log 2>&1; echo "smoke rc=$?"; tail -3 $out/${tag}_smoke.log
 fi
 if has bench; then
   timeout 400 python bench.py > $out/${tag}_bench_fwd.json 2> $out/${tag}_bench_fwd.err; echo "bench fwd rc=$?"
