@@ -172,9 +172,9 @@ __device__ __forceinline__ h2 h2_tanh(h2 a) {
   asm("tanh.approx.f16x2 %0, %1;" : "=r"(d) : "r"(a));
   return d;
 }
-__device__ __forceinline__ h2 h2_from_f32(float lo, float hi) {       // round-to-nearest pack
+__device__ __forceinline__ h2 h2_from_f32(float lo, float hi) {       // round-to-nearest pack, saturating at +-65504 (one F2FP)
   h2 d;
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
   return d;
 }
 __device__ __forceinline__ h2 h2_from_f2(f2 v) {
