@@ -175,8 +175,9 @@ __global__ void __launch_bounds__(kLFThreads, 1) leff_fused_kernel(const __grid_
   if (tid == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(smem_u32(&ms.bar_full[s]), 1); mbar_init(smem_u32(&ms.bar_empty[s]), 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(smem_u32(&ms.bar_x_full[i]), 1);  mbar_init(smem_u32(&ms.bar_x_empty[i]), 9);      // GEMM-1 commit + 8 epilogue warps (stats)
-      mbar_init(smem_u32(&ms.bar_st_full[i]), 8); mbar_init(smem_u32(&ms.bar_st_empty[i]), 8);     // one lane per epilogue warp
+      mbar_init(smem_u32(&ms.bar_x_full[i]), 1);  mbar_init(smem_u32(&ms.bar_x_empty[i]), 257);    // GEMM-1 commit + 256 epilogue threads (stats)
+      mbar_init(smem_u32(&ms.bar_st_full[i]), 256); mbar_init(smem_u32(&ms.bar_st_empty[i]), 8);   // every epilogue thread (each
+                                                                                                   // releases its own writes)
       mbar_init(smem_u32(&ms.bar_d1_full[i]), 1); mbar_init(smem_u32(&ms.bar_d1_empty[i]), Cfg::PAIR ? 512 : 256);
       mbar_init(smem_u32(&ms.bar_h_full[i]), 256); mbar_init(smem_u32(&ms.bar_h_empty[i]), kLFConv);
       mbar_init(smem_u32(&ms.bar_a2_full[i]), kLFConv); mbar_init(smem_u32(&ms.bar_a2_empty[i]), 1);
@@ -407,11 +408,8 @@ __global__ void __launch_bounds__(kLFThreads, 1) leff_fused_kernel(const __grid_
             }
           }
         }
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(smem_u32(&ms.bar_x_empty[ab]));        // this warp is done reading the raw tile
-          mbar_arrive(smem_u32(&ms.bar_st_full[sb]));
-        }
+        mbar_arrive(smem_u32(&ms.bar_x_empty[ab]));          // this thread is done reading the raw tile
+        mbar_arrive(smem_u32(&ms.bar_st_full[sb]));          // ... and has published its statistics (release)
         mbar_wait(smem_u32(&ms.bar_st_full[sb]), (it >> 1) & 1);             // all eight warps' rows are in
         if (q == 0 && lane == 0) { LF_TRACE(4, 2 * it + 1) }
       }
