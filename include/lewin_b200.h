@@ -79,8 +79,18 @@ typedef struct lw_wmsa_args {
   int32_t x_fp32;          /* x and resid are fp32 (the residual stream); the GEMM operand is still rounded to bf16 after LayerNorm */
   int32_t out_fp32;        /* out is fp32 */
   void* out_b;             /* optional bf16 copy of out (same layout): the GEMM operand of the LeFF kernel that follows */
+  /* TMA-gather path (persistent kernel, csrc/wmsa_tma.cuh).  Taken when wqkv_fold_img != NULL and the call is eligible:
+   * token-map input (windowed = 0), LayerNorm present, no modulator, lw_wmsa_tma_supported(C, head_dim), shift % 4 == 0, and a
+   * bf16 source for the gather (x itself, or x_b when x_fp32).  Otherwise the fields are ignored and wmsa_kernel runs.
+   * LayerNorm is folded into the projection: LN(x) Wqkv^T + b = rstd*(x Wg^T) - rstd*mean*cs + bf. */
+  const void* wqkv_fold_img; /* Wg = Wqkv diag(ln_w) rounded to bf16, packed like wqkv_img */
+  const float* bqkv_fold;    /* bf = bqkv + Wqkv ln_b, (heads, 3*hd) */
+  const float* cs_qkv;       /* row sums of the bf16 Wg, (heads, 3*hd) */
+  const void* x_b;           /* bf16 copy of an fp32 x (what the previous kernel wrote as its out_b), or NULL */
 } lw_wmsa_args;
 int lw_wmsa_fwd(const lw_wmsa_args* a, lw_stream_t stream);
+/* 1 if the TMA-gather W-MSA kernel is built for (C, head_dim): C in {16,32,64,128,256}, head_dim in {16,32}. */
+int lw_wmsa_tma_supported(int C, int head_dim);
 
 /* ---- LeFF part 1 (two-kernel path, C = 512): h1 = GELU( LN(x) W1^T + b1 )  (model.py:671 with norm2 of :987 folded in).
  * h1 is written in HALF precision (fp16): it is an internal buffer between the two kernels. */
@@ -136,6 +146,8 @@ typedef struct lw_leff_args {
   int32_t resid_fp32, out_fp32;                 /* 0: bf16, 1: fp32 */
   int32_t has_ln;
   float ln_eps;
+  void* out_b;             /* optional bf16 copy of out, contiguous (B*H*W, C): the TMA source of the W-MSA kernel that follows
+                              when out is the fp32 residual stream */
 } lw_leff_args;
 int lw_leff_fwd(const lw_leff_args* a, lw_stream_t stream);
 /* 1 if lw_leff_fwd handles (C, hidden), else 0 (use lw_leff1_fwd + lw_leff2_fwd). */

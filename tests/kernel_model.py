@@ -47,15 +47,29 @@ def _shift_mask(H, W, shift):
     return torch.where(rw[:, None, :] != rw[:, :, None], -100.0, 0.0)
 
 
-def wmsa(x, p, *, H, W, shift, windowed, resid, mask=None, out=None, out_dtype=None, bf16_copy=False):
+def _wmsa_tma_eligible(x, p, shift, windowed, x_b):
+    """lw_wmsa_fwd's choice of the TMA-gather kernel (include/lewin_b200.h, lw_wmsa_args.wqkv_fold_img)."""
+    C = x.shape[-1]
+    return ("wqkv_fold_img" in p and not windowed and p.get("modulator") is None and p.get("ln_w") is not None and shift % 4 == 0
+            and (x.dtype == BF or x_b is not None) and bool(_lib.load().lw_wmsa_tma_supported(C, p["head_dim"])))
+
+
+def wmsa(x, p, *, H, W, shift, windowed, resid, mask=None, out=None, out_dtype=None, bf16_copy=False, x_b=None):
     assert x.dtype in (BF, torch.float32) and x.is_contiguous()
     assert resid is None or resid.dtype == x.dtype
     C = x.shape[-1]
     hd = p["head_dim"]
     heads = C // hd
-    xf = x.float()
-    if p.get("ln_w") is not None:
-        xf = F.layer_norm(xf, (C,), p["ln_w"], p["ln_b"], p.get("ln_eps", 1e-5))
+    fold = _wmsa_tma_eligible(x, p, shift, windowed, x_b)
+    if fold:
+        # TMA-gather kernel: the raw bf16 tokens are the GEMM operand; LayerNorm statistics come from that same bf16 tile
+        # and are applied to the accumulator (rstd*acc - rstd*mean*cs + bf)
+        assert x_b is None or (x_b.dtype == BF and x_b.shape == x.shape)
+        xf = (x if x.dtype == BF else x_b).float()
+    else:
+        xf = x.float()
+        if p.get("ln_w") is not None:
+            xf = F.layer_norm(xf, (C,), p["ln_w"], p["ln_b"], p.get("ln_eps", 1e-5))
     if windowed:
         xw = xf
     else:
@@ -68,8 +82,14 @@ def wmsa(x, p, *, H, W, shift, windowed, resid, mask=None, out=None, out_dtype=N
         xw = xw + p["modulator"]
     xw = _q(xw)                                                   # A operand is bf16
     nW = xw.shape[0]
-    wcat = packing.unpack_kmajor(p["wqkv_img"], heads * 3 * hd, C, 3 * hd, "nk")        # [head][q|k|v][hd] rows, q pre-scaled
-    qkv = (xw @ wcat.t() + p["bqkv"]).view(nW, 64, heads, 3, hd)
+    if fold:
+        wg = packing.unpack_kmajor(p["wqkv_fold_img"], heads * 3 * hd, C, 3 * hd, "nk")
+        mean = xw.mean(-1, keepdim=True)
+        rstd = torch.rsqrt(((xw - mean) ** 2).mean(-1, keepdim=True) + p.get("ln_eps", 1e-5))
+        qkv = (rstd * (xw @ wg.t()) - (rstd * mean) * p["cs_qkv"] + p["bqkv_fold"]).view(nW, 64, heads, 3, hd)
+    else:
+        wcat = packing.unpack_kmajor(p["wqkv_img"], heads * 3 * hd, C, 3 * hd, "nk")        # [head][q|k|v][hd] rows, q pre-scaled
+        qkv = (xw @ wcat.t() + p["bqkv"]).view(nW, 64, heads, 3, hd)
     q, k, v = (_q(qkv[:, :, :, i].permute(0, 2, 1, 3)) for i in range(3))
     s = q @ k.transpose(-2, -1) + p["relpos"][:, _relidx().reshape(-1)].view(heads, 64, 64)[None]
     if not windowed and shift:
@@ -98,8 +118,9 @@ def wmsa(x, p, *, H, W, shift, windowed, resid, mask=None, out=None, out_dtype=N
     return (y, yb) if bf16_copy else y
 
 
-def leff(x, p, *, B, H, W, resid, out=None, out_dtype=None):
+def leff(x, p, *, B, H, W, resid, out=None, out_dtype=None, bf16_copy=False):
     assert x.dtype == BF
+    assert not bf16_copy or "w1f_img" in p
     C, hid = x.shape[-1], p["hidden"]
     xf = x.float().reshape(B * H * W, C)
     if "w1f_img" in p:
@@ -140,11 +161,12 @@ def leff(x, p, *, B, H, W, resid, out=None, out_dtype=None):
     if resid is not None:
         y = y + resid.float()
     odt = out.dtype if out is not None else (out_dtype or BF)
+    yb = y.to(BF).contiguous() if bf16_copy else None
     y = y.to(odt)
     if out is not None:
         out.copy_(y)
-        return out
-    return y
+        y = out
+    return (y, yb) if bf16_copy else y
 
 
 def downsample(x, p, *, B, H, W):

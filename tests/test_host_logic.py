@@ -63,7 +63,7 @@ def test_c_abi_exports_every_declared_symbol():
     lib = _lib.load()
     for s in declared:
         assert hasattr(lib, s), s
-    assert lib.lw_abi_version() == 4
+    assert lib.lw_abi_version() == 5
     # the ctypes mirrors have the compiled structs' sizes (also enforced at load time)
     for i, st in enumerate([_lib.WmsaArgs, _lib.Leff1Args, _lib.Leff2Args, _lib.LeffArgs, _lib.DownArgs, _lib.UpArgs, _lib.AdamWArgs]):
         assert lib.lw_struct_size(i) == ctypes.sizeof(st), st.__name__
@@ -132,7 +132,8 @@ def test_batched_prepack_is_bit_identical_to_lazy_packing():
     from uformer_b200.prepack import prepack
     from paramgen import randomize_state
     for cfg in [dict(img_size=128, embed_dim=16, depths=[2, 1, 2, 1, 2, 1, 2, 1, 2], win_size=8, modulator=True),
-                dict(img_size=128, embed_dim=32, depths=[1, 2, 1, 1, 1, 1, 1, 2, 1], win_size=8, modulator=True)]:
+                dict(img_size=128, embed_dim=32, depths=[1, 2, 1, 1, 1, 1, 1, 2, 1], win_size=8, modulator=True),
+                dict(img_size=128, embed_dim=16, depths=[2, 1, 1, 1, 1, 1, 1, 1, 2], win_size=8, modulator=False)]:
         net = uformer_b200.Uformer(**cfg)
         net.load_state_dict(randomize_state(net.state_dict(), 11))
         calls = []                                                        # (module, cache, packed-call)
@@ -140,10 +141,13 @@ def test_batched_prepack_is_bit_identical_to_lazy_packing():
             if isinstance(m, M.LeWinTransformerBlock):
                 calls += [(m, m._cache, m.packed), (m.attn, m.attn._cache, m.attn.packed),
                           (m.mlp, m.mlp._cache_ln, lambda mm=m: mm.mlp.packed(mm.norm2))]
+                if m.modulator is None and m.attn.tma_gather():           # LayerNorm-folded projection of the TMA-gather W-MSA
+                    calls.append((m.attn, m.attn._cache_ln, lambda mm=m: mm.attn.packed_fold(mm.norm1)))
             elif isinstance(m, (M.Downsample, M.Upsample)):
                 calls.append((m, m._cache, m.packed))
         lazy = [{k: (v.clone() if torch.is_tensor(v) else v) for k, v in call().items()} for _, _, call in calls]
         assert any("w1f_img" in d for d in lazy) and (cfg["embed_dim"] == 16 or any("w1_img" in d for d in lazy))   # both LeFF paths
+        assert cfg["modulator"] or any("wqkv_fold_img" in d for d in lazy)
         M.invalidate_packed()
         assert prepack(net) == sum(cfg["depths"]) + 8
         for (m, cache, call), want in zip(calls, lazy):

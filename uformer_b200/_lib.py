@@ -24,7 +24,8 @@ class WmsaArgs(C.Structure):
                 ("bproj", C.c_void_p), ("relpos", C.c_void_p), ("mask", C.c_void_p), ("n_mask_windows", C.c_int32),
                 ("n_windows", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32), ("head_dim", C.c_int32),
                 ("shift", C.c_int32), ("windowed", C.c_int32), ("ln_eps", C.c_float), ("dbg", C.c_int32), ("trace", C.c_void_p),
-                ("x_fp32", C.c_int32), ("out_fp32", C.c_int32), ("out_b", C.c_void_p)]
+                ("x_fp32", C.c_int32), ("out_fp32", C.c_int32), ("out_b", C.c_void_p),
+                ("wqkv_fold_img", C.c_void_p), ("bqkv_fold", C.c_void_p), ("cs_qkv", C.c_void_p), ("x_b", C.c_void_p)]
 
 
 class Leff1Args(C.Structure):
@@ -43,7 +44,7 @@ class LeffArgs(C.Structure):
                 ("cs", C.c_void_p), ("taps", C.c_void_p), ("w2_img", C.c_void_p), ("b2", C.c_void_p),
                 ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32), ("hidden", C.c_int32),
                 ("x_stride", C.c_int32), ("resid_stride", C.c_int32), ("out_stride", C.c_int32), ("resid_fp32", C.c_int32),
-                ("out_fp32", C.c_int32), ("has_ln", C.c_int32), ("ln_eps", C.c_float)]
+                ("out_fp32", C.c_int32), ("has_ln", C.c_int32), ("ln_eps", C.c_float), ("out_b", C.c_void_p)]
 
 
 class DownArgs(C.Structure):
@@ -65,7 +66,7 @@ class AdamWArgs(C.Structure):
 CHARBONNIER_PARTIALS = 1024      # LW_CHARBONNIER_PARTIALS
 
 # every symbol include/lewin_b200.h declares
-EXPORTS = ["lw_abi_version", "lw_struct_size", "lw_last_cuda_error", "lw_check_device", "lw_nch_ares", "lw_wmsa_fwd", "lw_leff1_fwd", "lw_leff2_fwd", "lw_leff_fwd", "lw_leff_fused_supported", "lw_leff_slice",
+EXPORTS = ["lw_abi_version", "lw_struct_size", "lw_last_cuda_error", "lw_check_device", "lw_nch_ares", "lw_wmsa_fwd", "lw_wmsa_tma_supported", "lw_leff1_fwd", "lw_leff2_fwd", "lw_leff_fwd", "lw_leff_fused_supported", "lw_leff_slice",
            "lw_downsample_fwd", "lw_upsample_fwd", "lw_input_proj_fwd", "lw_output_proj_fwd", "lw_charbonnier_fwd_bwd", "lw_adamw_step"]
 
 _lib = None
@@ -92,6 +93,8 @@ def load():
     lib.lw_nch_ares.argtypes = [C.c_int, C.c_int]
     lib.lw_leff_fused_supported.restype = C.c_int
     lib.lw_leff_fused_supported.argtypes = [C.c_int, C.c_int]
+    lib.lw_wmsa_tma_supported.restype = C.c_int
+    lib.lw_wmsa_tma_supported.argtypes = [C.c_int, C.c_int]
     lib.lw_leff_slice.restype = C.c_int
     lib.lw_leff_slice.argtypes = [C.c_int]
     for name, argt in [("lw_wmsa_fwd", WmsaArgs), ("lw_leff1_fwd", Leff1Args), ("lw_leff2_fwd", Leff2Args), ("lw_leff_fwd", LeffArgs),

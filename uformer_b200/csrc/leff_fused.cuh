@@ -49,6 +49,8 @@ struct LeffFArgs {
   int has_ln;
   float ln_eps;
   int tiles_x, tiles_y, n_tiles;
+  bf16* out_b;             // optional bf16 copy of out (row stride out_b_stride), or null
+  int out_b_stride;
   long long* trace;        // -DLW_TRACE builds: CTA 0 writes per-role clock64 timelines here (tools/leff_fused_trace.py)
 };
 
@@ -157,6 +159,7 @@ __device__ __forceinline__ void lf_store_rows(uint32_t stage_s, const int* row_o
     } else {
       *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(a.out) + (size_t)tok * a.out_stride + c) = pack8(f);
     }
+    if (a.out_b != nullptr) *reinterpret_cast<uint4*>(a.out_b + (size_t)tok * a.out_b_stride + c) = pack8(f);
   }
 }
 

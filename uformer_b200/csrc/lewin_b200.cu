@@ -4,6 +4,7 @@
 #include <cstring>
 #include <cstdlib>
 #include "wmsa.cuh"
+#include "wmsa_tma.cuh"
 #include "leff.cuh"
 #include "leff2.cuh"
 #include "leff_fused.cuh"
@@ -37,7 +38,7 @@ static bool all_aligned16(P... ps) {
   return ok;
 }
 
-extern "C" int lw_abi_version(void) { return 4; }
+extern "C" int lw_abi_version(void) { return 5; }
 extern "C" const char* lw_last_cuda_error(void) { return g_err; }
 extern "C" int lw_check_device(void) {
   int dev = 0, major = 0;
@@ -118,6 +119,9 @@ static int launch_wmsa(const lw_wmsa_args* a, cudaStream_t st) {
   return LW_OK;
 }
 
+static bool wmsa_tma_eligible(const lw_wmsa_args* a);
+static int launch_wmsa_tma_any(const lw_wmsa_args* a, cudaStream_t st);
+
 extern "C" int lw_wmsa_fwd(const lw_wmsa_args* a, lw_stream_t stream) {
   if (!a || !a->x || !a->out || !a->wqkv_img || !a->bqkv || !a->wproj_img || !a->bproj || !a->relpos) return LW_ERR_NULL;
   if ((a->ln_w == nullptr) != (a->ln_b == nullptr)) return LW_ERR_NULL;
@@ -140,6 +144,7 @@ extern "C" int lw_wmsa_fwd(const lw_wmsa_args* a, lw_stream_t stream) {
     aa.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr;
   }
   a = &aa;
+  if (wmsa_tma_eligible(a)) return launch_wmsa_tma_any(a, st);
 #define WMSA_CASE(c, hd) \
   if (a->C == c && a->head_dim == hd) return launch_wmsa<c, hd>(a, st);
   WMSA_CASE(32, 32) WMSA_CASE(64, 32) WMSA_CASE(128, 32) WMSA_CASE(256, 32) WMSA_CASE(512, 32)
@@ -263,6 +268,50 @@ static int make_token_map(CUtensorMap* m, const void* base, int B, int H, int W,
   return LW_OK;
 }
 
+// ---- W-MSA with the TMA window gather (wmsa_tma.cuh) ----
+extern "C" int lw_wmsa_tma_supported(int C, int head_dim) {
+  return (head_dim == 16 || head_dim == 32) && (C == 16 || C == 32 || C == 64 || C == 128 || C == 256) && C % head_dim == 0 && C >= head_dim;
+}
+static bool wmsa_tma_eligible(const lw_wmsa_args* a) {
+  if (!a->wqkv_fold_img || !a->bqkv_fold || !a->cs_qkv) return false;
+  if (a->windowed || a->modulator || !a->ln_w || (a->shift % 4) != 0) return false;
+  if (a->x_fp32 && !a->x_b) return false;
+  if (!all_aligned16(a->wqkv_fold_img, a->x_b)) return false;
+  return lw_wmsa_tma_supported(a->C, a->head_dim) != 0;
+}
+template <int C, int HD>
+static int launch_wmsa_tma(const CUtensorMap& map, const WmsaTArgs& a, cudaStream_t st) {
+  using Cfg = WmsaTCfg<C, HD>;
+  LW_ENSURE_SMEM((wmsa_tma_kernel<C, HD>), Cfg::SMEM_BYTES);
+  const int cap = sm_count() * (C <= 128 ? 2 : 1);
+  const int grid = a.n_tiles < cap ? a.n_tiles : cap;
+  wmsa_tma_kernel<C, HD><<<grid, kThreads8, Cfg::SMEM_BYTES, st>>>(map, a);
+  LW_TRY(cudaGetLastError());
+  return LW_OK;
+}
+static int launch_wmsa_tma_any(const lw_wmsa_args* p, cudaStream_t st) {
+  const int nwin_img = (p->H / 8) * (p->W / 8);
+  const int B = p->n_windows / nwin_img;
+  CUtensorMap map;
+  const int cb = p->C < 64 ? p->C : 64;
+  const int rc = make_token_map(&map, p->x_fp32 ? p->x_b : p->x, B, p->H, p->W, p->C, p->C, cb, 4, 4);
+  if (rc != LW_OK) return rc;
+  WmsaTArgs a{};
+  a.out = p->out; a.resid = p->resid; a.out_b = reinterpret_cast<bf16*>(p->out_b);
+  a.wqkv_img = reinterpret_cast<const uint8_t*>(p->wqkv_fold_img); a.bqkv = p->bqkv_fold; a.cs = p->cs_qkv;
+  a.wproj_img = reinterpret_cast<const uint8_t*>(p->wproj_img); a.bproj = p->bproj; a.relpos = p->relpos;
+  a.mask = p->mask; a.n_mask_windows = p->n_mask_windows; a.n_windows = p->n_windows; a.H = p->H; a.W = p->W; a.shift = p->shift;
+  a.ln_eps = p->ln_eps; a.resid_fp32 = p->x_fp32; a.out_fp32 = p->out_fp32;
+  a.n_tiles = (p->n_windows + 1) / 2;
+  a.dbg = p->dbg; a.trace = p->trace;
+#define WMSA_TCASE(c, hd) \
+  if (p->C == c && p->head_dim == hd) return launch_wmsa_tma<c, hd>(map, a, st);
+  WMSA_TCASE(32, 32) WMSA_TCASE(64, 32) WMSA_TCASE(128, 32) WMSA_TCASE(256, 32)
+  WMSA_TCASE(16, 16) WMSA_TCASE(32, 16) WMSA_TCASE(64, 16) WMSA_TCASE(128, 16) WMSA_TCASE(256, 16)
+#undef WMSA_TCASE
+  return LW_ERR_BAD_SHAPE;
+}
+
 extern "C" int lw_leff_fused_supported(int C, int hidden) {
   return (C == 16 || C == 32 || C == 64 || C == 128 || C == 256) && hidden % 64 == 0 && hidden >= 64 && hidden <= 1024;
 }
@@ -287,7 +336,7 @@ extern "C" int lw_leff_fwd(const lw_leff_args* p, lw_stream_t stream) {
   if (p->resid && (p->resid_stride < p->C || p->resid_stride % 8)) return LW_ERR_BAD_SHAPE;
   if (p->out == p->x) return LW_ERR_BAD_SHAPE;                       // halo rows of x are read after neighbouring tiles were written
   if ((long long)p->B * p->H * p->W >= (1ll << 31)) return LW_ERR_BAD_SHAPE;
-  if (!all_aligned16(p->x, p->out, p->resid, p->w1_img, p->b1f, p->cs, p->taps, p->w2_img, p->b2)) return LW_ERR_ALIGN;
+  if (!all_aligned16(p->x, p->out, p->out_b, p->resid, p->w1_img, p->b1f, p->cs, p->taps, p->w2_img, p->b2)) return LW_ERR_ALIGN;
   CUtensorMap map;
   const int cb = p->C < 64 ? p->C : 64;
   const int rc = make_token_map(&map, p->x, p->B, p->H, p->W, p->C, p->x_stride, cb, 18, 10);
@@ -299,6 +348,7 @@ extern "C" int lw_leff_fwd(const lw_leff_args* p, lw_stream_t stream) {
   a.w2_img = reinterpret_cast<const uint8_t*>(p->w2_img); a.b2 = p->b2;
   a.resid = p->resid; a.out = p->out; a.resid_stride = p->resid_stride; a.out_stride = p->out_stride;
   a.resid_fp32 = p->resid_fp32; a.out_fp32 = p->out_fp32; a.has_ln = p->has_ln; a.ln_eps = p->ln_eps;
+  a.out_b = reinterpret_cast<bf16*>(p->out_b); a.out_b_stride = p->C;
   a.tiles_x = (p->W + 15) / 16; a.tiles_y = p->H / 8; a.n_tiles = a.tiles_x * a.tiles_y * p->B;
   a.trace = nullptr;
   if (debug_flags() & 16) {   // profiling aid (-DLW_TRACE builds): env LW_TRACE_PTR = device buffer of >= 7*512 int64

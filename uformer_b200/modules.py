@@ -158,6 +158,7 @@ class WindowAttention(nn.Module):
         self.proj_drop = nn.Dropout(proj_drop)
         self.softmax = nn.Softmax(dim=-1)
         self._cache = _PackCache()
+        self._cache_ln = _PackCache()
 
     # ---- packing -------------------------------------------------------------------------------
     def pack_sources(self):
@@ -176,6 +177,26 @@ class WindowAttention(nn.Module):
             return dict(wqkv_img=wimg, bqkv=bqkv, wproj_img=packing.pack_kmajor(wp, min(C, 128), "nk"),
                         bproj=bp.float().contiguous(), relpos=packing.pack_relpos(table), head_dim=C // self.num_heads)
         return self._cache.get(srcs, build)
+
+    def tma_gather(self) -> bool:
+        """True when the persistent TMA-gather W-MSA kernel (csrc/wmsa_tma.cuh) is built for this shape; the block then also
+        packs the LayerNorm-folded projection.  UFORMER_B200_WMSA=classic keeps every launch on wmsa_kernel (A/B switch)."""
+        if os.environ.get("UFORMER_B200_WMSA", "tma") == "classic":
+            return False
+        return bool(_lib.load().lw_wmsa_tma_supported(self.dim, self.dim // self.num_heads))
+
+    def packed_fold(self, norm: nn.LayerNorm):
+        """The projection with `norm` (the block's norm1, model.py:953) folded in: packing.pack_qkv_fold."""
+        q, kv = self.qkv.to_q, self.qkv.to_kv
+        srcs = [q.weight, q.bias, kv.weight, kv.bias, norm.weight, norm.bias]
+
+        def build():
+            C = self.dim
+            bq_ = q.bias if q.bias is not None else torch.zeros(C, device=q.weight.device)
+            bkv_ = kv.bias if kv.bias is not None else torch.zeros(2 * C, device=q.weight.device)
+            img, bf, cs = packing.pack_qkv_fold(q.weight, bq_, kv.weight, bkv_, self.num_heads, float(self.scale), norm.weight, norm.bias)
+            return dict(wqkv_fold_img=img, bqkv_fold=bf, cs_qkv=cs)
+        return self._cache_ln.get(srcs, build)
 
     def _check_supported(self):
         if tuple(self.win_size) != (8, 8):
@@ -383,6 +404,15 @@ class LeWinTransformerBlock(nn.Module):
                         modulator=None if self.modulator is None else self.modulator.weight.float().contiguous())
         return self._cache.get(srcs, build)
 
+    def _attn_operands(self):
+        """Operand dict of ops.wmsa for this block: attention images + norm1 affine + modulator, plus the LayerNorm-folded
+        projection when the TMA-gather kernel can take the block (no modulator: its per-position term is not folded)."""
+        pk = self.packed()
+        pa = dict(self.attn.packed(), ln_w=pk["ln1_w"], ln_b=pk["ln1_b"], modulator=pk["modulator"], ln_eps=self.norm1.eps)
+        if pk["modulator"] is None and self.attn.tma_gather():
+            pa.update(self.attn.packed_fold(self.norm1))
+        return pa
+
     @staticmethod
     def input_mask_to_attn_mask(mask, H, W, ws):
         """(B,1,h,w) input mask -> additive (B*nW, N, N) mask, model.py:914-921 (host side, rarely used)."""
@@ -392,9 +422,11 @@ class LeWinTransformerBlock(nn.Module):
         am = m.unsqueeze(2) * m.unsqueeze(1)
         return torch.where(am != 0, torch.full_like(am, -100.0), torch.zeros_like(am))
 
-    def forward(self, x, mask=None, out=None, out_dtype=None):
+    def forward(self, x, mask=None, out=None, out_dtype=None, x_b=None, want_b=False):
         """`out` (optional, bf16, same shape as x): write the block output there (used by the stage scheduler).
-        `out_dtype` (fp32 residual-stream mode only): dtype of the returned tensor (fp32 inside a stage, bf16 at its end)."""
+        `out_dtype` (fp32 residual-stream mode only): dtype of the returned tensor (fp32 inside a stage, bf16 at its end).
+        `x_b` / `want_b` (fp32 residual-stream mode, used by the stage scheduler): a bf16 copy of an fp32 `x` — the TMA gather
+        source of the W-MSA kernel — and whether to return one of the output as well: the result is then (out, out_bf16)."""
         B, L, C = x.shape
         H = W = int(math.sqrt(L))
         if H * W != L or H % 8 or self.win_size != 8:
@@ -410,7 +442,9 @@ class LeWinTransformerBlock(nn.Module):
         _lib.require_device(x.device)
         stochastic = self.training and isinstance(self.drop_path, DropPath) and self.drop_path.drop_prob > 0.0
         if self.residual_fp32 and not stochastic and not (torch.is_grad_enabled() and autograd.wants_grad(x, *autograd.trainable_tensors(self))):
-            return self._forward_fp32_residual(x, B, H, W, mask, out, out_dtype)      # inference (nothing to differentiate)
+            return self._forward_fp32_residual(x, B, H, W, mask, out, out_dtype, x_b, want_b)      # inference (nothing to differentiate)
+        if want_b:
+            raise ValueError("want_b is an fp32 residual-stream option (inference)")
         xb, back = _as_bf16(x)
         # stochastic depth (model.py:986-987): the two per-sample factors, drawn in the reference's order
         dp = self.drop_path if isinstance(self.drop_path, DropPath) else None
@@ -428,8 +462,7 @@ class LeWinTransformerBlock(nn.Module):
 
         def native(t, *rest):
             a1, a2, m = split(rest)
-            pk = self.packed()
-            pa = dict(self.attn.packed(), ln_w=pk["ln1_w"], ln_b=pk["ln1_b"], modulator=pk["modulator"], ln_eps=self.norm1.eps)
+            pa = self._attn_operands()
             pm = self.mlp.packed(self.norm2)
             amask = None if m is None else self.input_mask_to_attn_mask(m, H, W, 8)
             if a1 is None:
@@ -449,24 +482,30 @@ class LeWinTransformerBlock(nn.Module):
         return res if back is None else res.to(back)
 
     @torch.no_grad()
-    def _forward_fp32_residual(self, x, B, H, W, mask=None, out=None, out_dtype=None):
+    def _forward_fp32_residual(self, x, B, H, W, mask=None, out=None, out_dtype=None, x_b=None, want_b=False):
         """Precision mode (set_residual_precision): the residual stream x -> x1 -> out stays fp32 in HBM, inside the kernels:
         W-MSA reads the fp32 stream (LayerNorm in fp32, bf16 GEMM operand), adds its branch in fp32 and writes x1 in fp32 plus
         a bf16 copy (the LeFF kernel's GEMM operand); LeFF adds its branch to the fp32 x1 and writes fp32 (bf16 at the end of
         a stage).  Removes the 80 bf16 roundings of the residual stream that dominate the flagship model's parity error
         (DESIGN §2).  Inference only; `x` may be bf16 (first block of a stage) or fp32."""
-        pk = self.packed()
-        pa = dict(self.attn.packed(), ln_w=pk["ln1_w"], ln_b=pk["ln1_b"], modulator=pk["modulator"], ln_eps=self.norm1.eps)
+        pa = self._attn_operands()
         pm = self.mlp.packed(self.norm2)
         if x.dtype not in (torch.bfloat16, torch.float32):
             x = x.float()
         x = x.contiguous()
         amask = None if mask is None else self.input_mask_to_attn_mask(mask, H, W, 8)
-        x1, x1b = ops.wmsa(x, pa, H=H, W=W, shift=self.shift_size, windowed=False, resid=x, mask=amask, out_dtype=torch.float32, bf16_copy=True)
+        x1, x1b = ops.wmsa(x, pa, H=H, W=W, shift=self.shift_size, windowed=False, resid=x, mask=amask, out_dtype=torch.float32, bf16_copy=True,
+                           x_b=x_b if x.dtype == torch.float32 else None)
         odt = out.dtype if out is not None else (out_dtype or torch.float32)
+        if want_b and not (self.mlp.fused() and odt == torch.float32):
+            raise ValueError("want_b needs the fused LeFF kernel and an fp32 output")
         if out is not None and not self.mlp.fused() and not out.is_contiguous():
             return out.copy_(ops.leff(x1b, pm, B=B, H=H, W=W, resid=x1, out_dtype=odt))
-        return ops.leff(x1b, pm, B=B, H=H, W=W, resid=x1, out=out, out_dtype=odt)
+        return ops.leff(x1b, pm, B=B, H=H, W=W, resid=x1, out=out, out_dtype=odt, bf16_copy=want_b)
+
+    def wants_bf16_copy(self) -> bool:
+        """Whether this block's W-MSA would gather an fp32 input through its bf16 copy (TMA path; see forward's x_b)."""
+        return self.modulator is None and self.attn.tma_gather() and self.mlp.fused()
 
     def flops(self):
         H, W = self.input_resolution

@@ -52,9 +52,12 @@ class LeWinStage(nn.Module):
         infer = not autograd.wants_grad(x, *autograd.trainable_tensors(self))
         if n and infer and self.blocks[0].residual_fp32:
             # fp32 residual-stream mode: bf16 in, fp32 between the blocks of the stage, bf16 out (set_residual_precision)
+            xb = None                                   # bf16 copy of the fp32 stream: gather source of the next block's W-MSA
             for i, blk in enumerate(self.blocks):
                 last = i == n - 1
-                x = blk(x, mask, out=out if last else None, out_dtype=torch.bfloat16 if last else torch.float32)
+                want_b = (not last) and self.blocks[i + 1].wants_bf16_copy() and blk.mlp.fused()
+                res = blk(x, mask, out=out if last else None, out_dtype=torch.bfloat16 if last else torch.float32, x_b=xb, want_b=want_b)
+                x, xb = res if want_b else (res, None)
             return x
         if out is None or n == 0:
             for blk in self.blocks:

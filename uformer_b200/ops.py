@@ -52,12 +52,15 @@ def _check_act(x: Tensor, name: str):
 
 
 def wmsa(x: Tensor, p: dict, *, H: int, W: int, shift: int, windowed: bool, resid: Tensor | None,
-         mask: Tensor | None = None, out: Tensor | None = None, out_dtype=None, bf16_copy: bool = False):
+         mask: Tensor | None = None, out: Tensor | None = None, out_dtype=None, bf16_copy: bool = False, x_b: Tensor | None = None):
     """Fused (LN) + (roll/partition) + W-MSA + proj + (reverse/unroll) + (residual).
     p: packed parameter dict from modules._pack_attention (+ optional ln_w/ln_b/modulator).
     fp32 residual-stream mode: x (and resid, which must then be x's dtype) may be fp32; out_dtype=torch.float32 writes the
     sum in fp32; bf16_copy=True additionally returns a bf16 copy of the output (the GEMM operand of the LeFF kernel that
-    follows): the return value is then the pair (out, out_bf16)."""
+    follows): the return value is then the pair (out, out_bf16).
+    When p carries the LayerNorm-folded projection ("wqkv_fold_img", packing.pack_qkv_fold) the library takes the persistent
+    TMA-gather kernel (csrc/wmsa_tma.cuh) for token-map inputs; an fp32 x then needs `x_b`, its bf16 copy (the previous
+    kernel's bf16_copy output), as the gather source."""
     if x.dtype not in (torch.bfloat16, torch.float32):
         raise TypeError(f"x must be bfloat16 or float32 (got {x.dtype})")
     if not x.is_contiguous():
@@ -84,6 +87,10 @@ def wmsa(x: Tensor, p: dict, *, H: int, W: int, shift: int, windowed: bool, resi
     a.n_windows, a.H, a.W, a.C, a.head_dim = n_windows, H, W, Cc, p["head_dim"]
     a.shift, a.windowed, a.ln_eps = shift, int(windowed), p.get("ln_eps", 1e-5)
     a.x_fp32, a.out_fp32, a.out_b = int(x.dtype == torch.float32), int(out.dtype == torch.float32), _ptr(out_b)
+    if "wqkv_fold_img" in p and not windowed:
+        if x_b is not None and (x_b.dtype != torch.bfloat16 or x_b.shape != x.shape or not x_b.is_contiguous()):
+            raise ValueError("x_b must be a contiguous bfloat16 tensor of x's shape")
+        a.wqkv_fold_img, a.bqkv_fold, a.cs_qkv, a.x_b = _ptr(p["wqkv_fold_img"]), _ptr(p["bqkv_fold"]), _ptr(p["cs_qkv"]), _ptr(x_b)
     ntok = n_windows * 64
     _launch(f"wmsa_C{Cc}_T{ntok}", 2.0 * ntok * (4 * Cc * Cc + 128 * Cc), lambda st: _lib.load().lw_wmsa_fwd(C.byref(a), st), "lw_wmsa_fwd", x.device)
     return (out, out_b) if bf16_copy else out
@@ -96,12 +103,17 @@ def _row_stride(t: Tensor, name: str) -> int:
     return t.stride(-2)
 
 
-def leff(x: Tensor, p: dict, *, B: int, H: int, W: int, resid: Tensor | None, out: Tensor | None = None, out_dtype=None) -> Tensor:
+def leff(x: Tensor, p: dict, *, B: int, H: int, W: int, resid: Tensor | None, out: Tensor | None = None, out_dtype=None,
+         bf16_copy: bool = False):
     """(LN) + Linear1 + GELU + dwconv3x3 + GELU + Linear2 (+ residual).
     p from packing.pack_leff_fused (key "w1f_img"): ONE launch (lw_leff_fwd), the hidden map stays on chip; x / resid / out
     may be column slices of wider buffers, resid / out may be fp32.  Otherwise (C = 512) the two-kernel path: the hidden
-    map makes one bf16 round trip through HBM/L2 between lw_leff1_fwd and lw_leff2_fwd."""
+    map makes one bf16 round trip through HBM/L2 between lw_leff1_fwd and lw_leff2_fwd.
+    bf16_copy=True (fused kernel only): additionally returns a contiguous bf16 copy of the output — the TMA source of the
+    W-MSA kernel that follows when `out` is the fp32 residual stream; the return value is then (out, out_bf16)."""
     if "w1f_img" not in p:
+        if bf16_copy:
+            raise ValueError("bf16_copy needs the fused LeFF kernel")
         return _leff_two_kernels(x, p, B=B, H=H, W=W, resid=resid, out=out, out_dtype=out_dtype)
     if x.dtype != torch.bfloat16:
         raise TypeError(f"x must be bfloat16 (got {x.dtype})")
@@ -123,9 +135,11 @@ def leff(x: Tensor, p: dict, *, B: int, H: int, W: int, resid: Tensor | None, ou
     a.resid_fp32 = int(resid is not None and resid.dtype == torch.float32)
     a.out_fp32 = int(out.dtype == torch.float32)
     a.has_ln, a.ln_eps = int(p["has_ln"]), p.get("ln_eps", 1e-5)
+    out_b = torch.empty(out.shape, dtype=torch.bfloat16, device=x.device) if bf16_copy else None
+    a.out_b = _ptr(out_b)
     lib = _lib.load()
     _launch(f"leff_C{Cc}_T{n_tokens}", 2.0 * n_tokens * (2 * hidden * Cc + 9 * hidden), lambda st: lib.lw_leff_fwd(C.byref(a), st), "lw_leff_fwd", x.device)
-    return out
+    return (out, out_b) if bf16_copy else out
 
 
 def _leff_two_kernels(x: Tensor, p: dict, *, B: int, H: int, W: int, resid: Tensor | None, out: Tensor | None = None, out_dtype=None) -> Tensor:

@@ -139,6 +139,25 @@ def pack_qkv(wq: Tensor, bq: Tensor, wkv: Tensor, bkv: Tensor, heads: int, scale
     return img, bias.contiguous()                               # bias (heads*3*hd,)
 
 
+def pack_qkv_fold(wq: Tensor, bq: Tensor, wkv: Tensor, bkv: Tensor, heads: int, scale: float, ln_w: Tensor, ln_b: Tensor):
+    """pack_qkv with the LayerNorm in front (norm1, model.py:953) folded into the projection, for the TMA-gather W-MSA kernel
+    (csrc/wmsa_tma.cuh), whose A operand is the raw token tile:
+      LN(x) W^T + b = rstd*(x Wg^T) - rstd*mean*cs + bf,  Wg = W diag(gamma) rounded to bf16, cs = row sums of that bf16
+    matrix (the mean term then cancels exactly against what the tensor core accumulates), bf = b + W beta.
+    Returns (image, bf, cs), rows in pack_qkv's per-head [q_h; k_h; v_h] order, q rows pre-scaled."""
+    C = wq.shape[0]
+    hd = C // heads
+    w3 = torch.cat([wq.float() * scale, wkv.float()], 0)                          # (3C, C)
+    b3 = torch.cat([bq.float() * scale, bkv.float()], 0)
+    bf = b3 + (w3 * ln_b.float()[None, :]).sum(1)              # same reductions as prepack.py (bit-identical images)
+    wg = (w3 * ln_w.float()[None, :]).to(torch.bfloat16)
+    cs = wg.float().sum(1)
+
+    def per_head(t):
+        return t.view(3, heads, hd, *t.shape[1:]).transpose(0, 1).reshape(heads * 3 * hd, *t.shape[1:])
+    return pack_kmajor(per_head(wg), 3 * hd, "nk"), per_head(bf).contiguous(), per_head(cs).contiguous()
+
+
 def pack_relpos(table: Tensor) -> Tensor:
     """relative_position_bias_table ((2ws-1)^2, heads) -> (heads, (2ws-1)^2) fp32 contiguous."""
     return table.float().t().contiguous()

@@ -25,7 +25,7 @@ def prepack(net: torch.nn.Module) -> int:
         if isinstance(m, LeWinTransformerBlock):
             a = m.attn
             key = (m.dim, m.num_heads, m.mlp.hidden_dim, float(a.scale), a.qkv.to_q.bias is not None, a.qkv.to_kv.bias is not None,
-                   str(a.proj.weight.device))
+                   str(a.proj.weight.device), m.modulator is None)
             groups[key].append(m)
         elif isinstance(m, (Downsample, Upsample)):
             m.packed()                              # four of each, all different shapes: nothing to batch
@@ -56,6 +56,19 @@ def _pack_blocks(blks):
     wcat = w3.view(nb, 3, heads, hd, C).permute(0, 2, 1, 3, 4).reshape(nb * heads * 3 * hd, C)
     wqkv_img = packing.pack_kmajor(wcat, 3 * hd, "nk").view(nb, heads, -1, 3 * hd * 64)
     bqkv = torch.cat([bq * scale, bkv], 1).view(nb, 3, heads, hd).permute(0, 2, 1, 3).reshape(nb, -1).contiguous()
+    # LayerNorm-folded projection for the TMA-gather W-MSA kernel (packing.pack_qkv_fold), blocks without a modulator
+    fold = b0.attn.tma_gather() and b0.modulator is None          # (groups are uniform in modulator presence)
+    if fold:
+        gamma1, beta1 = stack(lambda b: b.norm1.weight), stack(lambda b: b.norm1.bias)
+        b3 = torch.cat([bq * scale, bkv], 1)                                            # (nb, 3C)
+        bf = b3 + (w3 * beta1[:, None, :]).sum(2)
+        wg = (w3 * gamma1[:, None, :]).to(torch.bfloat16)
+        cs = wg.float().sum(2)
+
+        def per_head(t):
+            return t.view(nb, 3, heads, hd, *t.shape[2:]).transpose(1, 2).reshape(nb, heads * 3 * hd, *t.shape[2:])
+        wfold_img = packing.pack_kmajor(per_head(wg).reshape(nb * heads * 3 * hd, C), 3 * hd, "nk").view(nb, heads, -1, 3 * hd * 64)
+        bfold, csq = per_head(bf).contiguous(), per_head(cs).contiguous()
     nchp = min(C, 128)
     wproj_img = packing.pack_kmajor(stack(lambda b: b.attn.proj.weight).view(nb * C, C), nchp, "nk").view(nb, C // nchp, -1, nchp * 64)
     relpos = stack(lambda b: b.attn.relative_position_bias_table).transpose(1, 2).contiguous()          # (nb, heads, 225)
@@ -88,6 +101,10 @@ def _pack_blocks(blks):
         a, m = b.attn, b.mlp
         a._cache.put(a.pack_sources(), dict(wqkv_img=wqkv_img[i], bqkv=bqkv[i], wproj_img=wproj_img[i],
                                             bproj=a.proj.bias.detach().float().contiguous(), relpos=relpos[i], head_dim=hd))
+        if fold:
+            q, kv = a.qkv.to_q, a.qkv.to_kv
+            a._cache_ln.put([q.weight, q.bias, kv.weight, kv.bias, b.norm1.weight, b.norm1.bias],
+                            dict(wqkv_fold_img=wfold_img[i], bqkv_fold=bfold[i], cs_qkv=csq[i]))
         bd = m.dwconv[0].bias.detach().float().contiguous()
         b2 = m.linear2[0].bias.detach().float().contiguous()
         if fused:
