@@ -35,7 +35,7 @@ fi
 if has full; then       # one --set full capture with source correlation of the two dominant kernels
   timeout 300 ncu --set full --import-source on --clock-control none -k regex:leff_fused -s 2 -c 1 -o $out/${tag}_leff_fused_c256 \
     python tools/leff_fused_probe.py 256 64 32 > $out/${tag}_ncu_full1.log 2>&1; echo "ncu full leff rc=$?"
-  timeout 300 ncu --set full --import-source on --clock-control none -k regex:wmsa_kernel --profile-from-start off -c 12 -o $out/${tag}_wmsa_all \
+  timeout 300 ncu --set full --import-source on --clock-control none -k regex:wmsa --profile-from-start off -c 12 -o $out/${tag}_wmsa_all \
     python tools/forward_once.py > $out/${tag}_ncu_full2.log 2>&1; echo "ncu full wmsa rc=$?"
 fi
 ls -la $out | tail -14

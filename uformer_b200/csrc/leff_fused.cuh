@@ -128,41 +128,6 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
 
-// E2 copy-out: staged [128 rows][32 cols] bf16 tile -> out rows (bf16 or fp32), residual (bf16 or fp32) added in fp32.
-// 128 threads; 4 threads per row (8 columns each).
-__device__ __forceinline__ void lf_store_rows(uint32_t stage_s, const int* row_out, const LeffFArgs& a, int col0, int et) {
-#pragma unroll
-  for (int p = 0; p < 4; ++p) {
-    const int i = et + p * 128;
-    const int row = i >> 2, vec = i & 3;
-    const int tok = row_out[row];
-    if (tok < 0) continue;
-    float f[8];
-    unpack8(lds128(stage_s + row * 80 + vec * 16), f);
-    const int c = col0 + vec * 8;
-    if (a.resid != nullptr) {
-      if (a.resid_fp32) {
-        const float* rp = reinterpret_cast<const float*>(a.resid) + (size_t)tok * a.resid_stride + c;
-        const float4 r0 = __ldg(reinterpret_cast<const float4*>(rp)), r1 = __ldg(reinterpret_cast<const float4*>(rp + 4));
-        f[0] += r0.x; f[1] += r0.y; f[2] += r0.z; f[3] += r0.w; f[4] += r1.x; f[5] += r1.y; f[6] += r1.z; f[7] += r1.w;
-      } else {
-        float r[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(a.resid) + (size_t)tok * a.resid_stride + c)), r);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) f[k] += r[k];
-      }
-    }
-    if (a.out_fp32) {
-      float* op = reinterpret_cast<float*>(a.out) + (size_t)tok * a.out_stride + c;
-      *reinterpret_cast<float4*>(op) = make_float4(f[0], f[1], f[2], f[3]);
-      *reinterpret_cast<float4*>(op + 4) = make_float4(f[4], f[5], f[6], f[7]);
-    } else {
-      *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(a.out) + (size_t)tok * a.out_stride + c) = pack8(f);
-    }
-    if (a.out_b != nullptr) *reinterpret_cast<uint4*>(a.out_b + (size_t)tok * a.out_b_stride + c) = pack8(f);
-  }
-}
-
 template <int C>
 __global__ void __launch_bounds__(kLFThreads, 1) leff_fused_kernel(const __grid_constant__ CUtensorMap xmap, const LeffFArgs a) {
   using Cfg = LeffFCfg<C>;
@@ -587,6 +552,7 @@ __global__ void __launch_bounds__(kLFThreads, 1) leff_fused_kernel(const __grid_
           } else {
             *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(a.out) + (size_t)tok[p2] * a.out_stride + c) = pack8(f);
           }
+          if (a.out_b != nullptr) *reinterpret_cast<uint4*>(a.out_b + (size_t)tok[p2] * a.out_b_stride + c) = pack8(f);
         }
         grp_bar();
       }

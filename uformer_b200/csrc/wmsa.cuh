@@ -52,11 +52,11 @@ struct WmsaCfg {
   static constexpr int S_V = S_K + TILE_B;
   static constexpr int S_RING = S_V + TILE_B;
   static constexpr int S_MISC = S_RING + STAGES * STAGE_BYTES;
-  static constexpr int SMEM_BYTES = S_MISC + 4096 + 1024;  // + slack for 1024 B alignment
+  static constexpr int SMEM_BYTES = S_MISC + 5120 + 1024;  // + slack for 1024 B alignment
 };
 
 struct WmsaMisc {
-  float relpos[232];
+  float relpos[2][232];    // bias table of the current / next head
   int row_tok[128];
   uint8_t region[128];
   int win_mixed[2];
@@ -66,7 +66,7 @@ struct WmsaMisc {
   uint64_t bar_d_full[2], bar_d_empty[2];
   uint32_t tmem_base;
 };
-static_assert(sizeof(WmsaMisc) <= 4096, "misc too large");
+static_assert(sizeof(WmsaMisc) <= 5120, "misc too large");
 
 template <int C, int HD>
 __global__ void __launch_bounds__(kThreads8, (C <= 128 && HD <= 32) ? 2 : 1) wmsa_kernel(const lw_wmsa_args a) {
@@ -243,9 +243,9 @@ __global__ void __launch_bounds__(kThreads8, (C <= 128 && HD <= 32) ? 2 : 1) wms
     fence_async_smem();
     mbar_arrive(smem_u32(&ms.bar_xn));
 
-    const uint32_t relpos_s = smem_u32(&ms.relpos[0]);
-    // q|k|v bias of head 0 (later heads are written one head ahead, ordered by the p_ready / o_full chain)
+    // tables of head 0 (later heads are fetched one head ahead, see the head loop)
     if (tid < Cfg::QKV_N) ms.bqkv[0][tid] = __ldg(a.bqkv + tid);
+    if (tid < 225) ms.relpos[0][tid] = __ldg(a.relpos + tid);
     worker_bar8();
     // relative-position index base of this thread's two rows (token i = row & 63: yi = i>>3, xi = i&7)
     const int rp0 = (((r0 & 63) >> 3) + 7) * 15 + (r0 & 7) + 7;
@@ -256,10 +256,14 @@ __global__ void __launch_bounds__(kThreads8, (C <= 128 && HD <= 32) ? 2 : 1) wms
     LW_TRACE_STMT(if (trw) a.trace[tw++] = clock64();)
     for (int h = 0; h < Cfg::NH; ++h) {
       const uint32_t ph = h & 1;
-      // per-head tables -> smem (readers of the previous head are done: they arrived on p_ready / qkv_staged)
-      if (tid < 225) ms.relpos[tid] = __ldg(a.relpos + h * 225 + tid);
-      if (h + 1 < Cfg::NH && tid < Cfg::QKV_N) ms.bqkv[(h + 1) & 1][tid] = __ldg(a.bqkv + (h + 1) * Cfg::QKV_N + tid);
-      const uint32_t bqkv_s = smem_u32(&ms.bqkv[h & 1][0]);
+      // tables of the next head: the loads are issued here and parked in shared memory just before this head's qkv_staged
+      // arrival (their latency hides under the QKV epilogue; every thread past s_full of this head sees them; the slot's
+      // previous readers, head h-1, all arrived on p_ready(h-1) before anyone got here)
+      const bool nxt = h + 1 < Cfg::NH;
+      float rp_n = 0.f, bq_n = 0.f;
+      if (nxt && tid < 225) rp_n = __ldg(a.relpos + (h + 1) * 225 + tid);
+      if (nxt && tid < Cfg::QKV_N) bq_n = __ldg(a.bqkv + (h + 1) * Cfg::QKV_N + tid);
+      const uint32_t bqkv_s = smem_u32(&ms.bqkv[h & 1][0]), relpos_s = smem_u32(&ms.relpos[h & 1][0]);
       // ---- QKV epilogue: + bias -> bf16 -> stmatrix into the Q,K (K-major) and V (row-major = MN-major B) tiles ----
       mbar_wait(smem_u32(&ms.bar_qkv_full), ph);
       tc_fence_after();
@@ -301,6 +305,8 @@ __global__ void __launch_bounds__(kThreads8, (C <= 128 && HD <= 32) ? 2 : 1) wms
           for (int part = 0; part < 3; ++part) qkv_part(v[part], part);
         }
       }
+      if (nxt && tid < 225) ms.relpos[(h + 1) & 1][tid] = rp_n;
+      if (nxt && tid < Cfg::QKV_N) ms.bqkv[(h + 1) & 1][tid] = bq_n;
       fence_async_smem();
       tc_fence_before();
       mbar_arrive(smem_u32(&ms.bar_qkv_staged));

@@ -91,17 +91,17 @@ struct WmsaTCfg {
   static constexpr int S_V = S_K + TILE_B;
   static constexpr int S_RING = S_V + TILE_B;
   static constexpr int S_MISC = S_RING + STAGES * STAGE_BYTES;
-  static constexpr int SMEM_BYTES = S_MISC + 5120 + 1024;
+  static constexpr int SMEM_BYTES = S_MISC + 6144 + 1024;
   static_assert(S_Q % 1024 == 0 && S_RING % 1024 == 0, "operand alignment");
   static_assert(128 * PITCH <= 3 * TILE_B, "staging tile must fit in the Q/K/V tiles");
   static_assert(SMEM_BYTES <= 232448, "smem budget");
 };
 
 struct WmsaTMisc {
-  float relpos[232];
-  int row_tok[128];
-  uint8_t region[128];
-  int win_mixed[2];
+  float relpos[2][232];    // bias table of the current / next head in the stream
+  int row_tok[2][128];     // destination token of every tile row, this / next tile (written one tile ahead)
+  uint8_t region[2][128];
+  int win_mixed[2][2];
   float bqkv[2][96];       // folded q|k|v bias of the current / next head in the stream
   float csq[2][96];        // row sums of the folded weight
   float2 stats[128];       // (rstd, -mean*rstd) per tile row
@@ -111,7 +111,7 @@ struct WmsaTMisc {
   uint64_t bar_d_full, bar_d_empty;
   uint32_t tmem_base;
 };
-static_assert(sizeof(WmsaTMisc) <= 5120, "misc too large");
+static_assert(sizeof(WmsaTMisc) <= 6144, "misc too large");
 
 template <int C, int HD>
 __global__ void __launch_bounds__(kThreads8, C <= 128 ? 2 : 1) wmsa_tma_kernel(const __grid_constant__ CUtensorMap xmap, const WmsaTArgs a) {
@@ -287,17 +287,46 @@ __global__ void __launch_bounds__(kThreads8, C <= 128 ? 2 : 1) wmsa_tma_kernel(c
     // quarter-major row -> window coordinates
     auto row_y = [](int r) { return ((r >> 5) & 1) * 4 + ((r >> 2) & 3); };
     auto row_x = [](int r) { return ((r >> 4) & 1) * 4 + (r & 3); };
-    const uint32_t relpos_s = smem_u32(&ms.relpos[0]);
     constexpr int NBH = HD / 8;
-    bf16* __restrict__ outp = reinterpret_cast<bf16*>(a.out);
-    const bf16* __restrict__ resid = reinterpret_cast<const bf16*>(a.resid);
-    const bool mixed = (a.resid_fp32 | a.out_fp32) != 0 || a.out_b != nullptr;
-    constexpr int NCHS_LOG2 = Cfg::NCHS == 64 ? 6 : Cfg::NCHS == 32 ? 5 : 4;
     constexpr int NBP = Cfg::NCHS / 8;
     const uint32_t stage_s = sQ;
 
     if (tid < Cfg::QKV_N) { ms.bqkv[0][tid] = __ldg(a.bqkv + tid); ms.csq[0][tid] = __ldg(a.cs + tid); }
-    if (Cfg::NH == 1 && tid < 225) ms.relpos[tid] = __ldg(a.relpos + tid);
+    if (tid < 225) ms.relpos[0][tid] = __ldg(a.relpos + tid);
+
+    // destination token of every row + region id of the shift mask for this CTA's tile number itn -> table buffer itn & 1.
+    // Tables are built one tile ahead, underneath the projection GEMM of the previous tile (threads 0..127, one row each).
+    auto build_rows = [&](int itn) {
+      const int tile_n = blockIdx.x + itn * gridDim.x, nb = itn & 1;
+      const int r = tid, wlr = r >> 6;
+      const int w = tile_n * 2 + wlr;
+      int tok = -1;
+      uint8_t reg = 0;
+      if (w < a.n_windows) {
+        const int b = w / nwin_img, wi = w - b * nwin_img;
+        const int ry = (wi / nwx) * 8 + row_y(r), rx = (wi % nwx) * 8 + row_x(r);       // rolled coordinates
+        int y = ry + a.shift, x = rx + a.shift;
+        if (y >= a.H) y -= a.H;
+        if (x >= a.W) x -= a.W;
+        tok = (b * a.H + y) * a.W + x;
+        if (a.shift > 0) {
+          const int gy = (ry >= a.H - 8) + (ry >= a.H - a.shift);
+          const int gx = (rx >= a.W - 8) + (rx >= a.W - a.shift);
+          reg = (uint8_t)(3 * gy + gx);
+        }
+      }
+      ms.row_tok[nb][r] = tok;
+      ms.region[nb][r] = reg;
+      if ((r & 63) == 0) ms.win_mixed[nb][wlr] = 0;
+    };
+    auto mark_mixed = [&](int itn) {                     // after a barrier behind build_rows: does a window straddle shift regions?
+      const int nb = itn & 1;
+      if (a.shift > 0 && ms.region[nb][tid] != ms.region[nb][(tid >> 6) * 64]) ms.win_mixed[nb][tid >> 6] = 1;
+    };
+    if (tid < 128) build_rows(0);
+    worker_bar8();
+    if (tid < 128) mark_mixed(0);
+    worker_bar8();
 
     LW_TRACE_STMT(const bool trw = (a.dbg & 16) && blockIdx.x == 0 && tid == 0 && a.trace != nullptr; int tw = 0;)
     int g = 0;
@@ -305,31 +334,7 @@ __global__ void __launch_bounds__(kThreads8, C <= 128 ? 2 : 1) wmsa_tma_kernel(c
       const int tile = blockIdx.x + it * gridDim.x;
       const int buf = it % Cfg::NXB;
       LW_TRACE_STMT(if (trw && it < 3) a.trace[tw++] = clock64();)
-      // ---- destination token of every row + region id of the shift mask ----
-      if (tid < 128) {
-        const int r = tid, wlr = r >> 6;
-        const int w = tile * 2 + wlr;
-        int tok = -1;
-        uint8_t reg = 0;
-        if (w < a.n_windows) {
-          const int b = w / nwin_img, wi = w - b * nwin_img;
-          const int ry = (wi / nwx) * 8 + row_y(r), rx = (wi % nwx) * 8 + row_x(r);       // rolled coordinates
-          int y = ry + a.shift, x = rx + a.shift;
-          if (y >= a.H) y -= a.H;
-          if (x >= a.W) x -= a.W;
-          tok = (b * a.H + y) * a.W + x;
-          if (a.shift > 0) {
-            const int gy = (ry >= a.H - 8) + (ry >= a.H - a.shift);
-            const int gx = (rx >= a.W - 8) + (rx >= a.W - a.shift);
-            reg = (uint8_t)(3 * gy + gx);
-          }
-        }
-        ms.row_tok[r] = tok;
-        ms.region[r] = reg;
-        if ((r & 63) == 0) ms.win_mixed[wlr] = 0;
-      }
-      worker_bar8();
-      if (tid < 128 && a.shift > 0 && ms.region[tid] != ms.region[(tid >> 6) * 64]) ms.win_mixed[tid >> 6] = 1;
+      const int rb = it & 1;                             // row-table buffer of this tile
       // ---- LayerNorm statistics of this warp's 16 rows from the landed tile (one shifted pass, as in leff_fused.cuh) ----
       wt_wait(smem_u32(&ms.bar_x_full[buf]), (it / Cfg::NXB) & 1);
       {
@@ -380,13 +385,16 @@ __global__ void __launch_bounds__(kThreads8, C <= 128 ? 2 : 1) wmsa_tma_kernel(c
 
       for (int h = 0; h < Cfg::NH; ++h, ++g) {
         const uint32_t ph = g & 1;
-        if (Cfg::NH > 1 && tid < 225) ms.relpos[tid] = __ldg(a.relpos + h * 225 + tid);
-        if (tid < Cfg::QKV_N && (h + 1 < Cfg::NH || it + 1 < n_my)) {       // tables of the next head of the stream
-          const int hn = (h + 1 < Cfg::NH) ? h + 1 : 0;
-          ms.bqkv[(g + 1) & 1][tid] = __ldg(a.bqkv + hn * Cfg::QKV_N + tid);
-          ms.csq[(g + 1) & 1][tid] = __ldg(a.cs + hn * Cfg::QKV_N + tid);
-        }
-        const uint32_t bqkv_s = smem_u32(&ms.bqkv[g & 1][0]), cs_s = smem_u32(&ms.csq[g & 1][0]);
+        // tables of the next head of the stream (next head, or head 0 of the next tile): the loads are issued here and parked
+        // in shared memory just before this head's qkv_staged arrival, so that their latency hides under the QKV epilogue and
+        // every thread that has passed s_full of this head sees them
+        const bool nxt = Cfg::NH > 1 && (h + 1 < Cfg::NH || it + 1 < n_my);
+        const int hn = (h + 1 < Cfg::NH) ? h + 1 : 0;
+        float rp_n = 0.f, bq_n = 0.f, cs_n = 0.f;
+        if (nxt && tid < 225) rp_n = __ldg(a.relpos + hn * 225 + tid);
+        if (nxt && tid < Cfg::QKV_N) { bq_n = __ldg(a.bqkv + hn * Cfg::QKV_N + tid); cs_n = __ldg(a.cs + hn * Cfg::QKV_N + tid); }
+        const int slot = (Cfg::NH == 1) ? 0 : (g & 1);            // a single head never changes its tables
+        const uint32_t bqkv_s = smem_u32(&ms.bqkv[slot][0]), cs_s = smem_u32(&ms.csq[slot][0]), relpos_s = smem_u32(&ms.relpos[slot][0]);
         // ---- QKV epilogue: LayerNorm fold + bias -> bf16 -> Q, K (K-major) and V (row-major) tiles ----
         wt_wait(smem_u32(&ms.bar_qkv_full), ph);
         tc_fence_after();
@@ -424,6 +432,8 @@ __global__ void __launch_bounds__(kThreads8, C <= 128 ? 2 : 1) wmsa_tma_kernel(c
               stsm_x4(tile_s + swz<Cfg::SWH>(row, (2 * i2 + (m >> 1)) * 16), pk[4 * i2], pk[4 * i2 + 1], pk[4 * i2 + 2], pk[4 * i2 + 3]);
           }
         }
+        if (nxt && tid < 225) ms.relpos[slot ^ 1][tid] = rp_n;
+        if (nxt && tid < Cfg::QKV_N) { ms.bqkv[slot ^ 1][tid] = bq_n; ms.csq[slot ^ 1][tid] = cs_n; }
         fence_async_smem();
         tc_fence_before();
         mbar_arrive(smem_u32(&ms.bar_qkv_staged));
@@ -451,13 +461,13 @@ __global__ void __launch_bounds__(kThreads8, C <= 128 ? 2 : 1) wmsa_tma_kernel(c
               s1[2 * b + e] = __uint_as_float(v[4 * b + 2 + e]) + lds32f(relpos_s + (rp1 - koff) * 4);
             }
           }
-          if (ms.win_mixed[wl]) {
-            const uint8_t g0 = ms.region[r0], g1 = ms.region[r1];
+          if (ms.win_mixed[rb][wl]) {
+            const uint8_t g0 = ms.region[rb][r0], g1 = ms.region[rb][r1];
 #pragma unroll
             for (int b = 0; b < 8; ++b)
 #pragma unroll
               for (int e = 0; e < 2; ++e) {
-                const uint8_t gk = ms.region[wl * 64 + 8 * b + 2 * tq + e];
+                const uint8_t gk = ms.region[rb][wl * 64 + 8 * b + 2 * tq + e];
                 s0[2 * b + e] += (gk != g0) ? -100.0f : 0.0f;
                 s1[2 * b + e] += (gk != g1) ? -100.0f : 0.0f;
               }
@@ -533,7 +543,60 @@ __global__ void __launch_bounds__(kThreads8, C <= 128 ? 2 : 1) wmsa_tma_kernel(c
       mbar_arrive(smem_u32(&ms.bar_oall));
       LW_TRACE_STMT(if (trw && it < 3) a.trace[tw++] = clock64();)
 
-      // ---- projection epilogue: + bias -> bf16 -> staging tile (the dead Q/K/V tiles) -> coalesced scatter with the shortcut ----
+      // ---- projection epilogue: + bias -> bf16 -> staging tile (the dead Q/K/V tiles) -> coalesced scatter with the shortcut.
+      // The shortcut rows of a round are fetched into registers before the round's accumulator is waited for. ----
+      if (tid < 128 && it + 1 < n_my) build_rows(it + 1);          // next tile's row tables, under the projection GEMM
+      constexpr int VPR = Cfg::NCHS / 8;                             // 16-byte vectors per row and round
+      constexpr int VPT = 128 * VPR / kWorkers8;                     // vectors per thread and round: 4 / 2 / 1
+      int tok[VPT];
+      uint4 rv[VPT][2];
+      auto fetch_resid = [&](int col0) {
+#pragma unroll
+        for (int k = 0; k < VPT; ++k) {
+          const int i = tid + k * kWorkers8, row = i / VPR, vec = i % VPR;
+          tok[k] = ms.row_tok[rb][row];
+          if (tok[k] >= 0 && a.resid != nullptr) {
+            const size_t off = (size_t)tok[k] * C + col0 + vec * 8;
+            if (a.resid_fp32) {
+              rv[k][0] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(a.resid) + off));
+              rv[k][1] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(a.resid) + off + 4));
+            } else {
+              rv[k][0] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(a.resid) + off));
+            }
+          }
+        }
+      };
+      auto store_round = [&](int col0) {
+#pragma unroll
+        for (int k = 0; k < VPT; ++k) {
+          if (tok[k] < 0) continue;
+          const int i = tid + k * kWorkers8, row = i / VPR, vec = i % VPR;
+          float f[8];
+          unpack8(lds128(stage_s + row * Cfg::PITCH + vec * 16), f);
+          if (a.resid != nullptr) {
+            if (a.resid_fp32) {
+              const uint4 p = rv[k][0], q = rv[k][1];
+              f[0] += __uint_as_float(p.x); f[1] += __uint_as_float(p.y); f[2] += __uint_as_float(p.z); f[3] += __uint_as_float(p.w);
+              f[4] += __uint_as_float(q.x); f[5] += __uint_as_float(q.y); f[6] += __uint_as_float(q.z); f[7] += __uint_as_float(q.w);
+            } else {
+              float r[8];
+              unpack8(rv[k][0], r);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] += r[e];
+            }
+          }
+          const size_t off = (size_t)tok[k] * C + col0 + vec * 8;
+          if (a.out_fp32) {
+            float* op = reinterpret_cast<float*>(a.out) + off;
+            *reinterpret_cast<float4*>(op) = make_float4(f[0], f[1], f[2], f[3]);
+            *reinterpret_cast<float4*>(op + 4) = make_float4(f[4], f[5], f[6], f[7]);
+          } else {
+            *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(a.out) + off) = pack8(f);
+          }
+          if (a.out_b != nullptr) *reinterpret_cast<uint4*>(a.out_b + off) = pack8(f);
+        }
+      };
+      fetch_resid(0);
       for (int nc = 0; nc < Cfg::NC; ++nc) {
         const int pc = it * Cfg::NC + nc;
         wt_wait(smem_u32(&ms.bar_d_full), pc & 1);
@@ -554,11 +617,13 @@ __global__ void __launch_bounds__(kThreads8, C <= 128 ? 2 : 1) wmsa_tma_kernel(c
           uint32_t pk[2 * NBP];
           frag_bias_act_pack<NBP, false>(v, bb, pk);
           stage_frag<NBP>(stage_s, Cfg::PITCH, row16, 0, pk);
-          if (c0 + Cfg::NCHS >= Cfg::NCH) { tc_fence_before(); mbar_arrive(smem_u32(&ms.bar_d_empty)); }
-          worker_bar8();
-          if (mixed) store_staged_rows_mixed<kWorkers8>(stage_s, Cfg::PITCH, NCHS_LOG2, smem_u32(ms.row_tok), a.out, a.resid, a.out_b, a.resid_fp32 != 0,
-                                                         a.out_fp32 != 0, (size_t)C, nc * Cfg::NCH + c0, tid);
-          else store_staged_rows(stage_s, Cfg::PITCH, NCHS_LOG2, ms.row_tok, outp, resid, (size_t)C, nc * Cfg::NCH + c0, tid, kWorkers8);
+          const bool last_round = c0 + Cfg::NCHS >= Cfg::NCH;
+          if (last_round) { tc_fence_before(); mbar_arrive(smem_u32(&ms.bar_d_empty)); }
+          worker_bar8();                                   // (also: build_rows of the next tile is complete)
+          if (nc == 0 && c0 == 0 && tid < 128 && it + 1 < n_my) mark_mixed(it + 1);
+          const int col0 = nc * Cfg::NCH + c0;
+          store_round(col0);
+          if (!(last_round && nc + 1 == Cfg::NC)) fetch_resid(col0 + Cfg::NCHS);      // next round's shortcut rows
           worker_bar8();
         }
       }
