@@ -43,6 +43,10 @@ int lw_check_device(void);
  * lets a binding (uformer_b200/_lib.py mirrors the structs with ctypes) verify its layout; -1 for an unknown id. */
 int lw_struct_size(int id);
 
+/* Test hook: cap the grid of the persistent kernels (fused LeFF, LeFF part 2, TMA-gather W-MSA) at n CTAs so that small test
+ * inputs walk several tiles per CTA; 0 restores the default (one or two CTAs per SM). */
+void lw_set_max_ctas(int n);
+
 /* Rows per weight-image chunk the A-resident GEMM kernels (lw_leff1_fwd, lw_upsample_fwd) expect for
  * reduction depth K and output width n_total: the host packer must cut w1_img / w_img with this value. */
 int lw_nch_ares(int K, int n_total);

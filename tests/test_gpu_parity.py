@@ -334,3 +334,67 @@ def test_launch_on_non_current_device():
     torch.cuda.synchronize("cuda:1")
     assert y.device.index == 1 and torch.cuda.current_device() == 0
     _check(y.float().cpu(), O.lewin_block(x.float(), st, "", 2, 8, 4), "block on cuda:1 with cuda:0 current")
+
+
+@pytest.mark.parametrize("dim,heads,H,B,shift,max_ctas", [
+    (32, 1, 16, 2, 4, 0), (32, 1, 24, 1, 4, 2), (64, 2, 16, 3, 0, 1), (128, 4, 16, 2, 4, 2), (128, 4, 8, 3, 4, 1),     # 8x8 x 3 images: odd window count
+    (256, 8, 16, 2, 4, 3), (256, 16, 16, 1, 0, 1), (16, 1, 24, 1, 4, 2),
+])
+def test_wmsa_tma_gather_kernel(dim, heads, H, B, shift, max_ctas):
+    """Persistent TMA-gather W-MSA (csrc/wmsa_tma.cuh; lw_wmsa_fwd takes it when the LayerNorm-folded projection is passed):
+    the attention half of a block, x + reverse(W-MSA(partition(roll(LN1(x))))) (model.py:951-986), against the oracle — bf16
+    stream, fp32 residual stream gathered through its bf16 copy, and the explicit-mask path.  `max_ctas` caps the grid
+    (lw_set_max_ctas) so that every CTA walks several tiles: barrier phases, gather-buffer rotation, cross-tile prefetch."""
+    import math
+    import uformer_b200 as U
+    from uformer_b200 import _lib, ops
+    from oracle import lewin_oracle as O
+    from paramgen import randomize_state
+    torch.manual_seed(dim + H + shift)
+    blk = U.LeWinTransformerBlock(dim, (16, 16), heads, win_size=8, shift_size=shift).eval()
+    st = randomize_state(blk.state_dict(), 17)
+    blk.load_state_dict(st)
+    blk = blk.to(DEV)
+    pa = blk._attn_operands()
+    assert "wqkv_fold_img" in pa and _lib.load().lw_wmsa_tma_supported(dim, dim // heads)      # the TMA path is the one under test
+    x = torch.randn(B, H * H, dim).to(torch.bfloat16)
+    r32 = x.float() + 1e-3 * torch.randn(B, H * H, dim)        # an fp32 stream whose bf16 rounding is x
+
+    def attn_half(xf, mask=None):
+        y = O.layer_norm(xf, st["norm1.weight"], st["norm1.bias"]).reshape(B, H, H, dim)
+        if shift:
+            y = torch.roll(y, (-shift, -shift), (1, 2))
+        m = O.shift_attn_mask(H, H, 8, shift) if shift else None
+        if mask is not None:
+            m = mask if m is None else mask + m
+        a = O.window_attention(O.window_partition(y, 8).reshape(-1, 64, dim), st, "attn.", heads, 8, m)
+        y = O.window_reverse(a.reshape(-1, 8, 8, dim), 8, H, H)
+        if shift:
+            y = torch.roll(y, (shift, shift), (1, 2))
+        return y.reshape(B, H * H, dim)
+
+    lib = _lib.load()
+    lib.lw_set_max_ctas(max_ctas)
+    try:
+        with torch.no_grad():
+            xd = x.to(DEV)
+            y = ops.wmsa(xd, pa, H=H, W=H, shift=shift, windowed=False, resid=xd)
+            y32, y32b = ops.wmsa(r32.to(DEV), pa, H=H, W=H, shift=shift, windowed=False, resid=r32.to(DEV), out_dtype=torch.float32,
+                                 bf16_copy=True, x_b=xd)
+            ym = None
+            if shift == 0 or B == 1:                          # (the reference cannot combine an input mask with a shift at batch > 1)
+                nw = B * (H // 8) ** 2
+                mask = torch.where(torch.rand(nw, 64, 64) < 0.25, -100.0, 0.0)
+                ym = ops.wmsa(xd, pa, H=H, W=H, shift=shift, windowed=False, resid=xd, mask=mask.to(DEV))
+        torch.cuda.synchronize()
+    finally:
+        lib.lw_set_max_ctas(0)
+    branch = attn_half(x.float())
+    _check(y.float().cpu(), x.float() + branch, f"wmsa-tma C={dim} h={heads} s={shift}")
+    _check(y.float().cpu() - x.float(), branch, f"wmsa-tma C={dim} h={heads} s={shift} (branch)")
+    assert y32.dtype == torch.float32 and torch.equal(y32b, y32.to(torch.bfloat16))
+    _check(y32.cpu() - r32, branch, f"wmsa-tma fp32 stream C={dim} (branch)")
+    if ym is not None:
+        if shift:
+            mask = mask.view(1, -1, 64, 64).reshape(-1, 64, 64)
+        _check(ym.float().cpu() - x.float(), attn_half(x.float(), mask), f"wmsa-tma explicit mask C={dim} (branch)")

@@ -217,3 +217,36 @@ def test_torch_cuda_attribute_chains_exist():
             if not hasattr(torch.cuda, m.group(1)):
                 bad.append((os.path.basename(f), m.group(0)))
     assert not bad, bad
+
+
+def test_qkv_layernorm_fold_identity():
+    """packing.pack_qkv_fold: LN(x) Wqkv^T + b == rstd*(x Wg^T) - rstd*mean*cs + bf (the TMA-gather W-MSA kernel's projection,
+    csrc/wmsa_tma.cuh), with Wg rounded to bf16 and cs taken from the rounded matrix; rows in pack_qkv's per-head order."""
+    from uformer_b200 import packing
+    torch.manual_seed(3)
+    C, heads = 64, 2
+    hd = C // heads
+    wq, bq, wkv, bkv = torch.randn(C, C) * 0.1, torch.randn(C) * 0.1, torch.randn(2 * C, C) * 0.1, torch.randn(2 * C) * 0.1
+    g, b = 1 + 0.2 * torch.randn(C), 0.1 * torch.randn(C)
+    scale = hd ** -0.5
+    img, bf, cs = packing.pack_qkv_fold(wq, bq, wkv, bkv, heads, scale, g, b)
+    img0, b0 = packing.pack_qkv(wq, bq, wkv, bkv, heads, scale)
+    assert img.shape == img0.shape and img.dtype == torch.bfloat16 and bf.shape == b0.shape == cs.shape
+    wg = packing.unpack_kmajor(img, heads * 3 * hd, C, 3 * hd, "nk")
+    w0 = packing.unpack_kmajor(img0, heads * 3 * hd, C, 3 * hd, "nk")
+    assert torch.equal(cs, wg.sum(1))
+    x = torch.randn(50, C) * 3 + 1.5
+    mean = x.mean(1, keepdim=True)
+    rstd = torch.rsqrt(x.var(1, unbiased=False, keepdim=True) + 1e-5)
+    folded = rstd * (x @ wg.t()) - rstd * mean * cs + bf
+    direct = torch.nn.functional.layer_norm(x, (C,), g, b) @ w0.t() + b0
+    assert (folded - direct).abs().max() < 2e-2 * direct.abs().max()              # bf16 weight rounding on both sides
+    # exact in fp64 without the bf16 rounding of the weights
+    w3 = torch.cat([wq * scale, wkv], 0).double()
+    x64 = x.double()
+    ln = torch.nn.functional.layer_norm(x64, (C,), g.double(), b.double())
+    m64, r64 = x64.mean(1, keepdim=True), torch.rsqrt(x64.var(1, unbiased=False, keepdim=True) + 1e-5)
+    wg64 = w3 * g.double()[None]
+    lhs = ln @ w3.t()
+    rhs = r64 * (x64 @ wg64.t()) - r64 * m64 * wg64.sum(1) + (w3 * b.double()[None]).sum(1)
+    assert (lhs - rhs).abs().max() < 1e-9

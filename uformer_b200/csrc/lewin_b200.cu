@@ -101,6 +101,15 @@ static int sm_count() {
   return cached > 0 ? cached : 148;
 }
 
+// Test hook (lw_set_max_ctas): caps the grid of the persistent kernels so that small test inputs still walk several tiles per
+// CTA (the multi-tile paths: barrier phases, buffer rotation, cross-tile prefetch).  0 = no cap.
+static std::atomic<int> g_max_ctas{0};
+extern "C" void lw_set_max_ctas(int n) { g_max_ctas.store(n < 0 ? 0 : n); }
+static int cap_grid(int grid) {
+  const int c = g_max_ctas.load(std::memory_order_relaxed);
+  return (c > 0 && c < grid) ? c : grid;
+}
+
 static int pow2_cols(int n) {
   int c = 32;
   while (c < n) c <<= 1;
@@ -232,7 +241,7 @@ extern "C" int lw_leff2_fwd(const lw_leff2_args* p, lw_stream_t stream) {
   if ((long long)p->B * p->H * p->W * p->hidden >= (1ll << 32)) return LW_ERR_BAD_SHAPE;   // 32-bit element offsets in the halo prefetch
   const int nbuf_d = (2 * a.N <= 512) ? 2 : 1;                 // double-buffer the TMEM accumulator when it fits
   LW_ENSURE_SMEM(leff2_kernel, Leff2Cfg::SMEM_BYTES);
-  const int grid = tiles < sm_count() ? tiles : sm_count();    // persistent: one CTA per SM
+  const int grid = cap_grid(tiles < sm_count() ? tiles : sm_count());    // persistent: one CTA per SM
   leff2_kernel<<<grid, kL2Threads, Leff2Cfg::SMEM_BYTES, st>>>(a, pow2_cols(nbuf_d * a.N), tiles, nbuf_d);
   LW_TRY(cudaGetLastError());
   return LW_OK;
@@ -284,7 +293,7 @@ static int launch_wmsa_tma(const CUtensorMap& map, const WmsaTArgs& a, cudaStrea
   using Cfg = WmsaTCfg<C, HD>;
   LW_ENSURE_SMEM((wmsa_tma_kernel<C, HD>), Cfg::SMEM_BYTES);
   const int cap = sm_count() * (C <= 128 ? 2 : 1);
-  const int grid = a.n_tiles < cap ? a.n_tiles : cap;
+  const int grid = cap_grid(a.n_tiles < cap ? a.n_tiles : cap);
   wmsa_tma_kernel<C, HD><<<grid, kThreads8, Cfg::SMEM_BYTES, st>>>(map, a);
   LW_TRY(cudaGetLastError());
   return LW_OK;
@@ -322,7 +331,7 @@ template <int C>
 static int launch_leff_fused(const CUtensorMap& map, const LeffFArgs& a, cudaStream_t st) {
   using Cfg = LeffFCfg<C>;
   LW_ENSURE_SMEM(leff_fused_kernel<C>, Cfg::SMEM_BYTES);
-  const int grid = a.n_tiles < sm_count() ? a.n_tiles : sm_count();
+  const int grid = cap_grid(a.n_tiles < sm_count() ? a.n_tiles : sm_count());
   leff_fused_kernel<C><<<grid, kLFThreads, Cfg::SMEM_BYTES, st>>>(map, a);
   LW_TRY(cudaGetLastError());
   return LW_OK;
