@@ -84,13 +84,16 @@ typedef struct lw_wmsa_args {
   int32_t out_fp32;        /* out is fp32 */
   void* out_b;             /* optional bf16 copy of out (same layout): the GEMM operand of the LeFF kernel that follows */
   /* TMA-gather path (persistent kernel, csrc/wmsa_tma.cuh).  Taken when wqkv_fold_img != NULL and the call is eligible:
-   * token-map input (windowed = 0), LayerNorm present, no modulator, lw_wmsa_tma_supported(C, head_dim), shift % 4 == 0, and a
-   * bf16 source for the gather (x itself, or x_b when x_fp32).  Otherwise the fields are ignored and wmsa_kernel runs.
+   * token-map input (windowed = 0), LayerNorm present, lw_wmsa_tma_supported(C, head_dim), shift % 4 == 0, a bf16 source for
+   * the gather (x itself, or x_b when x_fp32) and, if there is a modulator, its folded image.  Otherwise the fields are ignored
+   * and wmsa_kernel runs.
    * LayerNorm is folded into the projection: LN(x) Wqkv^T + b = rstd*(x Wg^T) - rstd*mean*cs + bf. */
   const void* wqkv_fold_img; /* Wg = Wqkv diag(ln_w) rounded to bf16, packed like wqkv_img */
   const float* bqkv_fold;    /* bf = bqkv + Wqkv ln_b, (heads, 3*hd) */
   const float* cs_qkv;       /* row sums of the bf16 Wg, (heads, 3*hd) */
   const void* x_b;           /* bf16 copy of an fp32 x (what the previous kernel wrote as its out_b), or NULL */
+  const void* wmod_fold_img; /* with a modulator: packed bf16 [heads][3*hd rows x 64 positions]: (modulator Wqkv^T)^T per head,
+                                positions in the kernel's quarter-major window order (packing.pack_qkv_fold); else NULL */
 } lw_wmsa_args;
 int lw_wmsa_fwd(const lw_wmsa_args* a, lw_stream_t stream);
 /* 1 if the TMA-gather W-MSA kernel is built for (C, head_dim): C in {16,32,64,128,256}, head_dim in {16,32}. */

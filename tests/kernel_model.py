@@ -50,7 +50,7 @@ def _shift_mask(H, W, shift):
 def _wmsa_tma_eligible(x, p, shift, windowed, x_b):
     """lw_wmsa_fwd's choice of the TMA-gather kernel (include/lewin_b200.h, lw_wmsa_args.wqkv_fold_img)."""
     C = x.shape[-1]
-    return ("wqkv_fold_img" in p and not windowed and p.get("modulator") is None and p.get("ln_w") is not None and shift % 4 == 0
+    return ("wqkv_fold_img" in p and not windowed and (p.get("modulator") is None or "wmod_fold_img" in p) and p.get("ln_w") is not None and shift % 4 == 0
             and (x.dtype == BF or x_b is not None) and bool(_lib.load().lw_wmsa_tma_supported(C, p["head_dim"])))
 
 
@@ -78,7 +78,7 @@ def wmsa(x, p, *, H, W, shift, windowed, resid, mask=None, out=None, out_dtype=N
         if shift:
             m = torch.roll(m, (-shift, -shift), (1, 2))
         xw = _partition(m)
-    if p.get("modulator") is not None:
+    if p.get("modulator") is not None and not fold:
         xw = xw + p["modulator"]
     xw = _q(xw)                                                   # A operand is bf16
     nW = xw.shape[0]
@@ -86,7 +86,14 @@ def wmsa(x, p, *, H, W, shift, windowed, resid, mask=None, out=None, out_dtype=N
         wg = packing.unpack_kmajor(p["wqkv_fold_img"], heads * 3 * hd, C, 3 * hd, "nk")
         mean = xw.mean(-1, keepdim=True)
         rstd = torch.rsqrt(((xw - mean) ** 2).mean(-1, keepdim=True) + p.get("ln_eps", 1e-5))
-        qkv = (rstd * (xw @ wg.t()) - (rstd * mean) * p["cs_qkv"] + p["bqkv_fold"]).view(nW, 64, heads, 3, hd)
+        acc = xw @ wg.t()
+        if p.get("modulator") is not None:
+            # one-hot k-block: sigma (bf16) on the diagonal x the bf16 image of (m W^T)^T, accumulated with the projection
+            mwq = packing.unpack_kmajor(p["wmod_fold_img"], heads * 3 * hd, 64, 3 * hd, "nk")       # columns: quarter-major positions
+            mw = torch.empty_like(mwq)
+            mw[:, packing.quarter_major_positions()] = mwq                                           # -> natural positions
+            acc = acc + _q(1.0 / rstd) * mw.t()[None]
+        qkv = (rstd * acc - (rstd * mean) * p["cs_qkv"] + p["bqkv_fold"]).view(nW, 64, heads, 3, hd)
     else:
         wcat = packing.unpack_kmajor(p["wqkv_img"], heads * 3 * hd, C, 3 * hd, "nk")        # [head][q|k|v][hd] rows, q pre-scaled
         qkv = (xw @ wcat.t() + p["bqkv"]).view(nW, 64, heads, 3, hd)

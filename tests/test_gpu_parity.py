@@ -336,14 +336,17 @@ def test_launch_on_non_current_device():
     _check(y.float().cpu(), O.lewin_block(x.float(), st, "", 2, 8, 4), "block on cuda:1 with cuda:0 current")
 
 
-@pytest.mark.parametrize("dim,heads,H,B,shift,max_ctas", [
-    (32, 1, 16, 2, 4, 0), (32, 1, 24, 1, 4, 2), (64, 2, 16, 3, 0, 1), (128, 4, 16, 2, 4, 2), (128, 4, 8, 3, 4, 1),     # 8x8 x 3 images: odd window count
-    (256, 8, 16, 2, 4, 3), (256, 16, 16, 1, 0, 1), (16, 1, 24, 1, 4, 2),
+@pytest.mark.parametrize("dim,heads,H,B,shift,max_ctas,modu", [
+    (32, 1, 16, 2, 4, 0, False), (32, 1, 24, 1, 4, 2, False), (64, 2, 16, 3, 0, 1, False), (128, 4, 16, 2, 4, 2, False),
+    (128, 4, 8, 3, 4, 1, False),                                                         # 8x8 x 3 images: odd window count
+    (256, 8, 16, 2, 4, 3, False), (256, 16, 16, 1, 0, 1, False), (16, 1, 24, 1, 4, 2, False),
+    (64, 2, 16, 2, 4, 1, True), (128, 4, 16, 2, 4, 2, True), (256, 8, 16, 3, 4, 2, True), (32, 1, 16, 1, 0, 1, True), (16, 1, 16, 2, 4, 0, True),
 ])
-def test_wmsa_tma_gather_kernel(dim, heads, H, B, shift, max_ctas):
+def test_wmsa_tma_gather_kernel(dim, heads, H, B, shift, max_ctas, modu):
     """Persistent TMA-gather W-MSA (csrc/wmsa_tma.cuh; lw_wmsa_fwd takes it when the LayerNorm-folded projection is passed):
     the attention half of a block, x + reverse(W-MSA(partition(roll(LN1(x))))) (model.py:951-986), against the oracle — bf16
-    stream, fp32 residual stream gathered through its bf16 copy, and the explicit-mask path.  `max_ctas` caps the grid
+    stream, fp32 residual stream gathered through its bf16 copy, the explicit-mask path, and the window modulator (added by a
+    one-hot k-block on the tensor core).  `max_ctas` caps the grid
     (lw_set_max_ctas) so that every CTA walks several tiles: barrier phases, gather-buffer rotation, cross-tile prefetch."""
     import math
     import uformer_b200 as U
@@ -351,12 +354,13 @@ def test_wmsa_tma_gather_kernel(dim, heads, H, B, shift, max_ctas):
     from oracle import lewin_oracle as O
     from paramgen import randomize_state
     torch.manual_seed(dim + H + shift)
-    blk = U.LeWinTransformerBlock(dim, (16, 16), heads, win_size=8, shift_size=shift).eval()
+    blk = U.LeWinTransformerBlock(dim, (16, 16), heads, win_size=8, shift_size=shift, modulator=modu).eval()
     st = randomize_state(blk.state_dict(), 17)
     blk.load_state_dict(st)
     blk = blk.to(DEV)
     pa = blk._attn_operands()
     assert "wqkv_fold_img" in pa and _lib.load().lw_wmsa_tma_supported(dim, dim // heads)      # the TMA path is the one under test
+    assert ("wmod_fold_img" in pa) == modu
     x = torch.randn(B, H * H, dim).to(torch.bfloat16)
     r32 = x.float() + 1e-3 * torch.randn(B, H * H, dim)        # an fp32 stream whose bf16 rounding is x
 
@@ -367,7 +371,10 @@ def test_wmsa_tma_gather_kernel(dim, heads, H, B, shift, max_ctas):
         m = O.shift_attn_mask(H, H, 8, shift) if shift else None
         if mask is not None:
             m = mask if m is None else mask + m
-        a = O.window_attention(O.window_partition(y, 8).reshape(-1, 64, dim), st, "attn.", heads, 8, m)
+        win = O.window_partition(y, 8).reshape(-1, 64, dim)
+        if modu:
+            win = win + st["modulator.weight"]                 # model.py:966-969
+        a = O.window_attention(win, st, "attn.", heads, 8, m)
         y = O.window_reverse(a.reshape(-1, 8, 8, dim), 8, H, H)
         if shift:
             y = torch.roll(y, (shift, shift), (1, 2))

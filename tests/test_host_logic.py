@@ -141,13 +141,13 @@ def test_batched_prepack_is_bit_identical_to_lazy_packing():
             if isinstance(m, M.LeWinTransformerBlock):
                 calls += [(m, m._cache, m.packed), (m.attn, m.attn._cache, m.attn.packed),
                           (m.mlp, m.mlp._cache_ln, lambda mm=m: mm.mlp.packed(mm.norm2))]
-                if m.modulator is None and m.attn.tma_gather():           # LayerNorm-folded projection of the TMA-gather W-MSA
-                    calls.append((m.attn, m.attn._cache_ln, lambda mm=m: mm.attn.packed_fold(mm.norm1)))
+                if m.attn.tma_gather():                                   # LayerNorm-folded projection (+ modulator image) of the TMA-gather W-MSA
+                    calls.append((m.attn, m.attn._cache_ln, lambda mm=m: mm.attn.packed_fold(mm.norm1, mm.modulator)))
             elif isinstance(m, (M.Downsample, M.Upsample)):
                 calls.append((m, m._cache, m.packed))
         lazy = [{k: (v.clone() if torch.is_tensor(v) else v) for k, v in call().items()} for _, _, call in calls]
         assert any("w1f_img" in d for d in lazy) and (cfg["embed_dim"] == 16 or any("w1_img" in d for d in lazy))   # both LeFF paths
-        assert cfg["modulator"] or any("wqkv_fold_img" in d for d in lazy)
+        assert any("wqkv_fold_img" in d for d in lazy) and (not cfg["modulator"] or any("wmod_fold_img" in d for d in lazy))
         M.invalidate_packed()
         assert prepack(net) == sum(cfg["depths"]) + 8
         for (m, cache, call), want in zip(calls, lazy):

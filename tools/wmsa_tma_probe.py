@@ -13,6 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+MODULATOR = os.environ.get("PROBE_MODULATOR", "0") == "1"          # probe the modulated (decoder-type) blocks instead
 SHAPES = [(32, 1, 16, 1, 0), (32, 1, 16, 2, 4), (64, 2, 24, 1, 4), (128, 4, 16, 2, 4), (256, 8, 16, 1, 4), (256, 8, 16, 2, 0), (16, 1, 8, 1, 0),
           (16, 1, 24, 1, 4), (64, 4, 16, 1, 4), (256, 16, 16, 1, 4), (32, 1, 8, 3, 0),
           (32, 1, 256, 32, 4), (64, 2, 128, 32, 4), (64, 2, 256, 32, 4), (128, 4, 64, 32, 4), (128, 4, 128, 32, 4), (256, 8, 32, 32, 4), (256, 8, 64, 32, 4)]
@@ -27,11 +28,11 @@ def child(C, heads, H, B, shift):
     from paramgen import randomize_state
     torch.manual_seed(C + H + shift)
     dev = "cuda:0"
-    blk = U.LeWinTransformerBlock(C, (max(H, 16),) * 2, heads, win_size=8, shift_size=shift).eval()
+    blk = U.LeWinTransformerBlock(C, (max(H, 16),) * 2, heads, win_size=8, shift_size=shift, modulator=MODULATOR).eval()
     st = randomize_state(blk.state_dict(), 9)
     blk.load_state_dict(st)
     x = torch.randn(B, H * H, C).to(torch.bfloat16)
-    res = dict(C=C, heads=heads, H=H, B=B, shift=shift)
+    res = dict(C=C, heads=heads, H=H, B=B, shift=shift, modulator=MODULATOR)
     small = B * H * H <= 20000
     if small:
         os.environ["UFORMER_B200_WMSA"] = "tma"

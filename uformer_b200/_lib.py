@@ -25,7 +25,8 @@ class WmsaArgs(C.Structure):
                 ("n_windows", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32), ("head_dim", C.c_int32),
                 ("shift", C.c_int32), ("windowed", C.c_int32), ("ln_eps", C.c_float), ("dbg", C.c_int32), ("trace", C.c_void_p),
                 ("x_fp32", C.c_int32), ("out_fp32", C.c_int32), ("out_b", C.c_void_p),
-                ("wqkv_fold_img", C.c_void_p), ("bqkv_fold", C.c_void_p), ("cs_qkv", C.c_void_p), ("x_b", C.c_void_p)]
+                ("wqkv_fold_img", C.c_void_p), ("bqkv_fold", C.c_void_p), ("cs_qkv", C.c_void_p), ("x_b", C.c_void_p),
+                ("wmod_fold_img", C.c_void_p)]
 
 
 class Leff1Args(C.Structure):

@@ -283,9 +283,9 @@ extern "C" int lw_wmsa_tma_supported(int C, int head_dim) {
 }
 static bool wmsa_tma_eligible(const lw_wmsa_args* a) {
   if (!a->wqkv_fold_img || !a->bqkv_fold || !a->cs_qkv) return false;
-  if (a->windowed || a->modulator || !a->ln_w || (a->shift % 4) != 0) return false;
+  if (a->windowed || (a->modulator && !a->wmod_fold_img) || !a->ln_w || (a->shift % 4) != 0) return false;
   if (a->x_fp32 && !a->x_b) return false;
-  if (!all_aligned16(a->wqkv_fold_img, a->x_b)) return false;
+  if (!all_aligned16(a->wqkv_fold_img, a->x_b, a->wmod_fold_img)) return false;
   return lw_wmsa_tma_supported(a->C, a->head_dim) != 0;
 }
 template <int C, int HD>
@@ -308,6 +308,7 @@ static int launch_wmsa_tma_any(const lw_wmsa_args* p, cudaStream_t st) {
   WmsaTArgs a{};
   a.out = p->out; a.resid = p->resid; a.out_b = reinterpret_cast<bf16*>(p->out_b);
   a.wqkv_img = reinterpret_cast<const uint8_t*>(p->wqkv_fold_img); a.bqkv = p->bqkv_fold; a.cs = p->cs_qkv;
+  a.wmod_img = p->modulator ? reinterpret_cast<const uint8_t*>(p->wmod_fold_img) : nullptr;
   a.wproj_img = reinterpret_cast<const uint8_t*>(p->wproj_img); a.bproj = p->bproj; a.relpos = p->relpos;
   a.mask = p->mask; a.n_mask_windows = p->n_mask_windows; a.n_windows = p->n_windows; a.H = p->H; a.W = p->W; a.shift = p->shift;
   a.ln_eps = p->ln_eps; a.resid_fp32 = p->x_fp32; a.out_fp32 = p->out_fp32;

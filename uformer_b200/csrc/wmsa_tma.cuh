@@ -16,7 +16,12 @@
 //     gather of tile i+1 (two buffers; C = 128 keeps one so that two CTAs fit per SM) and — for C = 256 — the QKV GEMM of
 //     its first head run underneath tile i.
 // The scatter (window_reverse + roll back, model.py:975-983) is the staged copy-out of wmsa.cuh with the quarter-major row
-// table.  Modulator, window-major inputs, C = 512 and head_dim 64 stay on wmsa_kernel.
+// table.
+//   * the window modulator (model.py:966-969: LN(x) + m[pos] before the projection) rides on the tensor core as well: its
+//     contribution m[pos] W^T is a per-position constant, so the A operand gets one more 64-wide k-block that is a one-hot of
+//     the row's position scaled by sigma = 1/rstd (128 two-byte stores per tile), multiplied with the per-head image of
+//     (m W^T)^T; the epilogue's rstd * acc then yields rstd*(x Wg^T) + m W^T.  No SIMT work per head.
+// Window-major inputs, C = 512 and head_dim 64 stay on wmsa_kernel.
 #pragma once
 #include <cuda.h>
 #include "lewin_common.cuh"
@@ -31,6 +36,7 @@ struct WmsaTArgs {
   const uint8_t* wqkv_img; // LN-folded, packed as for wmsa_kernel
   const float* bqkv;       // folded bias (heads*3*hd)
   const float* cs;         // row sums of the bf16 folded weight (heads*3*hd)
+  const uint8_t* wmod_img; // per head [3hd rows x 64 positions (quarter-major)] bf16 image of (modulator W^T)^T, or null
   const uint8_t* wproj_img;
   const float* bproj;
   const float* relpos;
@@ -90,7 +96,11 @@ struct WmsaTCfg {
   static constexpr int S_K = S_Q + TILE_B;
   static constexpr int S_V = S_K + TILE_B;
   static constexpr int S_RING = S_V + TILE_B;
-  static constexpr int S_MISC = S_RING + STAGES * STAGE_BYTES;
+  // modulator blocks: a 128 x 64 one-hot A-operand tile (16 KB).  C = 64 has no room beside three ring stages and two CTAs per
+  // SM: there the tile takes the place of the third stage (the ring then runs two deep).
+  static constexpr int STAGES_MOD = (C == 64) ? 2 : STAGES;
+  static constexpr int S_OH = S_RING + STAGES_MOD * STAGE_BYTES;
+  static constexpr int S_MISC = (S_RING + STAGES * STAGE_BYTES > S_OH + 16384) ? S_RING + STAGES * STAGE_BYTES : S_OH + 16384;
   static constexpr int SMEM_BYTES = S_MISC + 6144 + 1024;
   static_assert(S_Q % 1024 == 0 && S_RING % 1024 == 0, "operand alignment");
   static_assert(128 * PITCH <= 3 * TILE_B, "staging tile must fit in the Q/K/V tiles");
@@ -109,6 +119,7 @@ struct WmsaTMisc {
   uint64_t bar_x_full[2], bar_x_empty[2];
   uint64_t bar_qkv_full, bar_qkv_staged, bar_s_full, bar_p_ready, bar_o_full, bar_oall;
   uint64_t bar_d_full, bar_d_empty;
+  uint64_t bar_oh_ready;
   uint32_t tmem_base;
 };
 static_assert(sizeof(WmsaTMisc) <= 6144, "misc too large");
@@ -133,6 +144,7 @@ __global__ void __launch_bounds__(kThreads8, C <= 128 ? 2 : 1) wmsa_tma_kernel(c
     mbar_init(smem_u32(&ms.bar_oall), kWorkers8);
     mbar_init(smem_u32(&ms.bar_d_full), 1);
     mbar_init(smem_u32(&ms.bar_d_empty), kWorkers8);
+    mbar_init(smem_u32(&ms.bar_oh_ready), kWorkers8);
     fence_mbar_init();
   }
   if (warp == 8) tmem_alloc(smem_u32(&ms.tmem_base), Cfg::T_ALLOC);
@@ -142,6 +154,9 @@ __global__ void __launch_bounds__(kThreads8, C <= 128 ? 2 : 1) wmsa_tma_kernel(c
   const uint32_t tb = ms.tmem_base;
   const uint32_t sX = smem_u32(smem + Cfg::S_X), sQ = smem_u32(smem + Cfg::S_Q), sK = smem_u32(smem + Cfg::S_K), sV = smem_u32(smem + Cfg::S_V);
   const int nwx = a.W >> 3, nwin_img = nwx * (a.H >> 3);
+  const bool has_mod = a.wmod_img != nullptr;
+  const int ring_stages = has_mod ? Cfg::STAGES_MOD : Cfg::STAGES;
+  const uint32_t sOH = smem_u32(smem + Cfg::S_OH);
 
   if (warp == 8) {
     // ======================= producer: window gather (TMA boxes) + weight chunk images =======================
@@ -172,28 +187,31 @@ __global__ void __launch_bounds__(kThreads8, C <= 128 ? 2 : 1) wmsa_tma_kernel(c
         }
       };
       for (int it = 0; it < Cfg::NXB && it < n_my; ++it) load_x(it);
-      Ring ring{smem_u32(smem + Cfg::S_RING), smem_u32(&ms.bar_full[0]), smem_u32(&ms.bar_empty[0]), Cfg::STAGES, 0, Cfg::STAGE_BYTES};
+      Ring ring{smem_u32(smem + Cfg::S_RING), smem_u32(&ms.bar_full[0]), smem_u32(&ms.bar_empty[0]), ring_stages, 0, Cfg::STAGE_BYTES};
       // chunk order = the issuer's consumption order.  PIPE: the QKV GEMM stream runs one head ahead, across tiles: head 0 of
       // tile it+1 is consumed before the projection of tile it.
       auto load_qkv = [&](int h0, int h1) {
-        for (int h = h0; h < h1; ++h)
+        for (int h = h0; h < h1; ++h) {
           for (int kb = 0; kb < Cfg::KB; ++kb)
             ring.load(a.wqkv_img + (size_t)(h * Cfg::KB + kb) * Cfg::QKV_CHUNK_BYTES, Cfg::QKV_CHUNK_BYTES);
+          if (has_mod) ring.load(a.wmod_img + (size_t)h * Cfg::QKV_CHUNK_BYTES, Cfg::QKV_CHUNK_BYTES);
+        }
       };
-      if (Cfg::PIPE) load_qkv(0, Cfg::NH);
+      const bool ahead = Cfg::PIPE && !has_mod;          // (a modulated head 0 needs its tile's statistics: no cross-tile issue)
+      if (ahead) load_qkv(0, Cfg::NH);
       for (int it = 0; it < n_my; ++it) {
-        if (!Cfg::PIPE) load_qkv(0, Cfg::NH);
+        if (!ahead) load_qkv(0, Cfg::NH);
         else if (it + 1 < n_my) load_qkv(0, 1);
         if (it + Cfg::NXB < n_my) load_x(it + Cfg::NXB);      // its buffer is released by the last QKV GEMM of tile `it`
         for (int nc = 0; nc < Cfg::NC; ++nc)
           for (int kb = 0; kb < Cfg::KB; ++kb)
             ring.load(a.wproj_img + (size_t)(nc * Cfg::KB + kb) * Cfg::PROJ_CHUNK_BYTES, Cfg::PROJ_CHUNK_BYTES);
-        if (Cfg::PIPE && it + 1 < n_my) load_qkv(1, Cfg::NH);
+        if (ahead && it + 1 < n_my) load_qkv(1, Cfg::NH);
       }
     }
   } else if (warp == 9) {
     // ======================= issuer =======================
-    Ring ring{smem_u32(smem + Cfg::S_RING), smem_u32(&ms.bar_full[0]), smem_u32(&ms.bar_empty[0]), Cfg::STAGES, 0, Cfg::STAGE_BYTES};
+    Ring ring{smem_u32(smem + Cfg::S_RING), smem_u32(&ms.bar_full[0]), smem_u32(&ms.bar_empty[0]), ring_stages, 0, Cfg::STAGE_BYTES};
     constexpr uint32_t idesc_qkv = make_idesc_bf16(128, Cfg::QKV_N);
     constexpr uint32_t idesc_s = make_idesc_bf16(128, 128);
     constexpr uint32_t idesc_pv = make_idesc_bf16(128, HD, false, true);
@@ -215,6 +233,17 @@ __global__ void __launch_bounds__(kThreads8, C <= 128 ? 2 : 1) wmsa_tma_kernel(c
         __syncwarp();
         ring.release();
       }
+      if (has_mod) {                                  // + sigma * onehot(pos) x (m W_h^T)^T: the modulator term, un-scaled by rstd
+        if (hq == 0) { wt_wait(smem_u32(&ms.bar_oh_ready), itq & 1); tc_fence_after(); }
+        const uint32_t wst = ring.acquire();
+        const uint64_t ad = kmajor_desc<128>(sOH), bd = b_desc0 + (uint64_t)((wst - ring_base) >> 4);
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) umma_ss(tb + Cfg::T_QKV, ad + 2 * ks, bd + 2 * ks, idesc_qkv, 1u);
+        }
+        __syncwarp();
+        ring.release();
+      }
       if (elect_one()) {
         umma_commit(smem_u32(&ms.bar_qkv_full));
         if (hq == Cfg::NH - 1) umma_commit(smem_u32(&ms.bar_x_empty[buf]));     // the gathered tile is dead: refill
@@ -222,8 +251,10 @@ __global__ void __launch_bounds__(kThreads8, C <= 128 ? 2 : 1) wmsa_tma_kernel(c
       __syncwarp();
     };
     int g = 0;                                        // heads processed so far (barrier phases)
-    if (Cfg::PIPE) issue_qkv(0, 0);
+    const bool ahead = Cfg::PIPE && !has_mod;
+    if (ahead) issue_qkv(0, 0);
     for (int it = 0; it < n_my; ++it) {
+      if (Cfg::PIPE && !ahead) issue_qkv(it, 0);
       for (int h = 0; h < Cfg::NH; ++h, ++g) {
         const uint32_t ph = g & 1;
         if (!Cfg::PIPE) {
@@ -243,7 +274,7 @@ __global__ void __launch_bounds__(kThreads8, C <= 128 ? 2 : 1) wmsa_tma_kernel(c
         __syncwarp();
         if (Cfg::PIPE) {                              // next QKV GEMM of the stream (next head, or head 0 of the next tile)
           if (h + 1 < Cfg::NH) issue_qkv(it, h + 1);
-          else if (it + 1 < n_my) issue_qkv(it + 1, 0);
+          else if (ahead && it + 1 < n_my) issue_qkv(it + 1, 0);
         }
         wt_wait(smem_u32(&ms.bar_p_ready), ph);
         tc_fence_after();
@@ -323,6 +354,10 @@ __global__ void __launch_bounds__(kThreads8, C <= 128 ? 2 : 1) wmsa_tma_kernel(c
       const int nb = itn & 1;
       if (a.shift > 0 && ms.region[nb][tid] != ms.region[nb][(tid >> 6) * 64]) ms.win_mixed[nb][tid >> 6] = 1;
     };
+    if (has_mod) {                                       // one-hot tile: zero once, the diagonal is rewritten per tile
+#pragma unroll
+      for (int k = 0; k < 4; ++k) sts128(sOH + (tid * 4 + k) * 16, make_uint4(0, 0, 0, 0));
+    }
     if (tid < 128) build_rows(0);
     worker_bar8();
     if (tid < 128) mark_mixed(0);
@@ -375,11 +410,17 @@ __global__ void __launch_bounds__(kThreads8, C <= 128 ? 2 : 1) wmsa_tma_kernel(c
             const float md = s1[u] * (1.0f / C);                             // mean - x0
             const float var = fmaxf(s2[u] * (1.0f / C) - md * md, 0.f);
             const float rstd = rsqrtf(var + a.ln_eps);
-            ms.stats[warp * 16 + u * RPP + rin] = make_float2(rstd, -(x0[u] + md) * rstd);
+            const int row = warp * 16 + u * RPP + rin;
+            ms.stats[row] = make_float2(rstd, -(x0[u] + md) * rstd);
+            if (has_mod) {                               // sigma on the diagonal of the one-hot k-block (column = position in the window)
+              const __nv_bfloat16 sg = __float2bfloat16_rn((var + a.ln_eps) * rstd);
+              asm volatile("st.shared.b16 [%0], %1;" ::"r"(sOH + swz<128>(row, (row & 63) * 2)), "h"(*reinterpret_cast<const unsigned short*>(&sg)) : "memory");
+            }
           }
         }
       }
       mbar_arrive(smem_u32(&ms.bar_x_empty[buf]));       // this thread is done reading the raw tile
+      if (has_mod) { fence_async_smem(); mbar_arrive(smem_u32(&ms.bar_oh_ready)); }
       worker_bar8();
       LW_TRACE_STMT(if (trw && it < 3) a.trace[tw++] = clock64();)
 

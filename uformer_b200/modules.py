@@ -185,17 +185,22 @@ class WindowAttention(nn.Module):
             return False
         return bool(_lib.load().lw_wmsa_tma_supported(self.dim, self.dim // self.num_heads))
 
-    def packed_fold(self, norm: nn.LayerNorm):
-        """The projection with `norm` (the block's norm1, model.py:953) folded in: packing.pack_qkv_fold."""
+    def packed_fold(self, norm: nn.LayerNorm, modulator: nn.Embedding | None = None):
+        """The projection with `norm` (the block's norm1, model.py:953) folded in, plus the image of the block's window
+        modulator pushed through the projection: packing.pack_qkv_fold."""
         q, kv = self.qkv.to_q, self.qkv.to_kv
-        srcs = [q.weight, q.bias, kv.weight, kv.bias, norm.weight, norm.bias]
+        srcs = [q.weight, q.bias, kv.weight, kv.bias, norm.weight, norm.bias] + ([modulator.weight] if modulator is not None else [])
 
         def build():
             C = self.dim
             bq_ = q.bias if q.bias is not None else torch.zeros(C, device=q.weight.device)
             bkv_ = kv.bias if kv.bias is not None else torch.zeros(2 * C, device=q.weight.device)
-            img, bf, cs = packing.pack_qkv_fold(q.weight, bq_, kv.weight, bkv_, self.num_heads, float(self.scale), norm.weight, norm.bias)
-            return dict(wqkv_fold_img=img, bqkv_fold=bf, cs_qkv=cs)
+            r = packing.pack_qkv_fold(q.weight, bq_, kv.weight, bkv_, self.num_heads, float(self.scale), norm.weight, norm.bias,
+                                      None if modulator is None else modulator.weight)
+            d = dict(wqkv_fold_img=r[0], bqkv_fold=r[1], cs_qkv=r[2])
+            if modulator is not None:
+                d["wmod_fold_img"] = r[3]
+            return d
         return self._cache_ln.get(srcs, build)
 
     def _check_supported(self):
@@ -406,11 +411,11 @@ class LeWinTransformerBlock(nn.Module):
 
     def _attn_operands(self):
         """Operand dict of ops.wmsa for this block: attention images + norm1 affine + modulator, plus the LayerNorm-folded
-        projection when the TMA-gather kernel can take the block (no modulator: its per-position term is not folded)."""
+        projection (and modulator image) when the TMA-gather kernel is built for the block's shape."""
         pk = self.packed()
         pa = dict(self.attn.packed(), ln_w=pk["ln1_w"], ln_b=pk["ln1_b"], modulator=pk["modulator"], ln_eps=self.norm1.eps)
-        if pk["modulator"] is None and self.attn.tma_gather():
-            pa.update(self.attn.packed_fold(self.norm1))
+        if self.attn.tma_gather():
+            pa.update(self.attn.packed_fold(self.norm1, self.modulator))
         return pa
 
     @staticmethod
@@ -505,7 +510,7 @@ class LeWinTransformerBlock(nn.Module):
 
     def wants_bf16_copy(self) -> bool:
         """Whether this block's W-MSA would gather an fp32 input through its bf16 copy (TMA path; see forward's x_b)."""
-        return self.modulator is None and self.attn.tma_gather() and self.mlp.fused()
+        return self.attn.tma_gather() and self.mlp.fused()
 
     def flops(self):
         H, W = self.input_resolution

@@ -91,6 +91,7 @@ def wmsa(x: Tensor, p: dict, *, H: int, W: int, shift: int, windowed: bool, resi
         if x_b is not None and (x_b.dtype != torch.bfloat16 or x_b.shape != x.shape or not x_b.is_contiguous()):
             raise ValueError("x_b must be a contiguous bfloat16 tensor of x's shape")
         a.wqkv_fold_img, a.bqkv_fold, a.cs_qkv, a.x_b = _ptr(p["wqkv_fold_img"]), _ptr(p["bqkv_fold"]), _ptr(p["cs_qkv"]), _ptr(x_b)
+        a.wmod_fold_img = _ptr(p.get("wmod_fold_img"))
     ntok = n_windows * 64
     _launch(f"wmsa_C{Cc}_T{ntok}", 2.0 * ntok * (4 * Cc * Cc + 128 * Cc), lambda st: _lib.load().lw_wmsa_fwd(C.byref(a), st), "lw_wmsa_fwd", x.device)
     return (out, out_b) if bf16_copy else out

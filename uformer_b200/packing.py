@@ -139,12 +139,25 @@ def pack_qkv(wq: Tensor, bq: Tensor, wkv: Tensor, bkv: Tensor, heads: int, scale
     return img, bias.contiguous()                               # bias (heads*3*hd,)
 
 
-def pack_qkv_fold(wq: Tensor, bq: Tensor, wkv: Tensor, bkv: Tensor, heads: int, scale: float, ln_w: Tensor, ln_b: Tensor):
+def quarter_major_positions() -> Tensor:
+    """Row order of a window inside the TMA-gather W-MSA kernel (csrc/wmsa_tma.cuh): row k of a window holds the natural
+    (row-major 8x8) position nat[k]; the four 4x4 quarters follow each other, each row-major."""
+    k = torch.arange(64)
+    y = ((k >> 5) & 1) * 4 + ((k >> 2) & 3)
+    x = ((k >> 4) & 1) * 4 + (k & 3)
+    return y * 8 + x
+
+
+def pack_qkv_fold(wq: Tensor, bq: Tensor, wkv: Tensor, bkv: Tensor, heads: int, scale: float, ln_w: Tensor, ln_b: Tensor,
+                  modulator: Tensor | None = None):
     """pack_qkv with the LayerNorm in front (norm1, model.py:953) folded into the projection, for the TMA-gather W-MSA kernel
     (csrc/wmsa_tma.cuh), whose A operand is the raw token tile:
       LN(x) W^T + b = rstd*(x Wg^T) - rstd*mean*cs + bf,  Wg = W diag(gamma) rounded to bf16, cs = row sums of that bf16
     matrix (the mean term then cancels exactly against what the tensor core accumulates), bf = b + W beta.
-    Returns (image, bf, cs), rows in pack_qkv's per-head [q_h; k_h; v_h] order, q rows pre-scaled."""
+    Returns (image, bf, cs), rows in pack_qkv's per-head [q_h; k_h; v_h] order, q rows pre-scaled.
+    With a window modulator (model.py:966-969, `LN(x) + m[pos]` before the projection) a fourth value: the image of
+    (m W^T)^T per head, [heads][3hd rows][64 positions in the kernel's quarter-major order] — the B operand of the one-hot
+    k-block that adds the per-position term on the tensor core."""
     C = wq.shape[0]
     hd = C // heads
     w3 = torch.cat([wq.float() * scale, wkv.float()], 0)                          # (3C, C)
@@ -155,7 +168,12 @@ def pack_qkv_fold(wq: Tensor, bq: Tensor, wkv: Tensor, bkv: Tensor, heads: int, 
 
     def per_head(t):
         return t.view(3, heads, hd, *t.shape[1:]).transpose(0, 1).reshape(heads * 3 * hd, *t.shape[1:])
-    return pack_kmajor(per_head(wg), 3 * hd, "nk"), per_head(bf).contiguous(), per_head(cs).contiguous()
+    out = (pack_kmajor(per_head(wg), 3 * hd, "nk"), per_head(bf).contiguous(), per_head(cs).contiguous())
+    if modulator is None:
+        return out
+    mw = w3 @ modulator.float().t()                                               # (3C, 64): row n, natural position
+    mw = per_head(mw)[:, quarter_major_positions().to(mw.device)]                 # columns in the kernel's window order
+    return out + (pack_kmajor(mw, 3 * hd, "nk"),)
 
 
 def pack_relpos(table: Tensor) -> Tensor:

@@ -57,7 +57,8 @@ def _pack_blocks(blks):
     wqkv_img = packing.pack_kmajor(wcat, 3 * hd, "nk").view(nb, heads, -1, 3 * hd * 64)
     bqkv = torch.cat([bq * scale, bkv], 1).view(nb, 3, heads, hd).permute(0, 2, 1, 3).reshape(nb, -1).contiguous()
     # LayerNorm-folded projection for the TMA-gather W-MSA kernel (packing.pack_qkv_fold), blocks without a modulator
-    fold = b0.attn.tma_gather() and b0.modulator is None          # (groups are uniform in modulator presence)
+    fold = b0.attn.tma_gather()
+    has_mod = b0.modulator is not None                             # (groups are uniform in modulator presence)
     if fold:
         gamma1, beta1 = stack(lambda b: b.norm1.weight), stack(lambda b: b.norm1.bias)
         b3 = torch.cat([bq * scale, bkv], 1)                                            # (nb, 3C)
@@ -69,6 +70,10 @@ def _pack_blocks(blks):
             return t.view(nb, 3, heads, hd, *t.shape[2:]).transpose(1, 2).reshape(nb, heads * 3 * hd, *t.shape[2:])
         wfold_img = packing.pack_kmajor(per_head(wg).reshape(nb * heads * 3 * hd, C), 3 * hd, "nk").view(nb, heads, -1, 3 * hd * 64)
         bfold, csq = per_head(bf).contiguous(), per_head(cs).contiguous()
+        if has_mod:                                 # (m W^T)^T per head, positions in the kernel's window order
+            mod = stack(lambda b: b.modulator.weight)                                   # (nb, 64, C)
+            mw = per_head(torch.matmul(w3, mod.transpose(1, 2)))[:, :, packing.quarter_major_positions().to(dev)]
+            wmod_img = packing.pack_kmajor(mw.reshape(nb * heads * 3 * hd, 64), 3 * hd, "nk").view(nb, heads, -1, 3 * hd * 64)
     nchp = min(C, 128)
     wproj_img = packing.pack_kmajor(stack(lambda b: b.attn.proj.weight).view(nb * C, C), nchp, "nk").view(nb, C // nchp, -1, nchp * 64)
     relpos = stack(lambda b: b.attn.relative_position_bias_table).transpose(1, 2).contiguous()          # (nb, heads, 225)
@@ -103,8 +108,10 @@ def _pack_blocks(blks):
                                             bproj=a.proj.bias.detach().float().contiguous(), relpos=relpos[i], head_dim=hd))
         if fold:
             q, kv = a.qkv.to_q, a.qkv.to_kv
-            a._cache_ln.put([q.weight, q.bias, kv.weight, kv.bias, b.norm1.weight, b.norm1.bias],
-                            dict(wqkv_fold_img=wfold_img[i], bqkv_fold=bfold[i], cs_qkv=csq[i]))
+            d = dict(wqkv_fold_img=wfold_img[i], bqkv_fold=bfold[i], cs_qkv=csq[i])
+            if has_mod:
+                d["wmod_fold_img"] = wmod_img[i]
+            a._cache_ln.put([q.weight, q.bias, kv.weight, kv.bias, b.norm1.weight, b.norm1.bias] + ([b.modulator.weight] if has_mod else []), d)
         bd = m.dwconv[0].bias.detach().float().contiguous()
         b2 = m.linear2[0].bias.detach().float().contiguous()
         if fused:
