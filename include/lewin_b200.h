@@ -94,10 +94,17 @@ typedef struct lw_wmsa_args {
   const void* x_b;           /* bf16 copy of an fp32 x (what the previous kernel wrote as its out_b), or NULL */
   const void* wmod_fold_img; /* with a modulator: packed bf16 [heads][3*hd rows x 64 positions]: (modulator Wqkv^T)^T per head,
                                 positions in the kernel's quarter-major window order (packing.pack_qkv_fold); else NULL */
+  /* Window size: 0 or 8 = 8x8 windows (everything above); 16 = 16x16 windows (csrc/wmsa16.cuh: one CTA per 256-token window).
+   * With 16: x is (n_windows, 256, C) if windowed; n_windows = B*(H/16)*(W/16); relpos is (heads, 961); modulator (256, C);
+   * mask (n_mask_windows, 256, 256); shift in [0, 16); H, W multiples of 16; C <= 256 and not (C = 256, head_dim = 64)
+   * (lw_wmsa16_supported).  The TMA-gather fields are ignored. */
+  int32_t win_size;
 } lw_wmsa_args;
 int lw_wmsa_fwd(const lw_wmsa_args* a, lw_stream_t stream);
 /* 1 if the TMA-gather W-MSA kernel is built for (C, head_dim): C in {16,32,64,128,256}, head_dim in {16,32}. */
 int lw_wmsa_tma_supported(int C, int head_dim);
+/* 1 if the 16x16-window kernel is built for (C, head_dim): head_dim in {16,32,64}, C = head_dim * 2^k <= 256, not (256, 64). */
+int lw_wmsa16_supported(int C, int head_dim);
 
 /* ---- LeFF part 1 (two-kernel path, C = 512): h1 = GELU( LN(x) W1^T + b1 )  (model.py:671 with norm2 of :987 folded in).
  * h1 is written in HALF precision (fp16): it is an internal buffer between the two kernels. */

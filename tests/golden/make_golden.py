@@ -34,10 +34,43 @@ def load_random(mod, seed):
     return st
 
 
+def ws16_fixtures(m):
+    """BASELINE configs[4], win_size 16: WindowAttention on 256-token windows (head_dim 16 / 32 / 64) and two LeWin blocks with
+    16x16 windows (shift 8 + modulator; shift 0 at C = 256).  Own RNG, so the older fixtures stay reproducible."""
+    out = {}
+    gen = torch.Generator().manual_seed(1616)
+    for name, dim, heads, nwin in [("wattn_ws16_c32_h1", 32, 1, 4), ("wattn_ws16_c64_h4_hd16", 64, 4, 3), ("wattn_ws16_c128_h2_hd64", 128, 2, 2)]:
+        mod = m.WindowAttention(dim, win_size=(16, 16), num_heads=heads)
+        st = load_random(mod, 21)
+        x = torch.randn(nwin, 256, dim, generator=gen)
+        mask = torch.where(torch.rand(nwin if nwin < 3 else 1, 256, 256, generator=gen) > 0.7, torch.tensor(-100.0), torch.tensor(0.0))
+        out[name] = dict(kind="wattn", ws=16, dim=dim, heads=heads, seed=21, x=x, y=mod(x), mask=mask, y_mask=mod(x, mask=mask),
+                         checksum=state_checksum(st))
+    for name, dim, heads, H, shift, modu, B in [("block_ws16_c64_s8_mod", 64, 2, 32, 8, True, 2), ("block_ws16_c256_s0", 256, 8, 16, 0, False, 1)]:
+        mod = m.LeWinTransformerBlock(dim, (32, 32), heads, win_size=16, shift_size=shift, modulator=modu)
+        st = load_random(mod, 22)
+        x = torch.randn(B, H * H, dim, generator=gen)
+        out[name] = dict(kind="block", ws=16, dim=dim, heads=heads, H=H, shift=shift, modulator=modu, seed=22, x=x, y=mod(x),
+                         checksum=state_checksum(st))
+    return out
+
+
+def save_all(out, only=None):
+    for k, v in out.items():
+        if only and not k.startswith(only):
+            continue
+        path = os.path.join(HERE, k + ".pt")
+        torch.save(v, path)
+        print("%-28s %8.1f KB" % (k, os.path.getsize(path) / 1024))
+
+
 def main():
     torch.manual_seed(1234)
     torch.set_grad_enabled(False)
     m = import_reference_model()
+    if os.environ.get("GOLDEN_ONLY") == "ws16":          # only the 16x16-window fixtures (skips the slow whole-model forwards)
+        save_all(ws16_fixtures(m))
+        return
     out = {}
 
     # ---- module level: WindowAttention (model.py:452-546), with and without mask ----
@@ -141,13 +174,8 @@ def main():
     out["wattn_c128_h2_hd64"] = dict(kind="wattn", dim=128, heads=2, seed=16, x=xw, y=mod(xw), mask=maskw, y_mask=mod(xw, mask=maskw),
                                      checksum=state_checksum(st))
 
-    only = os.environ.get("GOLDEN_ONLY")
-    for k, v in out.items():
-        if only and not k.startswith(only):
-            continue
-        path = os.path.join(HERE, k + ".pt")
-        torch.save(v, path)
-        print("%-28s %8.1f KB" % (k, os.path.getsize(path) / 1024))
+    out.update(ws16_fixtures(m))
+    save_all(out, os.environ.get("GOLDEN_ONLY"))
 
 
 if __name__ == "__main__":

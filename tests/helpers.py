@@ -50,7 +50,7 @@ def build_module(g):
     import uformer_b200 as U
     kind = g["kind"]
     if kind == "wattn":
-        mod = U.WindowAttention(g["dim"], win_size=(8, 8), num_heads=g["heads"])
+        mod = U.WindowAttention(g["dim"], win_size=(g.get("ws", 8),) * 2, num_heads=g["heads"])
     elif kind == "leff":
         mod = U.LeFF(g["dim"], 4 * g["dim"])
     elif kind == "down":
@@ -58,7 +58,8 @@ def build_module(g):
     elif kind == "up":
         mod = U.Upsample(g["cin"], g["cout"])
     elif kind == "block":
-        mod = U.LeWinTransformerBlock(g["dim"], (g["H"], g["H"]), g["heads"], win_size=8, shift_size=g["shift"], modulator=g["modulator"])
+        mod = U.LeWinTransformerBlock(g["dim"], (max(g["H"], 32),) * 2 if g.get("ws", 8) == 16 else (g["H"], g["H"]), g["heads"], win_size=g.get("ws", 8),
+                                      shift_size=g["shift"], modulator=g["modulator"])
     elif kind == "model":
         mod = U.Uformer(**g["cfg"])
     else:
@@ -84,7 +85,7 @@ def oracle_run(g, st, x, dtype=torch.float32, mask=None):
     x = x.to(dtype)
     kind = g["kind"]
     if kind == "wattn":
-        return O.window_attention(x, st, "", g["heads"], 8, None if mask is None else mask.to(dtype))
+        return O.window_attention(x, st, "", g["heads"], g.get("ws", 8), None if mask is None else mask.to(dtype))
     if kind == "leff":
         return O.leff(x, st, "")
     if kind == "down":
@@ -92,7 +93,7 @@ def oracle_run(g, st, x, dtype=torch.float32, mask=None):
     if kind == "up":
         return O.upsample(x, st["deconv.0.weight"], st["deconv.0.bias"])
     if kind == "block":
-        return O.lewin_block(x, st, "", g["heads"], 8, g["shift"])
+        return O.lewin_block(x, st, "", g["heads"], g.get("ws", 8), g["shift"])
     if kind == "model":
         c = g["cfg"]
         return O.uformer_forward(x, st, c["img_size"], c["embed_dim"], c["depths"], win_size=c["win_size"])

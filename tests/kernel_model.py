@@ -23,10 +23,10 @@ def _q(t):
     return t.to(BF).float()
 
 
-def _relidx():
-    t = torch.arange(64)
-    y, x = t // 8, t % 8
-    return (y[:, None] - y[None, :] + 7) * 15 + (x[:, None] - x[None, :] + 7)
+def _relidx(ws=8):
+    t = torch.arange(ws * ws)
+    y, x = t // ws, t % ws
+    return (y[:, None] - y[None, :] + ws - 1) * (2 * ws - 1) + (x[:, None] - x[None, :] + ws - 1)
 
 
 def _partition(x, ws=8):
@@ -40,10 +40,10 @@ def _reverse(w, H, W, ws=8):
     return w.view(B, H // ws, W // ws, ws, ws, C).permute(0, 1, 3, 2, 4, 5).reshape(B, H, W, C)
 
 
-def _shift_mask(H, W, shift):
+def _shift_mask(H, W, shift, ws=8):
     r, c = torch.arange(H), torch.arange(W)
-    reg = 3 * ((r >= H - 8).long() + (r >= H - shift).long())[:, None] + ((c >= W - 8).long() + (c >= W - shift).long())[None, :]
-    rw = _partition(reg[None, :, :, None].float()).squeeze(-1)
+    reg = 3 * ((r >= H - ws).long() + (r >= H - shift).long())[:, None] + ((c >= W - ws).long() + (c >= W - shift).long())[None, :]
+    rw = _partition(reg[None, :, :, None].float(), ws).squeeze(-1)
     return torch.where(rw[:, None, :] != rw[:, :, None], -100.0, 0.0)
 
 
@@ -54,13 +54,15 @@ def _wmsa_tma_eligible(x, p, shift, windowed, x_b):
             and (x.dtype == BF or x_b is not None) and bool(_lib.load().lw_wmsa_tma_supported(C, p["head_dim"])))
 
 
-def wmsa(x, p, *, H, W, shift, windowed, resid, mask=None, out=None, out_dtype=None, bf16_copy=False, x_b=None):
+def wmsa(x, p, *, H, W, shift, windowed, resid, mask=None, out=None, out_dtype=None, bf16_copy=False, x_b=None, win=8):
     assert x.dtype in (BF, torch.float32) and x.is_contiguous()
     assert resid is None or resid.dtype == x.dtype
     C = x.shape[-1]
     hd = p["head_dim"]
     heads = C // hd
-    fold = _wmsa_tma_eligible(x, p, shift, windowed, x_b)
+    assert win in (8, 16) and (win == 8 or _lib.load().lw_wmsa16_supported(C, hd))      # lw_wmsa_args.win_size
+    N = win * win
+    fold = win == 8 and _wmsa_tma_eligible(x, p, shift, windowed, x_b)
     if fold:
         # TMA-gather kernel: the raw bf16 tokens are the GEMM operand; LayerNorm statistics come from that same bf16 tile
         # and are applied to the accumulator (rstd*acc - rstd*mean*cs + bf)
@@ -77,7 +79,7 @@ def wmsa(x, p, *, H, W, shift, windowed, resid, mask=None, out=None, out_dtype=N
         m = xf.view(B, H, W, C)
         if shift:
             m = torch.roll(m, (-shift, -shift), (1, 2))
-        xw = _partition(m)
+        xw = _partition(m, win)
     if p.get("modulator") is not None and not fold:
         xw = xw + p["modulator"]
     xw = _q(xw)                                                   # A operand is bf16
@@ -96,20 +98,20 @@ def wmsa(x, p, *, H, W, shift, windowed, resid, mask=None, out=None, out_dtype=N
         qkv = (rstd * acc - (rstd * mean) * p["cs_qkv"] + p["bqkv_fold"]).view(nW, 64, heads, 3, hd)
     else:
         wcat = packing.unpack_kmajor(p["wqkv_img"], heads * 3 * hd, C, 3 * hd, "nk")        # [head][q|k|v][hd] rows, q pre-scaled
-        qkv = (xw @ wcat.t() + p["bqkv"]).view(nW, 64, heads, 3, hd)
+        qkv = (xw @ wcat.t() + p["bqkv"]).view(nW, N, heads, 3, hd)
     q, k, v = (_q(qkv[:, :, :, i].permute(0, 2, 1, 3)) for i in range(3))
-    s = q @ k.transpose(-2, -1) + p["relpos"][:, _relidx().reshape(-1)].view(heads, 64, 64)[None]
+    s = q @ k.transpose(-2, -1) + p["relpos"][:, _relidx(win).reshape(-1)].view(heads, N, N)[None]
     if not windowed and shift:
-        sm = _shift_mask(H, W, shift)
-        s = (s.view(-1, sm.shape[0], heads, 64, 64) + sm[None, :, None]).view(nW, heads, 64, 64)
+        sm = _shift_mask(H, W, shift, win)
+        s = (s.view(-1, sm.shape[0], heads, N, N) + sm[None, :, None]).view(nW, heads, N, N)
     if mask is not None:
         mk = mask.float()
         s = s + mk[torch.arange(nW) % mk.shape[0]][:, None]
-    o = _q(torch.softmax(s, -1) @ v).permute(0, 2, 1, 3).reshape(nW, 64, C)
+    o = _q(torch.softmax(s, -1) @ v).permute(0, 2, 1, 3).reshape(nW, N, C)
     wp = packing.unpack_kmajor(p["wproj_img"], C, C, min(C, 128), "nk")
     y = o @ wp.t() + p["bproj"]
     if not windowed:
-        y = _reverse(y, H, W)
+        y = _reverse(y, H, W, win)
         if shift:
             y = torch.roll(y, (shift, shift), (1, 2))
         y = y.reshape(x.shape)

@@ -405,3 +405,64 @@ def test_wmsa_tma_gather_kernel(dim, heads, H, B, shift, max_ctas, modu):
         if shift:
             mask = mask.view(1, -1, 64, 64).reshape(-1, 64, 64)
         _check(ym.float().cpu() - x.float(), attn_half(x.float(), mask), f"wmsa-tma explicit mask C={dim} (branch)")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cin,cout,H,W,B,max_ctas,resid", [(64, 3, 40, 24, 2, 0, True), (64, 3, 64, 64, 3, 2, True), (32, 3, 16, 48, 1, 1, True),
+                                                         (32, 1, 24, 24, 2, 0, False), (128, 3, 16, 16, 1, 0, True)])
+def test_output_proj_vs_fp32_conv(cin, cout, H, W, B, max_ctas, resid):
+    """OutputProj + global residual (model.py:834-842, :1305).  Cin in {32, 64} takes the tensor-core kernel (GEMM over the
+    halo'd token tile, then the 9 taps; the fp32 weight is split into two bf16 halves, so the only rounding is the fp32
+    accumulation order); other widths the SIMT kernel.  Checked against torch's fp32 conv2d of the SAME bf16 tokens — sizes that
+    are not multiples of the 8 x 16 tile, several tiles per CTA (lw_set_max_ctas), no residual."""
+    import torch.nn.functional as F
+    from uformer_b200 import _lib, ops
+    torch.manual_seed(cin + H + W)
+    tok = torch.randn(B, H * W, cin).to(torch.bfloat16)
+    w = torch.randn(cout, cin, 3, 3) * 0.05
+    b = torch.randn(cout)
+    img = torch.rand(B, cout, H, W) if resid else None
+    ref = F.conv2d(tok.float().transpose(1, 2).reshape(B, cin, H, W), w, b, padding=1)
+    if resid:
+        ref = ref + img
+    lib = _lib.load()
+    lib.lw_set_max_ctas(max_ctas)
+    try:
+        y = ops.output_proj(tok.to(DEV), w.to(DEV), b.to(DEV), None if img is None else img.to(DEV), H, W)
+        torch.cuda.synchronize()
+    finally:
+        lib.lw_set_max_ctas(0)
+    err = (y.cpu() - ref).abs().max().item() / ref.abs().max().item()
+    print(f"output_proj Cin={cin} Cout={cout} {H}x{W} B={B}: max-abs / max-abs = {err:.2e}")
+    assert err < 2e-5, err
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dim,heads,H,shift,modu,B", [
+    (16, 1, 32, 8, True, 1), (32, 2, 16, 0, False, 3), (64, 4, 32, 8, False, 1), (128, 8, 32, 8, True, 1), (256, 16, 16, 0, True, 2),   # head_dim 16
+    (32, 1, 32, 8, True, 2), (64, 2, 32, 4, True, 1), (128, 4, 16, 0, False, 2), (256, 8, 32, 8, True, 1),                                # head_dim 32
+    (64, 1, 32, 8, False, 1), (128, 2, 32, 8, True, 2),                                                                                     # head_dim 64
+])
+def test_block_ws16_vs_oracle(dim, heads, H, shift, modu, B):
+    """LeWin blocks with 16x16 windows (BASELINE configs[4]; csrc/wmsa16.cuh: one CTA per 256-token window, two M tiles,
+    N = 256 score GEMM, two-pass softmax over TMEM chunks) against the oracle: every (C, head_dim) the kernel is built for,
+    shift 0 / 8 / 4, modulator (256 x C) on / off, the fp32 residual stream, and an input mask on an un-shifted block."""
+    import uformer_b200 as U
+    from oracle import lewin_oracle as O
+    from paramgen import randomize_state
+    torch.manual_seed(dim + H + shift)
+    blk = U.LeWinTransformerBlock(dim, (32, 32), heads, win_size=16, shift_size=shift, modulator=modu).eval()
+    assert blk.win_size == 16 and not blk.attn.tma_gather()
+    st = randomize_state(blk.state_dict(), 200 + dim)
+    blk.load_state_dict(st)
+    x = torch.randn(B, H * H, dim).to(torch.bfloat16).float()
+    ref = O.lewin_block(x, st, "", heads, 16, shift)
+    blk.residual_fp32 = False
+    _check(_run(blk, x), ref, f"block ws16 C={dim} h={heads} H={H} s={shift}")
+    blk.residual_fp32 = True
+    y32 = _run(blk, x, out_dtype=torch.float32)
+    _check(y32, ref, f"block ws16 C={dim} fp32 stream")
+    if shift == 0:
+        mask = (torch.rand(B, 1, H, H) > 0.8).float()
+        blk.residual_fp32 = False
+        _check(_run(blk, x, mask=mask), O.lewin_block(x, st, "", heads, 16, 0, input_mask=mask), f"block ws16 C={dim} input mask")

@@ -63,7 +63,7 @@ def test_c_abi_exports_every_declared_symbol():
     lib = _lib.load()
     for s in declared:
         assert hasattr(lib, s), s
-    assert lib.lw_abi_version() == 5
+    assert lib.lw_abi_version() == 6
     # the ctypes mirrors have the compiled structs' sizes (also enforced at load time)
     for i, st in enumerate([_lib.WmsaArgs, _lib.Leff1Args, _lib.Leff2Args, _lib.LeffArgs, _lib.DownArgs, _lib.UpArgs, _lib.AdamWArgs]):
         assert lib.lw_struct_size(i) == ctypes.sizeof(st), st.__name__

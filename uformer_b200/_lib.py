@@ -26,7 +26,7 @@ class WmsaArgs(C.Structure):
                 ("shift", C.c_int32), ("windowed", C.c_int32), ("ln_eps", C.c_float), ("dbg", C.c_int32), ("trace", C.c_void_p),
                 ("x_fp32", C.c_int32), ("out_fp32", C.c_int32), ("out_b", C.c_void_p),
                 ("wqkv_fold_img", C.c_void_p), ("bqkv_fold", C.c_void_p), ("cs_qkv", C.c_void_p), ("x_b", C.c_void_p),
-                ("wmod_fold_img", C.c_void_p)]
+                ("wmod_fold_img", C.c_void_p), ("win_size", C.c_int32)]
 
 
 class Leff1Args(C.Structure):
@@ -67,7 +67,7 @@ class AdamWArgs(C.Structure):
 CHARBONNIER_PARTIALS = 1024      # LW_CHARBONNIER_PARTIALS
 
 # every symbol include/lewin_b200.h declares
-EXPORTS = ["lw_abi_version", "lw_struct_size", "lw_last_cuda_error", "lw_check_device", "lw_nch_ares", "lw_set_max_ctas", "lw_wmsa_fwd", "lw_wmsa_tma_supported", "lw_leff1_fwd", "lw_leff2_fwd", "lw_leff_fwd", "lw_leff_fused_supported", "lw_leff_slice",
+EXPORTS = ["lw_abi_version", "lw_struct_size", "lw_last_cuda_error", "lw_check_device", "lw_nch_ares", "lw_set_max_ctas", "lw_wmsa_fwd", "lw_wmsa_tma_supported", "lw_wmsa16_supported", "lw_leff1_fwd", "lw_leff2_fwd", "lw_leff_fwd", "lw_leff_fused_supported", "lw_leff_slice",
            "lw_downsample_fwd", "lw_upsample_fwd", "lw_input_proj_fwd", "lw_output_proj_fwd", "lw_charbonnier_fwd_bwd", "lw_adamw_step"]
 
 _lib = None
@@ -98,6 +98,8 @@ def load():
     lib.lw_set_max_ctas.argtypes = [C.c_int]
     lib.lw_wmsa_tma_supported.restype = C.c_int
     lib.lw_wmsa_tma_supported.argtypes = [C.c_int, C.c_int]
+    lib.lw_wmsa16_supported.restype = C.c_int
+    lib.lw_wmsa16_supported.argtypes = [C.c_int, C.c_int]
     lib.lw_leff_slice.restype = C.c_int
     lib.lw_leff_slice.argtypes = [C.c_int]
     for name, argt in [("lw_wmsa_fwd", WmsaArgs), ("lw_leff1_fwd", Leff1Args), ("lw_leff2_fwd", Leff2Args), ("lw_leff_fwd", LeffArgs),

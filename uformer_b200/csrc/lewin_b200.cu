@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include "wmsa.cuh"
 #include "wmsa_tma.cuh"
+#include "wmsa16.cuh"
 #include "leff.cuh"
 #include "leff2.cuh"
 #include "leff_fused.cuh"
@@ -38,7 +39,7 @@ static bool all_aligned16(P... ps) {
   return ok;
 }
 
-extern "C" int lw_abi_version(void) { return 5; }
+extern "C" int lw_abi_version(void) { return 6; }
 extern "C" const char* lw_last_cuda_error(void) { return g_err; }
 extern "C" int lw_check_device(void) {
   int dev = 0, major = 0;
@@ -131,14 +132,41 @@ static int launch_wmsa(const lw_wmsa_args* a, cudaStream_t st) {
 static bool wmsa_tma_eligible(const lw_wmsa_args* a);
 static int launch_wmsa_tma_any(const lw_wmsa_args* a, cudaStream_t st);
 
+// ---- 16 x 16 windows (wmsa16.cuh): one CTA per window ----
+extern "C" int lw_wmsa16_supported(int C, int head_dim) {
+  if (!(head_dim == 16 || head_dim == 32 || head_dim == 64) || C < head_dim || C > 256 || C % head_dim) return 0;
+  if (!(C == 16 || C == 32 || C == 64 || C == 128 || C == 256)) return 0;
+  return !(C == 256 && head_dim == 64);
+}
+template <int C, int HD>
+static int launch_wmsa16(const lw_wmsa_args* a, cudaStream_t st) {
+  using Cfg = Wmsa16Cfg<C, HD>;
+  LW_ENSURE_SMEM((wmsa16_kernel<C, HD>), Cfg::SMEM_BYTES);
+  wmsa16_kernel<C, HD><<<a->n_windows, kThreads8, Cfg::SMEM_BYTES, st>>>(*a);
+  LW_TRY(cudaGetLastError());
+  return LW_OK;
+}
+static int launch_wmsa16_any(const lw_wmsa_args* a, cudaStream_t st) {
+  if (!lw_wmsa16_supported(a->C, a->head_dim)) return LW_ERR_BAD_SHAPE;
+#define WMSA16_CASE(c, hd) \
+  if (a->C == c && a->head_dim == hd) return launch_wmsa16<c, hd>(a, st);
+  WMSA16_CASE(16, 16) WMSA16_CASE(32, 16) WMSA16_CASE(64, 16) WMSA16_CASE(128, 16) WMSA16_CASE(256, 16)
+  WMSA16_CASE(32, 32) WMSA16_CASE(64, 32) WMSA16_CASE(128, 32) WMSA16_CASE(256, 32)
+  WMSA16_CASE(64, 64) WMSA16_CASE(128, 64)
+#undef WMSA16_CASE
+  return LW_ERR_BAD_SHAPE;
+}
+
 extern "C" int lw_wmsa_fwd(const lw_wmsa_args* a, lw_stream_t stream) {
   if (!a || !a->x || !a->out || !a->wqkv_img || !a->bqkv || !a->wproj_img || !a->bproj || !a->relpos) return LW_ERR_NULL;
   if ((a->ln_w == nullptr) != (a->ln_b == nullptr)) return LW_ERR_NULL;
   if (a->n_windows <= 0) return LW_ERR_BAD_SHAPE;
+  if (a->win_size != 0 && a->win_size != 8 && a->win_size != 16) return LW_ERR_BAD_SHAPE;
+  const int ws = a->win_size == 16 ? 16 : 8;
   if (!a->windowed) {
-    if (a->H <= 0 || a->W <= 0 || (a->H % 8) || (a->W % 8)) return LW_ERR_BAD_SHAPE;
-    if (a->n_windows % ((a->H / 8) * (a->W / 8))) return LW_ERR_BAD_SHAPE;
-    if (a->shift < 0 || a->shift >= 8) return LW_ERR_BAD_SHAPE;
+    if (a->H <= 0 || a->W <= 0 || (a->H % ws) || (a->W % ws)) return LW_ERR_BAD_SHAPE;
+    if (a->n_windows % ((a->H / ws) * (a->W / ws))) return LW_ERR_BAD_SHAPE;
+    if (a->shift < 0 || a->shift >= ws) return LW_ERR_BAD_SHAPE;
   } else if (a->shift != 0) {
     return LW_ERR_BAD_SHAPE;
   }
@@ -153,6 +181,7 @@ extern "C" int lw_wmsa_fwd(const lw_wmsa_args* a, lw_stream_t stream) {
     aa.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr;
   }
   a = &aa;
+  if (ws == 16) return launch_wmsa16_any(a, st);
   if (wmsa_tma_eligible(a)) return launch_wmsa_tma_any(a, st);
 #define WMSA_CASE(c, hd) \
   if (a->C == c && a->head_dim == hd) return launch_wmsa<c, hd>(a, st);
@@ -411,6 +440,26 @@ extern "C" int lw_output_proj_fwd(const void* tokens, const float* w, const floa
                                   int32_t Cin, int32_t H, int32_t W, int32_t Cout, lw_stream_t stream) {
   if (!tokens || !w || !b || !out) return LW_ERR_NULL;
   if (B <= 0 || H <= 0 || W <= 0 || (W & 1) || Cin % 8 || Cin > 128 || Cout < 1 || Cout > 4) return LW_ERR_BAD_SHAPE;
+  if ((Cin == 32 || Cin == 64) && Cout <= 3 && aligned16(tokens)) {      // tensor-core path (GEMM first, taps after): proj.cuh
+    CUtensorMap map;
+    const int rc = make_token_map(&map, tokens, B, H, W, Cin, Cin, Cin, 18, 10);
+    if (rc != LW_OK) return rc;
+    const int tiles_x = (W + 15) / 16, tiles_y = (H + 7) / 8;
+    const long long n_tiles = (long long)tiles_x * tiles_y * B;
+    if (n_tiles >= (1ll << 31)) return LW_ERR_BAD_SHAPE;
+    const int cap = 4 * sm_count();
+    const int grid = cap_grid(n_tiles < cap ? (int)n_tiles : cap);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (Cin == 64) {
+      LW_ENSURE_SMEM(output_proj_tc_kernel<64>, OutProjCfg<64>::SMEM_BYTES);
+      output_proj_tc_kernel<64><<<grid, 128, OutProjCfg<64>::SMEM_BYTES, st>>>(map, w, b, img, out, B, H, W, Cout, tiles_x, tiles_y, (int)n_tiles);
+    } else {
+      LW_ENSURE_SMEM(output_proj_tc_kernel<32>, OutProjCfg<32>::SMEM_BYTES);
+      output_proj_tc_kernel<32><<<grid, 128, OutProjCfg<32>::SMEM_BYTES, st>>>(map, w, b, img, out, B, H, W, Cout, tiles_x, tiles_y, (int)n_tiles);
+    }
+    LW_TRY(cudaGetLastError());
+    return LW_OK;
+  }
   const long long npix = (long long)B * H * (W / 2);     // one thread per horizontal pixel pair
   const int blocks = (int)((npix + 127) / 128);
   const size_t smem = (size_t)9 * Cin * 4 * sizeof(float);

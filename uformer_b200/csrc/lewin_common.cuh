@@ -439,7 +439,7 @@ __device__ __forceinline__ void store_staged_rows(uint32_t stage_s, int pitch, i
 // tile row r (-1: row is padding -> zeros).  Executed by the 4 worker warps; warp w stages rows
 // [32w, 32w+32).  Lanes run along channels, so global reads are coalesced 16 B vectors.
 // ----------------------------------------------------------------------------------------------
-template <int C, int NW = 4, bool X32 = false>
+template <int C, int NW = 4, bool X32 = false, int TABMASK = 63>   // TABMASK: rows of the per-row table minus one (window positions)
 __device__ __forceinline__ void stage_rows_ln(uint8_t* sX, const void* __restrict__ xv,
                                               const int* row_tok, const float* __restrict__ ln_w,
                                               const float* __restrict__ ln_b, float eps,
@@ -527,7 +527,7 @@ __device__ __forceinline__ void stage_rows_ln(uint8_t* sX, const void* __restric
 #pragma unroll
         for (int j = 0; j < VPL; ++j) {
           const int c0 = j * 256 + sub * 8;
-          const float* t = addtab + (size_t)(r & 63) * C + c0;
+          const float* t = addtab + (size_t)(r & TABMASK) * C + c0;
           float4 a0 = __ldg(reinterpret_cast<const float4*>(t));
           float4 a1 = __ldg(reinterpret_cast<const float4*>(t + 4));
           v[j][0] += a0.x; v[j][1] += a0.y; v[j][2] += a0.z; v[j][3] += a0.w;

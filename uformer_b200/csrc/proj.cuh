@@ -8,7 +8,9 @@
 // Each thread owns TWO horizontally adjacent pixels so every broadcast weight read from shared memory
 // feeds two pixels; arithmetic is packed FFMA2 where the data comes in pairs.
 #pragma once
+#include <cuda.h>
 #include "lewin_common.cuh"
+#include "leff_fused.cuh"   // tma_load_4d / tma_prefetch_desc
 
 namespace lw {
 
@@ -127,6 +129,163 @@ __global__ void __launch_bounds__(128) output_proj_kernel(const bf16* __restrict
     }
     *reinterpret_cast<float2*>(out + o) = r;
   }
+}
+
+// ----------------------------------------------------------------------------------------------
+// output_proj on the tensor core (Cin in {32, 64}, Cout <= 3): the 3x3 convolution is re-associated as "GEMM first, taps
+// after".  Z[q, tap*Cout+co] = sum_ci tok[q, ci] w[co, ci, tap] is ONE small GEMM per halo'd token tile (K = Cin, N = 64), and
+//   out[p, co] = img[p, co] + b[co] + sum_tap Z[p + tap, tap*Cout + co]
+// is 9*Cout shared-memory reads per pixel.  PERSISTENT CTAs (4 per SM, 53 KB each) walk 8 x 16 pixel tiles:
+//   TMA    the 10 x 18 halo'd block of tokens lands with one cp.async.bulk.tensor box (4-D map (C, W, H, B); out-of-image
+//          coordinates are zero-filled = the conv's zero padding) in the K-major swizzled layout of the A operand; the box of
+//          tile i+1 is requested as soon as the GEMM of tile i has read the buffer and lands under the tap phase.
+//   GEMM   one M=128 + one M=64 tcgen05.mma chain over the 192 (>= 180) halo rows.  The weights keep fp32 accuracy with bf16
+//          operands: B rows [0, 32) carry bf16(w), rows [32, 64) carry bf16(w - bf16(w)); the epilogue adds the two halves.
+//   taps   Z -> shared memory ([192][29] fp32, odd pitch: conflict-free), one thread per output pixel sums its 9 taps and
+//          writes NCHW fp32 with the global residual.
+// One HBM read of the token map (neighbouring halos hit L2) instead of 9 x 4 register-blocked re-reads + 1728 FMAs per pixel.
+// ----------------------------------------------------------------------------------------------
+template <int CIN>
+struct OutProjCfg {
+  static constexpr int SW = CIN * 2;                        // row bytes = swizzle span (64 / 128)
+  static constexpr int KS = CIN / 16;
+  static constexpr int A_BYTES = 192 * SW;
+  static constexpr int W_BYTES = 64 * SW;
+  static constexpr int ZP = 29;                             // Z pitch (floats)
+  static constexpr int S_A = 0;                             // ONE input buffer: four CTAs share an SM and overlap each other's phases
+  static constexpr int S_W = A_BYTES;
+  static constexpr int S_Z = S_W + W_BYTES;
+  static constexpr int S_BAR = S_Z + 192 * ZP * 4;
+  static constexpr int SMEM_BYTES = S_BAR + 64 + 1024;
+  static_assert(A_BYTES % 1024 == 0 && S_W % 1024 == 0, "operand alignment");
+};
+
+template <int CIN>
+__global__ void __launch_bounds__(128, 4) output_proj_tc_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ w,
+                                                             const float* __restrict__ bias, const float* __restrict__ img,
+                                                             float* __restrict__ out, int B, int H, int W, int Cout, int tiles_x,
+                                                             int tiles_y, int n_tiles) {
+  using Cfg = OutProjCfg<CIN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::S_BAR);       // [0] x_full, [1] mma done
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Cfg::S_BAR + 32);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_my = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const uint32_t sA = smem_u32(smem + Cfg::S_A), sW = smem_u32(smem + Cfg::S_W), sZ = smem_u32(smem + Cfg::S_Z);
+  const int ntap = 9 * Cout;                                 // <= 27 columns of Z
+
+  if (tid == 0) {
+    mbar_init(smem_u32(&bars[0]), 1); mbar_init(smem_u32(&bars[1]), 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&xmap);
+  }
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 128);
+  // B operand image, built once per CTA from the fp32 conv weight: row n < 32: bf16(w) of (tap, co) = (n / Cout, n % Cout);
+  // row 32 + n: the bf16 remainder; unused rows zero.
+  for (int i = tid; i < 64 * CIN; i += 128) {
+    const int n = i / CIN, k = i % CIN, nn = n & 31;
+    float v = 0.f;
+    if (nn < ntap) {
+      const float wf = __ldg(w + ((size_t)(nn % Cout) * CIN + k) * 9 + nn / Cout);
+      const float hi = __bfloat162float(__float2bfloat16_rn(wf));
+      v = (n < 32) ? hi : wf - hi;
+    }
+    const __nv_bfloat16 hv = __float2bfloat16_rn(v);
+    asm volatile("st.shared.b16 [%0], %1;" ::"r"(sW + swz<Cfg::SW>(n, 2 * k)), "h"(*reinterpret_cast<const unsigned short*>(&hv)) : "memory");
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = *tmem_slot;
+
+  auto load_tile = [&](int it) {                             // thread 0
+    const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+    const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
+    const uint32_t bar = smem_u32(&bars[0]);
+    mbar_expect_tx(bar, 180 * Cfg::SW);
+    tma_load_4d(sA, &xmap, 0, tx * 16 - 1, ty * 8 - 1, b, bar);
+  };
+  if (tid == 0 && n_my > 0) load_tile(0);
+  constexpr uint32_t idesc_a = make_idesc_bf16(128, 64), idesc_b = make_idesc_bf16(64, 64);
+  const int py = tid >> 4, px = tid & 15;
+  float bco[3];
+#pragma unroll
+  for (int co = 0; co < 3; ++co) bco[co] = (co < Cout) ? __ldg(bias + co) : 0.f;
+
+  for (int it = 0; it < n_my; ++it) {
+    const uint32_t ph = it & 1;
+    const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+    const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
+    const int Y = ty * 8 + py, X = tx * 16 + px;
+    const bool inside = Y < H && X < W;
+    // this pixel's residual + bias: requested now, consumed after the taps (its latency hides under the GEMM and the Z pass)
+    float acc[3];
+#pragma unroll
+    for (int co = 0; co < 3; ++co) {
+      acc[co] = bco[co];
+      if (co < Cout && inside && img != nullptr) acc[co] += __ldg(img + (((size_t)b * Cout + co) * H + Y) * W + X);
+    }
+    if (warp == 0) {
+      mbar_wait(smem_u32(&bars[0]), ph);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < Cfg::KS; ++ks) {
+          const uint64_t bd = kmajor_desc<Cfg::SW>(sW + ks * 32);
+          umma_ss(tb, kmajor_desc<Cfg::SW>(sA + ks * 32), bd, idesc_a, ks != 0);
+          umma_ss(tb + 64, kmajor_desc<Cfg::SW>(sA + 128 * Cfg::SW + ks * 32), bd, idesc_b, ks != 0);
+        }
+        umma_commit(smem_u32(&bars[1]));
+      }
+      __syncwarp();
+    }
+    mbar_wait(smem_u32(&bars[1]), ph);
+    tc_fence_after();
+    if (tid == 0 && it + 1 < n_my) load_tile(it + 1);       // the GEMM has read the buffer: refill it under the rest of this tile
+    // ---- Z = hi + lo halves of the accumulators -> shared memory (thread = TMEM lane = halo row) ----
+    {
+      uint32_t hi[32], lo[32];
+      const uint32_t tl = (uint32_t)(32 * warp) << 16;
+      tmem_ld32(tb + tl, hi);
+      tmem_ld32(tb + tl + 32, lo);
+      tmem_wait_ld();
+      const uint32_t zr = sZ + (32 * warp + lane) * (Cfg::ZP * 4);
+#pragma unroll
+      for (int n = 0; n < 27; ++n) sts32f(zr + n * 4, __uint_as_float(hi[n]) + __uint_as_float(lo[n]));
+      // M = 64 part: its rows 16q .. 16q+15 sit in lanes 32q .. 32q+15 (halo rows 128 + 16q + lane)
+      tmem_ld32(tb + tl + 64, hi);
+      tmem_ld32(tb + tl + 96, lo);
+      tmem_wait_ld();
+      if (lane < 16) {
+        const uint32_t zr2 = sZ + (128 + 16 * warp + lane) * (Cfg::ZP * 4);
+#pragma unroll
+        for (int n = 0; n < 27; ++n) sts32f(zr2 + n * 4, __uint_as_float(hi[n]) + __uint_as_float(lo[n]));
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+    // ---- 9 taps per pixel (+ bias + global residual, already in acc), NCHW fp32 ----
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const uint32_t zr = sZ + ((py + ky) * 18 + px + kx) * (Cfg::ZP * 4) + (ky * 3 + kx) * Cout * 4;
+#pragma unroll
+        for (int co = 0; co < 3; ++co)
+          if (co < Cout) acc[co] += lds32f(zr + co * 4);
+      }
+    if (inside) {
+#pragma unroll
+      for (int co = 0; co < 3; ++co)
+        if (co < Cout) out[(((size_t)b * Cout + co) * H + Y) * W + X] = acc[co];
+    }
+    __syncthreads();                                        // Z is free again
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, 128);
 }
 
 }  // namespace lw

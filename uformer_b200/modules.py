@@ -181,7 +181,7 @@ class WindowAttention(nn.Module):
     def tma_gather(self) -> bool:
         """True when the persistent TMA-gather W-MSA kernel (csrc/wmsa_tma.cuh) is built for this shape; the block then also
         packs the LayerNorm-folded projection.  UFORMER_B200_WMSA=classic keeps every launch on wmsa_kernel (A/B switch)."""
-        if os.environ.get("UFORMER_B200_WMSA", "tma") == "classic":
+        if os.environ.get("UFORMER_B200_WMSA", "tma") == "classic" or tuple(self.win_size) != (8, 8):
             return False
         return bool(_lib.load().lw_wmsa_tma_supported(self.dim, self.dim // self.num_heads))
 
@@ -204,10 +204,13 @@ class WindowAttention(nn.Module):
         return self._cache_ln.get(srcs, build)
 
     def _check_supported(self):
-        if tuple(self.win_size) != (8, 8):
-            raise NotImplementedError(f"uformer_b200 kernels are specialised for 8x8 windows (got {self.win_size})")
+        if tuple(self.win_size) not in ((8, 8), (16, 16)):
+            raise NotImplementedError(f"uformer_b200 kernels are built for 8x8 and 16x16 windows (got {self.win_size})")
         hd = self.dim // self.num_heads
-        if hd not in (16, 32, 64) or self.dim % hd or self.dim > 512 or (hd in (16, 64) and self.dim > 256):
+        if tuple(self.win_size) == (16, 16):
+            if not _lib.load().lw_wmsa16_supported(self.dim, hd):
+                raise NotImplementedError(f"unsupported with 16x16 windows (dim={self.dim}, heads={self.num_heads})")
+        elif hd not in (16, 32, 64) or self.dim % hd or self.dim > 512 or (hd in (16, 64) and self.dim > 256):
             raise NotImplementedError(f"unsupported (dim={self.dim}, heads={self.num_heads})")
         if self.attn_drop.p > 0 and self.training or self.proj_drop.p > 0 and self.training:
             raise NotImplementedError("attention/projection dropout is not implemented (p=0 in every Uformer config)")
@@ -219,7 +222,7 @@ class WindowAttention(nn.Module):
         _lib.require_device(x.device)
         xb, back = _as_bf16(x)
         acts = [xb] if mask is None else [xb, mask.to(device=x.device, dtype=torch.float32)]
-        out = _run(self, lambda t, m=None: ops.wmsa(t, self.packed(), H=0, W=0, shift=0, windowed=True, resid=None, mask=m),
+        out = _run(self, lambda t, m=None: ops.wmsa(t, self.packed(), H=0, W=0, shift=0, windowed=True, resid=None, mask=m, win=self.win_size[0]),
                    lambda t, m=None: restated.window_attention(self, t, m), acts)
         return out if back is None else out.to(back)
 
@@ -434,9 +437,10 @@ class LeWinTransformerBlock(nn.Module):
         source of the W-MSA kernel — and whether to return one of the output as well: the result is then (out, out_bf16)."""
         B, L, C = x.shape
         H = W = int(math.sqrt(L))
-        if H * W != L or H % 8 or self.win_size != 8:
-            raise NotImplementedError(f"uformer_b200 block needs a square token map with side % 8 == 0 and 8x8 windows "
-                                      f"(L={L}, win_size={self.win_size})")
+        ws = self.win_size
+        if H * W != L or ws not in (8, 16) or H % ws:
+            raise NotImplementedError(f"uformer_b200 block needs a square token map with side % win_size == 0 and 8x8 or 16x16 "
+                                      f"windows (L={L}, win_size={self.win_size})")
         self.attn._check_supported()
         self.mlp._check_supported()
         if mask is not None and self.shift_size > 0 and B > 1:
@@ -469,11 +473,11 @@ class LeWinTransformerBlock(nn.Module):
             a1, a2, m = split(rest)
             pa = self._attn_operands()
             pm = self.mlp.packed(self.norm2)
-            amask = None if m is None else self.input_mask_to_attn_mask(m, H, W, 8)
+            amask = None if m is None else self.input_mask_to_attn_mask(m, H, W, ws)
             if a1 is None:
-                x1 = ops.wmsa(t, pa, H=H, W=W, shift=self.shift_size, windowed=False, resid=t, mask=amask)
+                x1 = ops.wmsa(t, pa, H=H, W=W, shift=self.shift_size, windowed=False, resid=t, mask=amask, win=ws)
                 return ops.leff(x1, pm, B=B, H=H, W=W, resid=x1, out=dst)
-            br = ops.wmsa(t, pa, H=H, W=W, shift=self.shift_size, windowed=False, resid=None, mask=amask)
+            br = ops.wmsa(t, pa, H=H, W=W, shift=self.shift_size, windowed=False, resid=None, mask=amask, win=ws)
             x1 = torch.addcmul(t.float(), br.float(), a1).to(torch.bfloat16)
             br = ops.leff(x1, pm, B=B, H=H, W=W, resid=None)
             y = torch.addcmul(x1.float(), br.float(), a2).to(torch.bfloat16)
@@ -498,9 +502,9 @@ class LeWinTransformerBlock(nn.Module):
         if x.dtype not in (torch.bfloat16, torch.float32):
             x = x.float()
         x = x.contiguous()
-        amask = None if mask is None else self.input_mask_to_attn_mask(mask, H, W, 8)
+        amask = None if mask is None else self.input_mask_to_attn_mask(mask, H, W, self.win_size)
         x1, x1b = ops.wmsa(x, pa, H=H, W=W, shift=self.shift_size, windowed=False, resid=x, mask=amask, out_dtype=torch.float32, bf16_copy=True,
-                           x_b=x_b if x.dtype == torch.float32 else None)
+                           x_b=x_b if x.dtype == torch.float32 else None, win=self.win_size)
         odt = out.dtype if out is not None else (out_dtype or torch.float32)
         if want_b and not (self.mlp.fused() and odt == torch.float32):
             raise ValueError("want_b needs the fused LeFF kernel and an fp32 output")

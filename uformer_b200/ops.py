@@ -52,7 +52,8 @@ def _check_act(x: Tensor, name: str):
 
 
 def wmsa(x: Tensor, p: dict, *, H: int, W: int, shift: int, windowed: bool, resid: Tensor | None,
-         mask: Tensor | None = None, out: Tensor | None = None, out_dtype=None, bf16_copy: bool = False, x_b: Tensor | None = None):
+         mask: Tensor | None = None, out: Tensor | None = None, out_dtype=None, bf16_copy: bool = False, x_b: Tensor | None = None,
+         win: int = 8):
     """Fused (LN) + (roll/partition) + W-MSA + proj + (reverse/unroll) + (residual).
     p: packed parameter dict from modules._pack_attention (+ optional ln_w/ln_b/modulator).
     fp32 residual-stream mode: x (and resid, which must then be x's dtype) may be fp32; out_dtype=torch.float32 writes the
@@ -72,7 +73,7 @@ def wmsa(x: Tensor, p: dict, *, H: int, W: int, shift: int, windowed: bool, resi
     if windowed:
         n_windows = x.shape[0]
     else:
-        n_windows = x.shape[0] * (H // 8) * (W // 8)
+        n_windows = x.shape[0] * (H // win) * (W // win)
     if out is None:
         out = torch.empty(x.shape, dtype=out_dtype or torch.bfloat16, device=x.device)
     out_b = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device) if bf16_copy else None
@@ -87,13 +88,14 @@ def wmsa(x: Tensor, p: dict, *, H: int, W: int, shift: int, windowed: bool, resi
     a.n_windows, a.H, a.W, a.C, a.head_dim = n_windows, H, W, Cc, p["head_dim"]
     a.shift, a.windowed, a.ln_eps = shift, int(windowed), p.get("ln_eps", 1e-5)
     a.x_fp32, a.out_fp32, a.out_b = int(x.dtype == torch.float32), int(out.dtype == torch.float32), _ptr(out_b)
-    if "wqkv_fold_img" in p and not windowed:
+    a.win_size = win
+    if "wqkv_fold_img" in p and not windowed and win == 8:
         if x_b is not None and (x_b.dtype != torch.bfloat16 or x_b.shape != x.shape or not x_b.is_contiguous()):
             raise ValueError("x_b must be a contiguous bfloat16 tensor of x's shape")
         a.wqkv_fold_img, a.bqkv_fold, a.cs_qkv, a.x_b = _ptr(p["wqkv_fold_img"]), _ptr(p["bqkv_fold"]), _ptr(p["cs_qkv"]), _ptr(x_b)
         a.wmod_fold_img = _ptr(p.get("wmod_fold_img"))
-    ntok = n_windows * 64
-    _launch(f"wmsa_C{Cc}_T{ntok}", 2.0 * ntok * (4 * Cc * Cc + 128 * Cc), lambda st: _lib.load().lw_wmsa_fwd(C.byref(a), st), "lw_wmsa_fwd", x.device)
+    ntok = n_windows * win * win
+    _launch(f"wmsa_C{Cc}_T{ntok}" if win == 8 else f"wmsa{win}_C{Cc}_T{ntok}", 2.0 * ntok * (4 * Cc * Cc + 2 * win * win * Cc), lambda st: _lib.load().lw_wmsa_fwd(C.byref(a), st), "lw_wmsa_fwd", x.device)
     return (out, out_b) if bf16_copy else out
 
 
