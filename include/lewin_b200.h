@@ -46,6 +46,10 @@ int lw_struct_size(int id);
 /* Test hook: cap the grid of the persistent kernels (fused LeFF, LeFF part 2, TMA-gather W-MSA) at n CTAs so that small test
  * inputs walk several tiles per CTA; 0 restores the default (one or two CTAs per SM). */
 void lw_set_max_ctas(int n);
+/* Programmatic dependent launch between the library's kernels (default OFF: measured 2 % slower on the Uformer-B forward graph,
+ * DESIGN §8): with 1 every launch carries the programmatic stream serialization attribute, each kernel runs its on-chip set-up
+ * under the tail of its predecessor and executes griddepcontrol.wait before its first global access. */
+void lw_set_pdl(int on);
 
 /* Rows per weight-image chunk the A-resident GEMM kernels (lw_leff1_fwd, lw_upsample_fwd) expect for
  * reduction depth K and output width n_total: the host packer must cut w1_img / w_img with this value. */

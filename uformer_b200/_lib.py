@@ -67,7 +67,7 @@ class AdamWArgs(C.Structure):
 CHARBONNIER_PARTIALS = 1024      # LW_CHARBONNIER_PARTIALS
 
 # every symbol include/lewin_b200.h declares
-EXPORTS = ["lw_abi_version", "lw_struct_size", "lw_last_cuda_error", "lw_check_device", "lw_nch_ares", "lw_set_max_ctas", "lw_wmsa_fwd", "lw_wmsa_tma_supported", "lw_wmsa16_supported", "lw_leff1_fwd", "lw_leff2_fwd", "lw_leff_fwd", "lw_leff_fused_supported", "lw_leff_slice",
+EXPORTS = ["lw_abi_version", "lw_struct_size", "lw_last_cuda_error", "lw_check_device", "lw_nch_ares", "lw_set_max_ctas", "lw_set_pdl", "lw_wmsa_fwd", "lw_wmsa_tma_supported", "lw_wmsa16_supported", "lw_leff1_fwd", "lw_leff2_fwd", "lw_leff_fwd", "lw_leff_fused_supported", "lw_leff_slice",
            "lw_downsample_fwd", "lw_upsample_fwd", "lw_input_proj_fwd", "lw_output_proj_fwd", "lw_charbonnier_fwd_bwd", "lw_adamw_step"]
 
 _lib = None
@@ -96,6 +96,10 @@ def load():
     lib.lw_leff_fused_supported.argtypes = [C.c_int, C.c_int]
     lib.lw_set_max_ctas.restype = None
     lib.lw_set_max_ctas.argtypes = [C.c_int]
+    lib.lw_set_pdl.restype = None
+    lib.lw_set_pdl.argtypes = [C.c_int]
+    if os.environ.get("UFORMER_B200_PDL", "0") == "1":          # A/B switch: programmatic dependent launches (off by default)
+        lib.lw_set_pdl(1)
     lib.lw_wmsa_tma_supported.restype = C.c_int
     lib.lw_wmsa_tma_supported.argtypes = [C.c_int, C.c_int]
     lib.lw_wmsa16_supported.restype = C.c_int

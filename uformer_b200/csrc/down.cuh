@@ -13,7 +13,7 @@
 namespace lw {
 
 struct DownCfg {
-  static constexpr int STAGES = 4;      // weight ring
+  static constexpr int STAGES = 2;      // weight ring (two stages: two CTAs share an SM, one runs its epilogue under the other's main loop)
   static constexpr int ABUF = 4;        // A k-block buffers
   static constexpr int S_A = 0;
   static constexpr int S_RING = ABUF * 16384;
@@ -33,7 +33,7 @@ static_assert(sizeof(DownMisc) <= 1024, "misc too large");
 __device__ __forceinline__ void cp_async_wait_group2() { asm volatile("cp.async.wait_group 2;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_group1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
-__global__ void __launch_bounds__(kThreads8, 1) down_kernel(const AStreamArgs a, const int t_alloc) {
+__global__ void __launch_bounds__(kThreads8, 2) down_kernel(const AStreamArgs a, const int t_alloc) {
   using Cfg = DownCfg;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -53,6 +53,8 @@ __global__ void __launch_bounds__(kThreads8, 1) down_kernel(const AStreamArgs a,
     fence_mbar_init();
   }
   if (warp == 8) tmem_alloc(smem_u32(&ms.tmem_base), t_alloc);
+  pdl_launch_dependents();
+  pdl_wait();                      // nothing above touches global memory
   tc_fence_before();
   __syncthreads();
   tc_fence_after();

@@ -86,6 +86,8 @@ __global__ void __launch_bounds__(kL2Threads, 1) leff2_kernel(const AStreamArgs 
     fence_mbar_init();
   }
   if (warp == 8) tmem_alloc(smem_u32(&ms.tmem_base), t_alloc);
+  pdl_launch_dependents();
+  pdl_wait();                      // nothing above touches global memory
   tc_fence_before();
   __syncthreads();
   tc_fence_after();

@@ -156,6 +156,8 @@ __global__ void __launch_bounds__(kLFThreads, 1) leff_fused_kernel(const __grid_
     tma_prefetch_desc(&xmap);
   }
   if (warp == 12) tmem_alloc(smem_u32(&ms.tmem_base), Cfg::T_ALLOC);
+  pdl_launch_dependents();
+  pdl_wait();                      // nothing above touches global memory
   // resident per-channel tables: b1f, cs, b2; the never-loaded A rows 180..191 are zeroed once
   {
     for (int i = tid; i < a.hidden; i += kLFThreads) {

@@ -111,6 +111,29 @@ static int cap_grid(int grid) {
   return (c > 0 && c < grid) ? c : grid;
 }
 
+// Programmatic dependent launch (PDL, umma.cuh pdl_*), OFF by default: with lw_set_pdl(1) every launch carries the
+// programmatic-stream-serialization attribute, so a kernel may be scheduled while its predecessor drains and runs its on-chip
+// set-up there; griddepcontrol.wait orders its first global access behind the predecessor's completion (captured into a CUDA
+// graph the launches become programmatic dependency edges).  Measured on the Uformer-B forward graph (100 launches, B200):
+// 17.74 ms with PDL against 17.39 ms without — early CTAs of the next persistent grid land unevenly on the SMs that free up
+// first — so the default stays the plain serialised launch; the switch is kept for A/B measurements.
+static std::atomic<int> g_pdl{0};
+extern "C" void lw_set_pdl(int on) { g_pdl.store(on != 0); }
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3((unsigned)block, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl.load(std::memory_order_relaxed) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static int pow2_cols(int n) {
   int c = 32;
   while (c < n) c <<= 1;
@@ -124,8 +147,7 @@ static int launch_wmsa(const lw_wmsa_args* a, cudaStream_t st) {
   static_assert(Cfg::SMEM_BYTES <= 232448, "smem budget");
   LW_ENSURE_SMEM((wmsa_kernel<C, HD>), Cfg::SMEM_BYTES);
   const int tiles = (a->n_windows + 1) / 2;
-  wmsa_kernel<C, HD><<<tiles, kThreads8, Cfg::SMEM_BYTES, st>>>(*a);
-  LW_TRY(cudaGetLastError());
+  LW_TRY(launch_k(wmsa_kernel<C, HD>, tiles, kThreads8, Cfg::SMEM_BYTES, st, *a));
   return LW_OK;
 }
 
@@ -142,8 +164,7 @@ template <int C, int HD>
 static int launch_wmsa16(const lw_wmsa_args* a, cudaStream_t st) {
   using Cfg = Wmsa16Cfg<C, HD>;
   LW_ENSURE_SMEM((wmsa16_kernel<C, HD>), Cfg::SMEM_BYTES);
-  wmsa16_kernel<C, HD><<<a->n_windows, kThreads8, Cfg::SMEM_BYTES, st>>>(*a);
-  LW_TRY(cudaGetLastError());
+  LW_TRY(launch_k(wmsa16_kernel<C, HD>, a->n_windows, kThreads8, Cfg::SMEM_BYTES, st, *a));
   return LW_OK;
 }
 static int launch_wmsa16_any(const lw_wmsa_args* a, cudaStream_t st) {
@@ -199,8 +220,7 @@ static int launch_ares(const AResArgs& a, cudaStream_t st) {
   static_assert(Cfg::SMEM_BYTES <= 232448, "smem budget");
   LW_ENSURE_SMEM((ares_kernel<K, EPI>), Cfg::SMEM_BYTES);
   const int tiles = (a.n_rows + 127) / 128;
-  ares_kernel<K, EPI><<<tiles, kThreads8, Cfg::SMEM_BYTES, st>>>(a);
-  LW_TRY(cudaGetLastError());
+  LW_TRY(launch_k(ares_kernel<K, EPI>, tiles, kThreads8, Cfg::SMEM_BYTES, st, a));
   return LW_OK;
 }
 template <int EPI>
@@ -271,8 +291,7 @@ extern "C" int lw_leff2_fwd(const lw_leff2_args* p, lw_stream_t stream) {
   const int nbuf_d = (2 * a.N <= 512) ? 2 : 1;                 // double-buffer the TMEM accumulator when it fits
   LW_ENSURE_SMEM(leff2_kernel, Leff2Cfg::SMEM_BYTES);
   const int grid = cap_grid(tiles < sm_count() ? tiles : sm_count());    // persistent: one CTA per SM
-  leff2_kernel<<<grid, kL2Threads, Leff2Cfg::SMEM_BYTES, st>>>(a, pow2_cols(nbuf_d * a.N), tiles, nbuf_d);
-  LW_TRY(cudaGetLastError());
+  LW_TRY(launch_k(leff2_kernel, grid, kL2Threads, Leff2Cfg::SMEM_BYTES, st, a, pow2_cols(nbuf_d * a.N), tiles, nbuf_d));
   return LW_OK;
 }
 
@@ -323,8 +342,7 @@ static int launch_wmsa_tma(const CUtensorMap& map, const WmsaTArgs& a, cudaStrea
   LW_ENSURE_SMEM((wmsa_tma_kernel<C, HD>), Cfg::SMEM_BYTES);
   const int cap = sm_count() * (C <= 128 ? 2 : 1);
   const int grid = cap_grid(a.n_tiles < cap ? a.n_tiles : cap);
-  wmsa_tma_kernel<C, HD><<<grid, kThreads8, Cfg::SMEM_BYTES, st>>>(map, a);
-  LW_TRY(cudaGetLastError());
+  LW_TRY(launch_k(wmsa_tma_kernel<C, HD>, grid, kThreads8, Cfg::SMEM_BYTES, st, map, a));
   return LW_OK;
 }
 static int launch_wmsa_tma_any(const lw_wmsa_args* p, cudaStream_t st) {
@@ -362,8 +380,7 @@ static int launch_leff_fused(const CUtensorMap& map, const LeffFArgs& a, cudaStr
   using Cfg = LeffFCfg<C>;
   LW_ENSURE_SMEM(leff_fused_kernel<C>, Cfg::SMEM_BYTES);
   const int grid = cap_grid(a.n_tiles < sm_count() ? a.n_tiles : sm_count());
-  leff_fused_kernel<C><<<grid, kLFThreads, Cfg::SMEM_BYTES, st>>>(map, a);
-  LW_TRY(cudaGetLastError());
+  LW_TRY(launch_k(leff_fused_kernel<C>, grid, kLFThreads, Cfg::SMEM_BYTES, st, map, a));
   return LW_OK;
 }
 
@@ -418,9 +435,14 @@ extern "C" int lw_downsample_fwd(const lw_down_args* p, lw_stream_t stream) {
   a.bias = p->bias; a.out = reinterpret_cast<bf16*>(p->out);
   const int rows = p->B * (p->H / 2) * (p->W / 2);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  LW_ENSURE_SMEM(down_kernel, DownCfg::SMEM_BYTES);
-  down_kernel<<<(rows + 127) / 128, kThreads8, DownCfg::SMEM_BYTES, st>>>(a, pow2_cols(a.N));
-  LW_TRY(cudaGetLastError());
+  // two CTAs share an SM (one drains its accumulator under the other's main loop) unless the accumulator needs more than half
+  // of TMEM: then a second resident CTA would only block in tcgen05.alloc, so the launch asks for more than half of the SM's
+  // shared memory to keep one CTA per SM
+  constexpr int kDownSmemSolo = 120 * 1024;
+  static_assert(DownCfg::SMEM_BYTES <= kDownSmemSolo, "solo smem request");
+  LW_ENSURE_SMEM(down_kernel, kDownSmemSolo);
+  const int t_alloc = pow2_cols(a.N);
+  LW_TRY(launch_k(down_kernel, (rows + 127) / 128, kThreads8, t_alloc > 256 ? kDownSmemSolo : DownCfg::SMEM_BYTES, st, a, t_alloc));
   return LW_OK;
 }
 
@@ -431,8 +453,7 @@ extern "C" int lw_input_proj_fwd(const float* img, const float* w, const float* 
   if (B <= 0 || H <= 0 || W <= 0 || (W & 1) || E % 8 || E > 64 || Cin < 1 || Cin > 4) return LW_ERR_BAD_SHAPE;
   const long long npix = (long long)B * H * (W / 2);     // one thread per horizontal pixel pair
   const int blocks = (int)((npix + 127) / 128);
-  input_proj_kernel<<<blocks, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(img, w, b, reinterpret_cast<bf16*>(tokens), B, Cin, H, W, E);
-  LW_TRY(cudaGetLastError());
+  LW_TRY(launch_k(input_proj_kernel, blocks, 128, 0, reinterpret_cast<cudaStream_t>(stream), img, w, b, reinterpret_cast<bf16*>(tokens), B, Cin, H, W, E));
   return LW_OK;
 }
 
@@ -452,10 +473,10 @@ extern "C" int lw_output_proj_fwd(const void* tokens, const float* w, const floa
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (Cin == 64) {
       LW_ENSURE_SMEM(output_proj_tc_kernel<64>, OutProjCfg<64>::SMEM_BYTES);
-      output_proj_tc_kernel<64><<<grid, 128, OutProjCfg<64>::SMEM_BYTES, st>>>(map, w, b, img, out, B, H, W, Cout, tiles_x, tiles_y, (int)n_tiles);
+      LW_TRY(launch_k(output_proj_tc_kernel<64>, grid, 128, OutProjCfg<64>::SMEM_BYTES, st, map, w, b, img, out, B, H, W, Cout, tiles_x, tiles_y, (int)n_tiles));
     } else {
       LW_ENSURE_SMEM(output_proj_tc_kernel<32>, OutProjCfg<32>::SMEM_BYTES);
-      output_proj_tc_kernel<32><<<grid, 128, OutProjCfg<32>::SMEM_BYTES, st>>>(map, w, b, img, out, B, H, W, Cout, tiles_x, tiles_y, (int)n_tiles);
+      LW_TRY(launch_k(output_proj_tc_kernel<32>, grid, 128, OutProjCfg<32>::SMEM_BYTES, st, map, w, b, img, out, B, H, W, Cout, tiles_x, tiles_y, (int)n_tiles));
     }
     LW_TRY(cudaGetLastError());
     return LW_OK;
@@ -463,9 +484,8 @@ extern "C" int lw_output_proj_fwd(const void* tokens, const float* w, const floa
   const long long npix = (long long)B * H * (W / 2);     // one thread per horizontal pixel pair
   const int blocks = (int)((npix + 127) / 128);
   const size_t smem = (size_t)9 * Cin * 4 * sizeof(float);
-  output_proj_kernel<<<blocks, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const bf16*>(tokens), w, b, img, out, B, Cin, H,
-                                                                                    W, Cout);
-  LW_TRY(cudaGetLastError());
+  LW_TRY(launch_k(output_proj_kernel, blocks, 128, smem, reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<const bf16*>(tokens), w, b, img, out, B,
+                  Cin, H, W, Cout));
   return LW_OK;
 }
 

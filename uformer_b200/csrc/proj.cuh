@@ -19,6 +19,8 @@ __global__ void __launch_bounds__(128) input_proj_kernel(const float* __restrict
                                                          const float* __restrict__ bias, bf16* __restrict__ tok, int B,
                                                          int Cin, int H, int W, int E) {
   __shared__ __align__(16) float sw[36 * 64 + 64];
+  pdl_launch_dependents();
+  pdl_wait();
   const int K = Cin * 9;
   for (int i = threadIdx.x; i < K * E; i += 128) {
     const int k = i / E, e = i % E;
@@ -76,6 +78,8 @@ __global__ void __launch_bounds__(128) output_proj_kernel(const bf16* __restrict
                                                           const float* __restrict__ bias, const float* __restrict__ img,
                                                           float* __restrict__ out, int B, int Cin, int H, int W, int Cout) {
   extern __shared__ __align__(16) float swo[];        // [9][Cin][4]
+  pdl_launch_dependents();
+  pdl_wait();
   for (int i = threadIdx.x; i < 9 * Cin * 4; i += 128) {
     const int tap = i / (Cin * 4), ci = (i / 4) % Cin, co = i & 3;
     swo[i] = (co < Cout) ? w[((size_t)co * Cin + ci) * 9 + tap] : 0.f;
@@ -181,6 +185,8 @@ __global__ void __launch_bounds__(128, 4) output_proj_tc_kernel(const __grid_con
     tma_prefetch_desc(&xmap);
   }
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 128);
+  pdl_launch_dependents();
+  pdl_wait();                      // nothing above touches global memory
   // B operand image, built once per CTA from the fp32 conv weight: row n < 32: bf16(w) of (tap, co) = (n / Cout, n % Cout);
   // row 32 + n: the bf16 remainder; unused rows zero.
   for (int i = tid; i < 64 * CIN; i += 128) {

@@ -304,6 +304,15 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
                : "memory");
 }
 
+// ----------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  Every kernel of the library calls pdl_launch_dependents() at its top, so the next
+// kernel in the stream / graph may be scheduled onto SMs as they free up, and pdl_wait() after its own on-chip set-up
+// (mbarrier init, TMEM allocation, tensor-map prefetch) and BEFORE its first global-memory access: the wait returns when every
+// prerequisite grid has completed and its writes are visible.  Launched without the programmatic attribute both are no-ops.
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // explicit shared-space accesses on 32-bit shared addresses (keeps LDS/STS instead of generic LD/ST)
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;

@@ -92,6 +92,8 @@ __global__ void __launch_bounds__(kThreads8, (C <= 128 && HD <= 32) ? 2 : 1) wms
     fence_mbar_init();
   }
   if (warp == 8) tmem_alloc(smem_u32(&ms.tmem_base), Cfg::T_ALLOC);
+  pdl_launch_dependents();
+  pdl_wait();                      // nothing above touches global memory
   tc_fence_before();
   __syncthreads();
   tc_fence_after();

@@ -85,6 +85,8 @@ __global__ void __launch_bounds__(kThreads8, 1) wmsa16_kernel(const lw_wmsa_args
     fence_mbar_init();
   }
   if (warp == 8) tmem_alloc(smem_u32(&ms.tmem_base), Cfg::T_ALLOC);
+  pdl_launch_dependents();
+  pdl_wait();                      // nothing above touches global memory
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
