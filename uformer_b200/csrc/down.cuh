@@ -13,13 +13,16 @@
 namespace lw {
 
 struct DownCfg {
-  static constexpr int STAGES = 2;      // weight ring (two stages: two CTAs share an SM, one runs its epilogue under the other's main loop)
   static constexpr int ABUF = 4;        // A k-block buffers
   static constexpr int S_A = 0;
-  static constexpr int S_RING = ABUF * 16384;
-  static constexpr int S_MISC = S_RING + STAGES * kStageBytes;
-  static constexpr int SMEM_BYTES = S_MISC + 1024 + 1024;
+  static constexpr int S_MISC = ABUF * 16384;
+  static constexpr int S_RING = S_MISC + 1024;
+  // weight ring depth (kernel argument): 2 stages where the accumulator is <= 256 TMEM columns — two CTAs then share an SM and
+  // one runs its epilogue under the other's main loop; 4 stages for wider outputs (Cout = 512 streams four 16 KB chunks per
+  // k-block), whose 133 KB keep one CTA per SM (a second one could only block in tcgen05.alloc).
+  static constexpr int smem_bytes(int stages) { return S_RING + stages * kStageBytes + 1024; }
 };
+static_assert(DownCfg::S_RING % 1024 == 0, "ring alignment");
 
 struct DownMisc {
   int row_tok[128];
@@ -33,7 +36,7 @@ static_assert(sizeof(DownMisc) <= 1024, "misc too large");
 __device__ __forceinline__ void cp_async_wait_group2() { asm volatile("cp.async.wait_group 2;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_group1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
-__global__ void __launch_bounds__(kThreads8, 2) down_kernel(const AStreamArgs a, const int t_alloc) {
+__global__ void __launch_bounds__(kThreads8, 2) down_kernel(const AStreamArgs a, const int t_alloc, const int stages) {
   using Cfg = DownCfg;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -64,13 +67,13 @@ __global__ void __launch_bounds__(kThreads8, 2) down_kernel(const AStreamArgs a,
 
   if (warp == 8) {
     if (lane == 0) {
-      Ring ring{smem_u32(smem + Cfg::S_RING), smem_u32(&ms.bar_full[0]), smem_u32(&ms.bar_empty[0]), Cfg::STAGES, 0};
+      Ring ring{smem_u32(smem + Cfg::S_RING), smem_u32(&ms.bar_full[0]), smem_u32(&ms.bar_empty[0]), stages, 0};
       for (int kb = 0; kb < KB; ++kb)
         for (int nc = 0; nc < NC; ++nc)
           ring.load(a.w_img + (size_t)(kb * NC + nc) * chunk_bytes, chunk_bytes);
     }
   } else if (warp == 9) {
-    Ring ring{smem_u32(smem + Cfg::S_RING), smem_u32(&ms.bar_full[0]), smem_u32(&ms.bar_empty[0]), Cfg::STAGES, 0};
+    Ring ring{smem_u32(smem + Cfg::S_RING), smem_u32(&ms.bar_full[0]), smem_u32(&ms.bar_empty[0]), stages, 0};
     const uint32_t idesc = make_idesc_bf16(128, a.nch);
     const uint32_t ring_base = smem_u32(smem + Cfg::S_RING);
     const uint64_t b_desc0 = kmajor_desc<128>(ring_base);

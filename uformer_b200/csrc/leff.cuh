@@ -37,6 +37,9 @@ struct AResArgs {
   int H, W, Cout, out_stride;
   long long* trace;   // dbg&16: CTA 0 writes clock64 timestamps here (profiling aid)
   int dbg;   // profiling knobs (env LW_DEBUG): 1 skip epilogue stores, 2 skip GELU, 4 skip weight loads, 8 skip A staging loads
+  int nsplit;         // CTAs per 128-row tile (grid = tiles * nsplit): each takes NC / nsplit consecutive N chunks.  Small token
+                      // maps (the 16 x 16 and 32 x 32 stages) otherwise launch fewer CTAs than there are SMs; staging the A tile
+                      // twice is cheap next to streaming the whole weight through one CTA.
 };
 
 template <int K>
@@ -96,8 +99,9 @@ __global__ void __launch_bounds__(kThreads8, (K <= 128) ? 2 : 1) ares_kernel(con
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   GemmMisc& ms = *reinterpret_cast<GemmMisc*>(smem + Cfg::S_MISC);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int tile = blockIdx.x;
-  const int NC = a.n_total / a.nch;
+  const int tile = blockIdx.x / a.nsplit;
+  const int NCT = a.n_total / a.nch / a.nsplit;                 // N chunks of this CTA: [nc0, nc0 + NCT)
+  const int nc0 = (blockIdx.x % a.nsplit) * NCT;
 
   if (tid == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(smem_u32(&ms.bar_full[s]), 1); mbar_init(smem_u32(&ms.bar_empty[s]), 1); }
@@ -118,7 +122,7 @@ __global__ void __launch_bounds__(kThreads8, (K <= 128) ? 2 : 1) ares_kernel(con
   if (warp == 8) {
     if (lane == 0) {
       Ring ring{smem_u32(smem + Cfg::S_RING), smem_u32(&ms.bar_full[0]), smem_u32(&ms.bar_empty[0]), Cfg::STAGES, 0, Cfg::STAGE_BYTES};
-      for (int nc = 0; nc < NC; ++nc)
+      for (int nc = nc0; nc < nc0 + NCT; ++nc)
         for (int kb = 0; kb < Cfg::KB; ++kb)
           if (LW_DBG(a, 4)) { mbar_wait(ring.empty(), ring.phase() ^ 1); mbar_arrive(ring.full()); ++ring.idx; }
           else ring.load(a.w_img + (size_t)(nc * Cfg::KB + kb) * chunk_bytes, chunk_bytes);
@@ -134,7 +138,7 @@ __global__ void __launch_bounds__(kThreads8, (K <= 128) ? 2 : 1) ares_kernel(con
       mbar_wait(smem_u32(&ms.bar_a_ready), 0);
       tc_fence_after();
       LW_TRACE_STMT(if (tr) a.trace[ti++] = clock64();)
-      for (int nc = 0; nc < NC; ++nc) {
+      for (int nc = 0; nc < NCT; ++nc) {                      // (local chunk counter: buffers and phases)
         const int buf = nc & 1;
         mbar_wait(smem_u32(&ms.bar_d_empty[buf]), ((nc >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -201,9 +205,9 @@ __global__ void __launch_bounds__(kThreads8, (K <= 128) ? 2 : 1) ares_kernel(con
     auto group_bar = [](int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 2) : "memory"); };
     LW_TRACE_STMT(const bool trw = (a.dbg & 16) && blockIdx.x == 0 && tid == 0 && a.trace != nullptr; int tw = 512, tw2 = 1024;)
     LW_TRACE_STMT(if (trw) a.trace[tw++] = clock64();)
-    for (int nc = 0; nc < NC; ++nc) {
-      const int buf = nc & 1;
-      mbar_wait(smem_u32(&ms.bar_d_full[buf]), (nc >> 1) & 1);
+    for (int ncl = 0; ncl < NCT; ++ncl) {
+      const int buf = ncl & 1, nc = nc0 + ncl;
+      mbar_wait(smem_u32(&ms.bar_d_full[buf]), (ncl >> 1) & 1);
       tc_fence_after();
       LW_TRACE_STMT(if (trw) a.trace[tw++] = clock64();)
       for (int sc = 0; sc < a.nch; sc += 128) {

@@ -214,13 +214,21 @@ extern "C" int lw_wmsa_fwd(const lw_wmsa_args* a, lw_stream_t stream) {
 }
 
 // ------------------------------------------------------------------------------------------------
+template <int K>
+static int cap_ares_ctas() { return sm_count() * (K <= 128 ? 2 : 1); }
 template <int K, int EPI>
 static int launch_ares(const AResArgs& a, cudaStream_t st) {
   using Cfg = AResCfg<K>;
   static_assert(Cfg::SMEM_BYTES <= 232448, "smem budget");
   LW_ENSURE_SMEM((ares_kernel<K, EPI>), Cfg::SMEM_BYTES);
   const int tiles = (a.n_rows + 127) / 128;
-  LW_TRY(launch_k(ares_kernel<K, EPI>, tiles, kThreads8, Cfg::SMEM_BYTES, st, a));
+  // few tiles (the 16 x 16 / 32 x 32 token maps): split the N range of a tile over 2 or 4 CTAs while the grid still fits the machine
+  AResArgs aa = a;
+  aa.nsplit = 1;
+  const int cap = cap_ares_ctas<K>();
+  const int NC = a.n_total / a.nch;
+  while (aa.nsplit < 4 && tiles * aa.nsplit * 2 <= cap && NC % (aa.nsplit * 2) == 0) aa.nsplit *= 2;
+  LW_TRY(launch_k(ares_kernel<K, EPI>, tiles * aa.nsplit, kThreads8, Cfg::SMEM_BYTES, st, aa));
   return LW_OK;
 }
 template <int EPI>
@@ -435,14 +443,10 @@ extern "C" int lw_downsample_fwd(const lw_down_args* p, lw_stream_t stream) {
   a.bias = p->bias; a.out = reinterpret_cast<bf16*>(p->out);
   const int rows = p->B * (p->H / 2) * (p->W / 2);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  // two CTAs share an SM (one drains its accumulator under the other's main loop) unless the accumulator needs more than half
-  // of TMEM: then a second resident CTA would only block in tcgen05.alloc, so the launch asks for more than half of the SM's
-  // shared memory to keep one CTA per SM
-  constexpr int kDownSmemSolo = 120 * 1024;
-  static_assert(DownCfg::SMEM_BYTES <= kDownSmemSolo, "solo smem request");
-  LW_ENSURE_SMEM(down_kernel, kDownSmemSolo);
   const int t_alloc = pow2_cols(a.N);
-  LW_TRY(launch_k(down_kernel, (rows + 127) / 128, kThreads8, t_alloc > 256 ? kDownSmemSolo : DownCfg::SMEM_BYTES, st, a, t_alloc));
+  const int stages = t_alloc > 256 ? 4 : 2;            // see DownCfg
+  LW_ENSURE_SMEM(down_kernel, DownCfg::smem_bytes(4));
+  LW_TRY(launch_k(down_kernel, (rows + 127) / 128, kThreads8, DownCfg::smem_bytes(stages), st, a, t_alloc, stages));
   return LW_OK;
 }
 
