@@ -409,12 +409,13 @@ def test_wmsa_tma_gather_kernel(dim, heads, H, B, shift, max_ctas, modu):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("cin,cout,H,W,B,max_ctas,resid", [(64, 3, 40, 24, 2, 0, True), (64, 3, 64, 64, 3, 2, True), (32, 3, 16, 48, 1, 1, True),
-                                                         (32, 1, 24, 24, 2, 0, False), (128, 3, 16, 16, 1, 0, True)])
+                                                         (32, 1, 24, 24, 2, 0, False), (128, 3, 16, 16, 1, 0, True), (64, 3, 16, 18, 2, 0, True)])
 def test_output_proj_vs_fp32_conv(cin, cout, H, W, B, max_ctas, resid):
     """OutputProj + global residual (model.py:834-842, :1305).  Cin in {32, 64} takes the tensor-core kernel (GEMM over the
     halo'd token tile, then the 9 taps; the fp32 weight is split into two bf16 halves, so the only rounding is the fp32
-    accumulation order); other widths the SIMT kernel.  Checked against torch's fp32 conv2d of the SAME bf16 tokens — sizes that
-    are not multiples of the 8 x 16 tile, several tiles per CTA (lw_set_max_ctas), no residual."""
+    accumulation order; the NCHW planes leave through TMA tensor stores, per-thread stores when W % 4 != 0); other widths the
+    SIMT kernel.  Checked against torch's fp32 conv2d of the SAME bf16 tokens — sizes that are not multiples of the 8 x 16 tile,
+    several tiles per CTA (lw_set_max_ctas), no residual."""
     import torch.nn.functional as F
     from uformer_b200 import _lib, ops
     torch.manual_seed(cin + H + W)
@@ -466,3 +467,30 @@ def test_block_ws16_vs_oracle(dim, heads, H, shift, modu, B):
         mask = (torch.rand(B, 1, H, H) > 0.8).float()
         blk.residual_fp32 = False
         _check(_run(blk, x, mask=mask), O.lewin_block(x, st, "", heads, 16, 0, input_mask=mask), f"block ws16 C={dim} input mask")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("E,H,W,B,max_ctas", [(32, 40, 24, 2, 0), (32, 64, 64, 3, 2), (16, 16, 48, 1, 1), (16, 24, 18, 2, 0), (64, 16, 16, 1, 0)])
+def test_input_proj_vs_fp32_conv(E, H, W, B, max_ctas):
+    """InputProj (model.py:800-805): conv3x3 + LeakyReLU(0.01), NCHW fp32 image -> bf16 tokens.  E in {16, 32} takes the
+    tensor-core kernel (im2col rows in shared memory, three-term bf16 split of image and weight: fp32-accurate products); other
+    widths the SIMT kernel.  Against torch's fp32 conv2d on the CPU: the only rounding left is the bf16 store (2^-9 relative)."""
+    import torch.nn.functional as F
+    from uformer_b200 import _lib, ops
+    torch.manual_seed(E + H + W)
+    img = torch.rand(B, 3, H, W)
+    w = torch.randn(E, 3, 3, 3) * 0.3
+    b = torch.randn(E) * 0.1
+    ref = F.leaky_relu(F.conv2d(img, w, b, padding=1), 0.01).flatten(2).transpose(1, 2)         # (B, HW, E)
+    lib = _lib.load()
+    lib.lw_set_max_ctas(max_ctas)
+    try:
+        y = ops.input_proj(img.to(DEV), w.to(DEV), b.to(DEV))
+        torch.cuda.synchronize()
+    finally:
+        lib.lw_set_max_ctas(0)
+    y = y.float().cpu()
+    err = ((y - ref).abs() / ref.abs().clamp_min(0.05)).max().item()
+    exact = (y == ref.to(torch.bfloat16).float()).float().mean().item()
+    print(f"input_proj E={E} {H}x{W} B={B}: max rel err {err:.2e}, {100 * exact:.2f}% of the outputs equal bf16(fp32 reference)")
+    assert err < 4.5e-3 and exact > 0.98, (err, exact)

@@ -32,7 +32,7 @@ def main(csv_path, labels_path, out_path):
         d = launches.setdefault(int(r[iid]), {"name": r[ikn]})
         d[r[imn]] = (r[imv], r[imu])
     ordered = [launches[k] for k in sorted(launches)]
-    OURS = ("input_proj_kernel", "output_proj_kernel", "output_proj_tc_kernel", "wmsa_kernel", "wmsa16_kernel", "wmsa_tma_kernel", "leff_fused_kernel", "ares_kernel", "leff2_kernel", "down_kernel",
+    OURS = ("input_proj_kernel", "input_proj_tc_kernel", "output_proj_kernel", "output_proj_tc_kernel", "wmsa_kernel", "wmsa16_kernel", "wmsa_tma_kernel", "leff_fused_kernel", "ares_kernel", "leff2_kernel", "down_kernel",
             "charbonnier", "adamw_kernel")
     is_ours = lambda n: n.replace("void ", "").replace("lw::", "").startswith(OURS)          # noqa: E731
     ours = [d for d in ordered if is_ours(d["name"])]

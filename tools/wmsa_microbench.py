@@ -45,7 +45,7 @@ def main():
                 x = torch.randn(B_, N, dim, device=dev).to(torch.bfloat16)
                 times = []
                 with torch.no_grad():
-                    for it in range(23):
+                    for it in range(int(os.environ.get("WMSA_MB_ITERS", 23))):      # (4 under ncu: 3 warm-ups + 1)
                         flush.zero_()
                         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                         a.record()

@@ -36,7 +36,8 @@ static_assert(sizeof(DownMisc) <= 1024, "misc too large");
 __device__ __forceinline__ void cp_async_wait_group2() { asm volatile("cp.async.wait_group 2;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_group1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
-__global__ void __launch_bounds__(kThreads8, 2) down_kernel(const AStreamArgs a, const int t_alloc, const int stages) {
+template <int OCC>      // CTAs per SM the register allocation is bounded for (2: <= 96 registers; 1: the deep-K Cout = 512 case keeps its 142)
+__global__ void __launch_bounds__(kThreads8, OCC) down_kernel(const AStreamArgs a, const int t_alloc, const int stages) {
   using Cfg = DownCfg;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));

@@ -333,6 +333,20 @@ static int make_token_map(CUtensorMap* m, const void* base, int B, int H, int W,
   return LW_OK;
 }
 
+// fp32 planes (P, H, W) contiguous -> 3-D map (W, H, P), box (bw, bh, 1), no swizzle (the NCHW output of OutputProj)
+static int make_plane_map(CUtensorMap* m, const void* base, int P, int H, int W, int bw, int bh) {
+  PFN_encodeTiled enc = encode_tiled_fn();
+  if (!enc) { snprintf(g_err, sizeof(g_err), "cuTensorMapEncodeTiled unavailable"); return LW_ERR_CUDA; }
+  const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)P};
+  const cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * 4 * H};
+  const cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)bh, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { snprintf(g_err, sizeof(g_err), "cuTensorMapEncodeTiled failed (%d)", (int)r); return LW_ERR_CUDA; }
+  return LW_OK;
+}
+
 // ---- W-MSA with the TMA window gather (wmsa_tma.cuh) ----
 extern "C" int lw_wmsa_tma_supported(int C, int head_dim) {
   return (head_dim == 16 || head_dim == 32) && (C == 16 || C == 32 || C == 64 || C == 128 || C == 256) && C % head_dim == 0 && C >= head_dim;
@@ -445,8 +459,13 @@ extern "C" int lw_downsample_fwd(const lw_down_args* p, lw_stream_t stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int t_alloc = pow2_cols(a.N);
   const int stages = t_alloc > 256 ? 4 : 2;            // see DownCfg
-  LW_ENSURE_SMEM(down_kernel, DownCfg::smem_bytes(4));
-  LW_TRY(launch_k(down_kernel, (rows + 127) / 128, kThreads8, DownCfg::smem_bytes(stages), st, a, t_alloc, stages));
+  if (stages == 4) {
+    LW_ENSURE_SMEM(down_kernel<1>, DownCfg::smem_bytes(4));
+    LW_TRY(launch_k(down_kernel<1>, (rows + 127) / 128, kThreads8, DownCfg::smem_bytes(4), st, a, t_alloc, stages));
+  } else {
+    LW_ENSURE_SMEM(down_kernel<2>, DownCfg::smem_bytes(2));
+    LW_TRY(launch_k(down_kernel<2>, (rows + 127) / 128, kThreads8, DownCfg::smem_bytes(2), st, a, t_alloc, stages));
+  }
   return LW_OK;
 }
 
@@ -455,6 +474,24 @@ extern "C" int lw_input_proj_fwd(const float* img, const float* w, const float* 
                                  int32_t H, int32_t W, int32_t E, lw_stream_t stream) {
   if (!img || !w || !b || !tokens) return LW_ERR_NULL;
   if (B <= 0 || H <= 0 || W <= 0 || (W & 1) || E % 8 || E > 64 || Cin < 1 || Cin > 4) return LW_ERR_BAD_SHAPE;
+  if (Cin == 3 && (E == 16 || E == 32) && aligned16(tokens)) {           // tensor-core path (im2col rows in shared memory): proj.cuh
+    const int tiles_x = (W + 15) / 16, tiles_y = (H + 7) / 8;
+    const long long n_tiles = (long long)tiles_x * tiles_y * B;
+    if (n_tiles >= (1ll << 31)) return LW_ERR_BAD_SHAPE;
+    const int cap = 4 * sm_count();
+    const int grid = cap_grid(n_tiles < cap ? (int)n_tiles : cap);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (E == 32) {
+      LW_ENSURE_SMEM(input_proj_tc_kernel<32>, InProjCfg<32>::SMEM_BYTES);
+      LW_TRY(launch_k(input_proj_tc_kernel<32>, grid, 128, InProjCfg<32>::SMEM_BYTES, st, img, w, b, reinterpret_cast<bf16*>(tokens), B, H, W, tiles_x, tiles_y,
+                      (int)n_tiles));
+    } else {
+      LW_ENSURE_SMEM(input_proj_tc_kernel<16>, InProjCfg<16>::SMEM_BYTES);
+      LW_TRY(launch_k(input_proj_tc_kernel<16>, grid, 128, InProjCfg<16>::SMEM_BYTES, st, img, w, b, reinterpret_cast<bf16*>(tokens), B, H, W, tiles_x, tiles_y,
+                      (int)n_tiles));
+    }
+    return LW_OK;
+  }
   const long long npix = (long long)B * H * (W / 2);     // one thread per horizontal pixel pair
   const int blocks = (int)((npix + 127) / 128);
   LW_TRY(launch_k(input_proj_kernel, blocks, 128, 0, reinterpret_cast<cudaStream_t>(stream), img, w, b, reinterpret_cast<bf16*>(tokens), B, Cin, H, W, E));
@@ -467,8 +504,16 @@ extern "C" int lw_output_proj_fwd(const void* tokens, const float* w, const floa
   if (B <= 0 || H <= 0 || W <= 0 || (W & 1) || Cin % 8 || Cin > 128 || Cout < 1 || Cout > 4) return LW_ERR_BAD_SHAPE;
   if ((Cin == 32 || Cin == 64) && Cout <= 3 && aligned16(tokens)) {      // tensor-core path (GEMM first, taps after): proj.cuh
     CUtensorMap map;
-    const int rc = make_token_map(&map, tokens, B, H, W, Cin, Cin, Cin, 18, 10);
+    int rc = make_token_map(&map, tokens, B, H, W, Cin, Cin, Cin, 18, 10);
     if (rc != LW_OK) return rc;
+    // the output leaves through TMA stores when its rows are 16-byte pitched and aligned (else per-thread stores)
+    const int use_tma_store = (W % 4 == 0) && aligned16(out);
+    CUtensorMap omap;
+    memset(&omap, 0, sizeof(omap));
+    if (use_tma_store) {
+      rc = make_plane_map(&omap, out, B * Cout, H, W, 16, 8);
+      if (rc != LW_OK) return rc;
+    }
     const int tiles_x = (W + 15) / 16, tiles_y = (H + 7) / 8;
     const long long n_tiles = (long long)tiles_x * tiles_y * B;
     if (n_tiles >= (1ll << 31)) return LW_ERR_BAD_SHAPE;
@@ -477,10 +522,10 @@ extern "C" int lw_output_proj_fwd(const void* tokens, const float* w, const floa
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (Cin == 64) {
       LW_ENSURE_SMEM(output_proj_tc_kernel<64>, OutProjCfg<64>::SMEM_BYTES);
-      LW_TRY(launch_k(output_proj_tc_kernel<64>, grid, 128, OutProjCfg<64>::SMEM_BYTES, st, map, w, b, img, out, B, H, W, Cout, tiles_x, tiles_y, (int)n_tiles));
+      LW_TRY(launch_k(output_proj_tc_kernel<64>, grid, 128, OutProjCfg<64>::SMEM_BYTES, st, map, omap, w, b, img, out, B, H, W, Cout, tiles_x, tiles_y, (int)n_tiles, use_tma_store));
     } else {
       LW_ENSURE_SMEM(output_proj_tc_kernel<32>, OutProjCfg<32>::SMEM_BYTES);
-      LW_TRY(launch_k(output_proj_tc_kernel<32>, grid, 128, OutProjCfg<32>::SMEM_BYTES, st, map, w, b, img, out, B, H, W, Cout, tiles_x, tiles_y, (int)n_tiles));
+      LW_TRY(launch_k(output_proj_tc_kernel<32>, grid, 128, OutProjCfg<32>::SMEM_BYTES, st, map, omap, w, b, img, out, B, H, W, Cout, tiles_x, tiles_y, (int)n_tiles, use_tma_store));
     }
     LW_TRY(cudaGetLastError());
     return LW_OK;

@@ -145,8 +145,11 @@ __global__ void __launch_bounds__(128) output_proj_kernel(const bf16* __restrict
 //          tile i+1 is requested as soon as the GEMM of tile i has read the buffer and lands under the tap phase.
 //   GEMM   one M=128 + one M=64 tcgen05.mma chain over the 192 (>= 180) halo rows.  The weights keep fp32 accuracy with bf16
 //          operands: B rows [0, 32) carry bf16(w), rows [32, 64) carry bf16(w - bf16(w)); the epilogue adds the two halves.
-//   taps   Z -> shared memory ([192][29] fp32, odd pitch: conflict-free), one thread per output pixel sums its 9 taps and
-//          writes NCHW fp32 with the global residual.
+//   taps   Z -> shared memory ([180][29] fp32, odd pitch: conflict-free), one thread per output pixel sums its 9 taps, adds
+//          bias and the global residual and parks the result in an [Cout][8][16] fp32 tile.
+//   store  the NCHW output leaves through the TMA engine: one cp.async.bulk.tensor.3d store of a 16 x 8 box per channel plane
+//          (tensor map (W, H, B*Cout); boxes that overhang the image are clipped by the hardware).  Falls back to per-thread
+//          stores when the row pitch is not a multiple of 16 bytes (use_tma_store = 0).
 // One HBM read of the token map (neighbouring halos hit L2) instead of 9 x 4 register-blocked re-reads + 1728 FMAs per pixel.
 // ----------------------------------------------------------------------------------------------
 template <int CIN>
@@ -159,16 +162,24 @@ struct OutProjCfg {
   static constexpr int S_A = 0;                             // ONE input buffer: four CTAs share an SM and overlap each other's phases
   static constexpr int S_W = A_BYTES;
   static constexpr int S_Z = S_W + W_BYTES;
-  static constexpr int S_BAR = S_Z + 192 * ZP * 4;
+  static constexpr int S_O = (S_Z + 180 * ZP * 4 + 127) / 128 * 128;   // [3][8][16] fp32 output planes of the tile: the source of the TMA store
+  static constexpr int S_BAR = S_O + 3 * 512;
+  static_assert(4 * (S_BAR + 64 + 1024 + 1024) <= 233472, "four CTAs per SM");
   static constexpr int SMEM_BYTES = S_BAR + 64 + 1024;
   static_assert(A_BYTES % 1024 == 0 && S_W % 1024 == 0, "operand alignment");
 };
 
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src_smem, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(src_smem), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+
 template <int CIN>
-__global__ void __launch_bounds__(128, 4) output_proj_tc_kernel(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ w,
-                                                             const float* __restrict__ bias, const float* __restrict__ img,
-                                                             float* __restrict__ out, int B, int H, int W, int Cout, int tiles_x,
-                                                             int tiles_y, int n_tiles) {
+__global__ void __launch_bounds__(128, 4) output_proj_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap omap,
+                                                             const float* __restrict__ w, const float* __restrict__ bias,
+                                                             const float* __restrict__ img, float* __restrict__ out, int B, int H, int W, int Cout,
+                                                             int tiles_x, int tiles_y, int n_tiles, int use_tma_store) {
   using Cfg = OutProjCfg<CIN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -176,13 +187,14 @@ __global__ void __launch_bounds__(128, 4) output_proj_tc_kernel(const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Cfg::S_BAR + 32);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_my = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-  const uint32_t sA = smem_u32(smem + Cfg::S_A), sW = smem_u32(smem + Cfg::S_W), sZ = smem_u32(smem + Cfg::S_Z);
+  const uint32_t sA = smem_u32(smem + Cfg::S_A), sW = smem_u32(smem + Cfg::S_W), sZ = smem_u32(smem + Cfg::S_Z), sO = smem_u32(smem + Cfg::S_O);
   const int ntap = 9 * Cout;                                 // <= 27 columns of Z
 
   if (tid == 0) {
     mbar_init(smem_u32(&bars[0]), 1); mbar_init(smem_u32(&bars[1]), 1);
     fence_mbar_init();
     tma_prefetch_desc(&xmap);
+    if (use_tma_store) tma_prefetch_desc(&omap);
   }
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 128);
   pdl_launch_dependents();
@@ -264,12 +276,13 @@ __global__ void __launch_bounds__(128, 4) output_proj_tc_kernel(const __grid_con
       tmem_ld32(tb + tl + 64, hi);
       tmem_ld32(tb + tl + 96, lo);
       tmem_wait_ld();
-      if (lane < 16) {
+      if (lane < 16 && 128 + 16 * warp + lane < 180) {       // (Z holds the 180 halo rows only)
         const uint32_t zr2 = sZ + (128 + 16 * warp + lane) * (Cfg::ZP * 4);
 #pragma unroll
         for (int n = 0; n < 27; ++n) sts32f(zr2 + n * 4, __uint_as_float(hi[n]) + __uint_as_float(lo[n]));
       }
     }
+    if (tid == 0 && use_tma_store) bulk_wait_read0();       // the previous tile's TMA stores (issued a GEMM ago) have read the output planes
     tc_fence_before();
     __syncthreads();
     // ---- 9 taps per pixel (+ bias + global residual, already in acc), NCHW fp32 ----
@@ -282,16 +295,174 @@ __global__ void __launch_bounds__(128, 4) output_proj_tc_kernel(const __grid_con
         for (int co = 0; co < 3; ++co)
           if (co < Cout) acc[co] += lds32f(zr + co * 4);
       }
-    if (inside) {
+    if (use_tma_store) {
+#pragma unroll
+      for (int co = 0; co < 3; ++co)
+        if (co < Cout) sts32f(sO + co * 512 + tid * 4, acc[co]);
+      fence_async_smem();
+    } else if (inside) {
 #pragma unroll
       for (int co = 0; co < 3; ++co)
         if (co < Cout) out[(((size_t)b * Cout + co) * H + Y) * W + X] = acc[co];
     }
-    __syncthreads();                                        // Z is free again
+    __syncthreads();                                        // Z is free again; the output planes are complete
+    if (tid == 0 && use_tma_store) {
+      for (int co = 0; co < Cout; ++co) tma_store_3d(&omap, sO + co * 512, tx * 16, ty * 8, b * Cout + co);
+      bulk_commit();
+    }
   }
+  if (tid == 0 && use_tma_store) bulk_wait0();
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tb, 128);
+}
+
+// ----------------------------------------------------------------------------------------------
+// input_proj on the tensor core (Cin = 3, E in {16, 32}): the 3 x 3 x 3 im2col row of a pixel (K = 27) is built in shared memory
+// and multiplied with the weight by tcgen05.  Both operands keep fp32 accuracy with bf16 inputs through a three-term split
+//   x w ~ xh wh + xh wl + xl wh      (xh = bf16(x), xl = bf16(x - xh); the dropped xl wl term is 2^-18 relative)
+// laid out as ONE K = 96 chain: A k-block 0 = [xh | xh], k-block 1 = [xl | -];  B k-block 0 = [wh | wl], k-block 1 = [wh | -].
+// PERSISTENT CTAs (4 per SM) walk 8 x 16 pixel tiles: the fp32 image halo (3 x 10 x 18, zero outside the image = the conv's
+// padding) is staged in shared memory — the loads of tile i+1 are issued before the GEMM of tile i is waited for — every
+// thread builds the im2col row of its pixel (12 16-byte stores), one elected thread issues six M = 128 UMMAs, and the epilogue
+// (thread = TMEM lane = pixel) adds the bias, applies LeakyReLU(0.01) and writes the pixel's E bf16 channels.
+// Replaces 864 fp32 FMAs per pixel of the SIMT kernel (which stays for other widths).
+// ----------------------------------------------------------------------------------------------
+template <int E>
+struct InProjCfg {
+  static constexpr int S_A = 0;                             // 2 k-blocks x 128 rows x 128 B
+  static constexpr int S_W = 2 * 16384;                     // 2 k-blocks x E rows x 128 B
+  static constexpr int S_HALO = S_W + 2 * E * 128;          // 3 x 10 x 18 fp32
+  static constexpr int S_BAR = S_HALO + 2176;
+  static constexpr int SMEM_BYTES = S_BAR + 64 + 1024;
+  static_assert(S_W % 1024 == 0 && (E * 128) % 1024 == 0, "operand alignment");
+};
+
+template <int E>
+__global__ void __launch_bounds__(128, 4) input_proj_tc_kernel(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ bias,
+                                                            bf16* __restrict__ tok, int B, int H, int W, int tiles_x, int tiles_y, int n_tiles) {
+  using Cfg = InProjCfg<E>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::S_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Cfg::S_BAR + 32);
+  float* halo = reinterpret_cast<float*>(smem + Cfg::S_HALO);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int n_my = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const uint32_t sA = smem_u32(smem + Cfg::S_A), sW = smem_u32(smem + Cfg::S_W);
+
+  if (tid == 0) { mbar_init(smem_u32(&bars[0]), 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 32);
+  pdl_launch_dependents();
+  pdl_wait();                      // nothing above touches global memory
+  // B operand images, built once per CTA: k-block 0 row e = [wh(27) 0.. | wl(27) 0..], k-block 1 row e = [wh(27) 0.. | 0]
+  for (int i = tid; i < 2 * E * 64; i += 128) {
+    const int kb = i / (E * 64), e = (i / 64) % E, c = i % 64, k = c & 31;
+    float v = 0.f;
+    if (k < 27 && !(kb == 1 && c >= 32)) {
+      const float wf = __ldg(w + e * 27 + k);
+      const float hi = __bfloat162float(__float2bfloat16_rn(wf));
+      v = (kb == 0 && c >= 32) ? wf - hi : hi;
+    }
+    const __nv_bfloat16 hv = __float2bfloat16_rn(v);
+    asm volatile("st.shared.b16 [%0], %1;" ::"r"(sW + kb * (E * 128) + swz<128>(e, 2 * c)), "h"(*reinterpret_cast<const unsigned short*>(&hv)) : "memory");
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = *tmem_slot;
+  constexpr uint32_t idesc = make_idesc_bf16(128, E);
+  const int py = tid >> 4, px = tid & 15;
+  float bv[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) bv[e] = __ldg(bias + e);
+
+  // halo elements i = tid + 128 j (j < 5) of a tile: channel i / 180, row (i % 180) / 18, column i % 18
+  float pre[5];
+  auto prefetch = [&](int it) {
+    const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+    const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const int i = tid + 128 * j;
+      const int c = i / 180, r = (i % 180) / 18, col = i % 18;
+      const int Y = ty * 8 - 1 + r, X = tx * 16 - 1 + col;
+      pre[j] = (i < 540 && Y >= 0 && Y < H && X >= 0 && X < W) ? __ldg(img + (((size_t)b * 3 + c) * H + Y) * W + X) : 0.f;
+    }
+  };
+  if (n_my > 0) prefetch(0);
+
+  for (int it = 0; it < n_my; ++it) {
+    const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+    const int tx = tile % tiles_x, ty = (tile / tiles_x) % tiles_y, b = tile / (tiles_x * tiles_y);
+#pragma unroll
+    for (int j = 0; j < 5; ++j)
+      if (tid + 128 * j < 540) halo[tid + 128 * j] = pre[j];
+    tc_fence_before();                                       // (the previous tile's TMEM reads precede the barrier, the next GEMM follows it)
+    __syncthreads();
+    // ---- im2col row of this thread's pixel: k = ci*9 + ky*3 + kx, hi / lo bf16 split ----
+    {
+      uint32_t hi[16], lo[16];                               // 32 bf16 each (k = 27..31 zero)
+#pragma unroll
+      for (int k2 = 0; k2 < 16; ++k2) {
+        float v0 = 0.f, v1 = 0.f;
+        const int k0 = 2 * k2, k1 = 2 * k2 + 1;
+        if (k0 < 27) v0 = halo[(k0 / 9) * 180 + (py + (k0 % 9) / 3) * 18 + px + (k0 % 3)];
+        if (k1 < 27) v1 = halo[(k1 / 9) * 180 + (py + (k1 % 9) / 3) * 18 + px + (k1 % 3)];
+        const uint32_t h = pack_bf16(v0, v1);
+        hi[k2] = h;
+        lo[k2] = pack_bf16(v0 - __uint_as_float(h << 16), v1 - __uint_as_float(h & 0xffff0000u));
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 hv = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+        sts128(sA + swz<128>(tid, 16 * j), hv);
+        sts128(sA + swz<128>(tid, 64 + 16 * j), hv);
+        sts128(sA + 16384 + swz<128>(tid, 16 * j), make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]));
+      }
+    }
+    fence_async_smem();
+    if (it + 1 < n_my) prefetch(it + 1);                     // next tile's halo: in flight under the GEMM and the epilogue
+    __syncthreads();
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) umma_ss(tb, kmajor_desc<128>(sA + ks * 32), kmajor_desc<128>(sW + ks * 32), idesc, ks != 0);
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) umma_ss(tb, kmajor_desc<128>(sA + 16384 + ks * 32), kmajor_desc<128>(sW + E * 128 + ks * 32), idesc, 1u);
+        umma_commit(smem_u32(&bars[0]));
+      }
+      __syncwarp();
+    }
+    mbar_wait(smem_u32(&bars[0]), it & 1);
+    tc_fence_after();
+    // ---- epilogue: thread = TMEM lane = pixel: + bias, LeakyReLU(0.01), E bf16 channels ----
+    {
+      uint32_t v[E];
+      if (E == 32) tmem_ld32(tb + ((uint32_t)(32 * warp) << 16), v);
+      else tmem_ld16(tb + ((uint32_t)(32 * warp) << 16), v);
+      tmem_wait_ld();
+      const int Y = ty * 8 + py, X = tx * 16 + px;
+      if (Y < H && X < W) {
+        bf16* o = tok + ((size_t)(b * H + Y) * W + X) * E;
+#pragma unroll
+        for (int e0 = 0; e0 < E; e0 += 8) {
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float a = __uint_as_float(v[e0 + j]) + bv[e0 + j];
+            f[j] = a > 0.f ? a : 0.01f * a;
+          }
+          *reinterpret_cast<uint4*>(o + e0) = pack8(f);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, 32);
 }
 
 }  // namespace lw
