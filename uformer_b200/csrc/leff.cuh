@@ -16,7 +16,7 @@ namespace lw {
 
 struct GemmMisc {
   int row_tok[128];
-  uint64_t bar_full[4], bar_empty[4];
+  uint64_t bar_full[8], bar_empty[8];
   uint64_t bar_a_ready;
   uint64_t bar_a_full[2], bar_a_empty[2];
   uint64_t bar_d_full[2], bar_d_empty[2];
@@ -49,12 +49,17 @@ struct AResCfg {
   // re-reads its whole 128 x 16 A slice every instruction); only K == 256 has the capacity for it.
   static constexpr int NCH_MAX = (K == 256) ? 256 : 128;
   static constexpr int STAGE_BYTES = NCH_MAX * 128;
-  static constexpr int STAGES = (K <= 128) ? 2 : 3;
+  // Ring depth.  The ring is latency-bound rather than bandwidth-bound: one producer thread keeps STAGES bulk copies of 16 KB in
+  // flight against ~1.3 us of loaded L2 latency (~12 GB/s per stage and SM).  K = 512 streams 2 MB of weights per 128-row tile
+  // (28 GB/s at the measured 75 us per tile): a fourth stage is paid for by epilogue passes of 64 instead of 128 accumulator
+  // columns (SUB_COLS), whose staging tiles are 20 KB instead of 36 KB.
+  static constexpr int STAGES = (K <= 128) ? 2 : (K == 512 ? 4 : 3);
+  static constexpr int SUB_COLS = (K == 512) ? 64 : 128;             // accumulator columns per epilogue pass (two column halves)
+  static constexpr int STAGE_HALF = 128 * (SUB_COLS + 16);           // one half's staging tile: 128 rows x (SUB_COLS/2 bf16 + 16 B)
   static constexpr int S_X = 0;
   static constexpr int S_RING = KB * 16384;
-  static constexpr int S_STAGE = S_RING + STAGES * STAGE_BYTES;      // epilogue staging tile: 128 rows x 272 B
-  static constexpr int STAGE_PITCH = 272;
-  static constexpr int S_BIAS = S_STAGE + 36864;                     // (2 halves x 128 rows x 144 B) ; bias of the whole N range (<= 2048 fp32)
+  static constexpr int S_STAGE = S_RING + STAGES * STAGE_BYTES;      // epilogue staging tiles of the two column halves
+  static constexpr int S_BIAS = S_STAGE + 2 * STAGE_HALF;            // bias of the whole N range (<= 2048 fp32)
   static constexpr int S_MISC = S_BIAS + 8192;
   static constexpr int SMEM_BYTES = S_MISC + 1024 + 1024;
   static constexpr int T_ALLOC = 2 * NCH_MAX;                        // two accumulator buffers
@@ -195,13 +200,13 @@ __global__ void __launch_bounds__(kThreads8, (K <= 128) ? 2 : 1) ares_kernel(con
     }
     GeluH2 gelu;
     gelu.init();
-    const int sub_cols = a.nch < 128 ? a.nch : 128;          // 128 accumulator columns per pass: 64 per column half
+    const int sub_cols = a.nch < Cfg::SUB_COLS ? a.nch : Cfg::SUB_COLS;   // accumulator columns per pass: half of them per column half
     const int grp = warp >> 2;                               // column half == synchronisation group (128 threads)
     const int cph = sub_cols >> 1;
     int cph_log2 = 4;
     while ((1 << cph_log2) < cph) ++cph_log2;
     const int pitch_g = cph * 2 + 16;
-    const uint32_t stage_g = stage_s + grp * 18432;          // 128 rows x 144 B per half
+    const uint32_t stage_g = stage_s + grp * Cfg::STAGE_HALF;
     auto group_bar = [](int g) { asm volatile("bar.sync %0, 128;" ::"r"(g + 2) : "memory"); };
     LW_TRACE_STMT(const bool trw = (a.dbg & 16) && blockIdx.x == 0 && tid == 0 && a.trace != nullptr; int tw = 512, tw2 = 1024;)
     LW_TRACE_STMT(if (trw) a.trace[tw++] = clock64();)
@@ -210,13 +215,13 @@ __global__ void __launch_bounds__(kThreads8, (K <= 128) ? 2 : 1) ares_kernel(con
       mbar_wait(smem_u32(&ms.bar_d_full[buf]), (ncl >> 1) & 1);
       tc_fence_after();
       LW_TRACE_STMT(if (trw) a.trace[tw++] = clock64();)
-      for (int sc = 0; sc < a.nch; sc += 128) {
+      for (int sc = 0; sc < a.nch; sc += sub_cols) {
         // ---- phase A: TMEM (16x256b fragments) -> (+bias, GELU) -> bf16 -> stmatrix into this column half's private
         // staging tile.  The two halves (warps 0-3 / 4-7) synchronise only among themselves, so one half's
         // copy-out overlaps the other half's GELU math. ----
         if (sub_cols == 128) ares_phase_a<8, EPI>(a, tb + buf * Cfg::NCH_MAX + sc, nc * a.nch + sc, bias_s, stage_g, pitch_g, gelu);
         else ares_phase_a<4, EPI>(a, tb + buf * Cfg::NCH_MAX + sc, nc * a.nch + sc, bias_s, stage_g, pitch_g, gelu);
-        if (sc + 128 >= a.nch) {            // accumulator fully read: hand the buffer back to the issuer
+        if (sc + sub_cols >= a.nch) {       // accumulator fully read: hand the buffer back to the issuer
           tc_fence_before();
           mbar_arrive(smem_u32(&ms.bar_d_empty[buf]));
         }

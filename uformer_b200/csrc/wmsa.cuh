@@ -29,7 +29,7 @@ struct WmsaCfg {
   static constexpr int NCH = C < 128 ? C : 128;            // proj N chunk
   static constexpr int NC = C / NCH;
   static constexpr int PROJ_CHUNK_BYTES = NCH * 128;
-  static constexpr int STAGES = (C >= 512) ? 3 : (C == 128 ? 2 : 4);   // C=128: 2 stages so two CTAs fit per SM
+  static constexpr int STAGES = (C == 128) ? 2 : 4;   // C=128: 2 stages so two CTAs fit per SM; C=512: four 16 KB stages just fit (227 KB)
   static constexpr int STAGE_BYTES = (HD == 64) ? 24576 : kStageBytes; // head_dim 64: a (head, k-block) QKV chunk is 192 rows
   // TMEM columns
   static constexpr int T_OALL = 0;                         // O for all heads, bf16 packed: C/2 cols
