@@ -1,3 +1,4 @@
-timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "block_vs_oracle or upsample or leff or module_golden or model_golden" 2>&1 | tail -3
-timeout 300 python bench.py --no-cpu-baseline --steps 10 > gpurun_out/c8_bench.json 2> gpurun_out/c8_bench.err; echo "bench rc=$?"; python -c "
-import json;d=json.load(open('gpurun_out/c8_bench.json'));print(d['value'],d['ms_per_step'],d['e2e']['value']); r=d['roofline']['by_kernel_ms']; print({k:r[k] for k in r if 'C512' in k or k.startswith('up')})"
+bash tools/collect_round.sh r02f "tests smoke bench b512 wmsa ncu"
+timeout 100 python tools/outproj_probe.py > gpurun_out/r02f_outproj_probe.log 2>&1; tail -2 gpurun_out/r02f_outproj_probe.log
+TAG=r02f bash tools/sanitizer_run.sh
+WMSA_MB_ITERS=1 timeout 400 ncu --clock-control none --csv -k regex:wmsa --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,smsp__issue_active.avg.pct --log-file gpurun_out/r02f_wmsa_microbench_ncu.csv python tools/wmsa_microbench.py > /dev/null 2>&1; echo "ncu microbench rc=$?"

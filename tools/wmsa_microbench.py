@@ -26,6 +26,7 @@ def main():
     hbm, tf = peaks.get("hbm_gbs", 6650.0), peaks.get("bf16_tflops", 1590.0)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     rows = []
+    iters = int(os.environ.get("WMSA_MB_ITERS", 23))         # 1 under ncu (one profiled launch per point)
     for ws in (8, 16):
         for hd in (16, 32, 64):
             for heads in (1, 2, 4, 8):
@@ -45,14 +46,14 @@ def main():
                 x = torch.randn(B_, N, dim, device=dev).to(torch.bfloat16)
                 times = []
                 with torch.no_grad():
-                    for it in range(int(os.environ.get("WMSA_MB_ITERS", 23))):      # (4 under ncu: 3 warm-ups + 1)
+                    for it in range(iters):
                         flush.zero_()
                         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                         a.record()
                         att(x)
                         b.record()
                         torch.cuda.synchronize()
-                        if it >= 3:
+                        if it >= 3 or iters < 4:           # (3 warm-ups unless the run is cut short for a profiler)
                             times.append(a.elapsed_time(b))
                 ms = sorted(times)[len(times) // 2]
                 flops = 2.0 * B_ * N * (4 * dim * dim + 2 * N * dim)
