@@ -479,19 +479,18 @@ def main():
     dom = max(prof.items(), key=lambda kv: kv[1][0])
     dname, (dms, dcount, dflops) = dom
     ach = dflops / dcount / (dms / dcount * 1e-3) / 1e12
-    # DRAM traffic of the dominant kernel: from the committed ncu table (tools/kernel_metrics.py), only while it describes THIS
-    # build of the library (sha256 recorded next to the numbers); otherwise null rather than a stale figure
+    # DRAM traffic of the dominant kernel: from the committed ncu table (tools/kernel_metrics.py), only while it describes THESE
+    # kernel sources (sha256 of csrc/ + the header recorded next to the numbers); otherwise null rather than a stale figure
     traffic, traffic_src, tensor_pct = None, None, None
     tpath = os.path.join(ROOT, "profiles", "r02_kernel_metrics.json")
     if os.path.isfile(tpath):
-        import hashlib
+        from uformer_b200 import _lib as _ulib
         tj = json.load(open(tpath))
-        cur = hashlib.sha256(open(lib, "rb").read()).hexdigest()[:16]
-        if tj.get("lib_sha256_16") == cur and dname in tj["dram_bytes_per_launch"]:
-            traffic, traffic_src = tj["dram_bytes_per_launch"][dname], "profiles/r02_kernel_metrics.json (ncu, same library build)"
+        if tj.get("csrc_sha256_16") == _ulib.csrc_hash() and dname in tj["dram_bytes_per_launch"]:
+            traffic, traffic_src = tj["dram_bytes_per_launch"][dname], "profiles/r02_kernel_metrics.json (ncu, same kernel sources)"
             tensor_pct = tj.get("tensor_pipe_pct", {}).get(dname)
         else:
-            traffic_src = "profiles/r02_kernel_metrics.json is for another library build: dropped"
+            traffic_src = "profiles/r02_kernel_metrics.json is for other kernel sources: dropped"
     roofline = {"bound": "tensor", "kernel": dname, "achieved": ach, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                 "frac": ach / peaks["tf_sustained"], "peak_source": peaks["src"] + " sustained (kernel timed inside a long step)",
                 "traffic": traffic, "traffic_source": traffic_src, "tensor_pipe_pct_ncu": tensor_pct, "share_of_step": dms / tot_prof, "launches_per_step": dcount,

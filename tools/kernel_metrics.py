@@ -8,8 +8,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def lib_hash():
-    p = os.path.join(ROOT, "uformer_b200", "lib", "liblewin_b200.so")
-    return hashlib.sha256(open(p, "rb").read()).hexdigest()[:16]
+    """Identity of the profiled kernels: hash of the kernel SOURCES (two nvcc builds of the same sources are not byte-identical)."""
+    sys.path.insert(0, ROOT)
+    from uformer_b200 import _lib
+    return _lib.csrc_hash()
 
 
 def to_bytes(v, unit):
@@ -48,7 +50,7 @@ def main(csv_path, labels_path, out_path):
         a["tensor"] += float(d["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"][0])
     out = dict(source=f"ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,sm__pipe_tensor_cycles_active... "
                       f"--clock-control none over one batch-32 forward ({os.path.basename(csv_path)}); cold-cache, serialised launches",
-               lib_sha256_16=lib_hash(), others_aten=[d["name"][:80] for d in ordered if not is_ours(d["name"])],
+               csrc_sha256_16=lib_hash(), others_aten=[d["name"][:80] for d in ordered if not is_ours(d["name"])],
                dram_bytes_per_launch={k: round(v["dram"] / v["n"]) for k, v in agg.items()},
                us_per_launch={k: round(v["us"] / v["n"], 2) for k, v in agg.items()},
                tensor_pipe_pct={k: round(v["tensor"] / v["n"], 2) for k, v in agg.items()},

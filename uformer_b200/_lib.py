@@ -73,6 +73,20 @@ EXPORTS = ["lw_abi_version", "lw_struct_size", "lw_last_cuda_error", "lw_check_d
 _lib = None
 
 
+def csrc_hash() -> str:
+    """sha256 (16 hex digits) over the kernel sources (uformer_b200/csrc/*, include/lewin_b200.h): identifies the kernels a
+    committed measurement (profiles/r02_kernel_metrics.json) describes.  (The built .so is no such identity: nvcc embeds
+    per-build module ids, two builds of the same sources differ.)"""
+    import hashlib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    csrc = os.path.join(root, "uformer_b200", "csrc")
+    h = hashlib.sha256()
+    for f in sorted(os.listdir(csrc)) + [os.path.join(root, "include", "lewin_b200.h")]:
+        with open(f if os.path.isabs(f) else os.path.join(csrc, f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
 def load():
     """Load the shared library (works without a GPU; compute calls do not)."""
     global _lib
