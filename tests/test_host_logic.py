@@ -250,3 +250,52 @@ def test_qkv_layernorm_fold_identity():
     lhs = ln @ w3.t()
     rhs = r64 * (x64 @ wg64.t()) - r64 * m64 * wg64.sum(1) + (w3 * b.double()[None]).sum(1)
     assert (lhs - rhs).abs().max() < 1e-9
+
+
+def test_window_size_validation_and_support_grid_without_gpu():
+    """lw_wmsa_args.win_size (C ABI v6): 0 / 8 = 8x8 windows, 16 = 16x16 windows, anything else is rejected before any launch; the
+    token-map geometry is validated against the window size; WindowAttention._check_supported follows lw_wmsa16_supported over
+    the BASELINE configs[4] grid (21 of its 24 points are built)."""
+    lib = _lib.load()
+    a = _lib.WmsaArgs()
+    for f in ("x", "out", "wqkv_img", "bqkv", "wproj_img", "bproj", "relpos"):
+        setattr(a, f, 0x10000)
+    a.n_windows, a.windowed, a.C, a.head_dim = 4, 0, 32, 32
+    a.H = a.W = 32
+    a.win_size = 7
+    assert lib.lw_wmsa_fwd(ctypes.byref(a), None) == -1
+    a.win_size, a.H = 16, 24                                      # 24 is a multiple of 8 but not of 16
+    assert lib.lw_wmsa_fwd(ctypes.byref(a), None) == -1
+    a.H, a.shift = 32, 16                                         # shift must stay below the window size
+    assert lib.lw_wmsa_fwd(ctypes.byref(a), None) == -1
+    a.shift, a.n_windows = 8, 3                                   # 32x32 tokens = 4 windows of 16x16 per image
+    assert lib.lw_wmsa_fwd(ctypes.byref(a), None) == -1
+    a.n_windows, a.C, a.head_dim = 4, 256, 64                     # not built: tiles exceed shared memory
+    assert lib.lw_wmsa_fwd(ctypes.byref(a), None) == -1
+    a.C, a.head_dim = 32, 32
+    assert lib.lw_wmsa_fwd(ctypes.byref(a), None) in (0, -3)      # passes validation (-3: no CUDA device in this container)
+    built = {}
+    for ws in (8, 16):
+        for hd in (16, 32, 64):
+            for heads in (1, 2, 4, 8):
+                att = uformer_b200.WindowAttention(hd * heads, (ws, ws), heads)
+                try:
+                    att._check_supported()
+                    built[(ws, hd, heads)] = True
+                except NotImplementedError:
+                    built[(ws, hd, heads)] = False
+                if ws == 16:
+                    assert built[(ws, hd, heads)] == bool(lib.lw_wmsa16_supported(hd * heads, hd))
+    assert sorted(k for k, v in built.items() if not v) == [(8, 64, 8), (16, 64, 4), (16, 64, 8)]
+    with pytest.raises(NotImplementedError):
+        uformer_b200.WindowAttention(32, (4, 4), 1)._check_supported()
+
+
+def test_kernel_source_hash_identifies_the_profiled_build():
+    """bench.py reports roofline.traffic from profiles/r02_kernel_metrics.json only while that table describes the current kernel
+    sources: the identity is _lib.csrc_hash() (deterministic, unlike the nvcc output)."""
+    import json
+    h = _lib.csrc_hash()
+    assert h == _lib.csrc_hash() and len(h) == 16 and int(h, 16) >= 0
+    tj = json.load(open(os.path.join(ROOT, "profiles", "r02_kernel_metrics.json")))
+    assert "csrc_sha256_16" in tj and set(tj["dram_bytes_per_launch"]) == set(tj["us_per_launch"])

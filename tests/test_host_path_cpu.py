@@ -334,6 +334,34 @@ def test_block_property_random_shapes_through_contract_model():
     run()
 
 
+def test_block_ws16_property_through_contract_model():
+    """The same property for 16x16 windows (BASELINE configs[4]; lw_wmsa_args.win_size = 16): every (C, head_dim) pair the
+    16x16-window kernel is built for, shift 0 / 8, modulator (256 x C), input mask, fp32 residual stream."""
+    from hypothesis import given, settings, strategies as st
+    from oracle import lewin_oracle as O
+
+    @settings(max_examples=8, deadline=None)
+    @given(ch=st.sampled_from([(16, 1), (32, 2), (32, 1), (64, 2), (64, 1), (128, 8), (128, 2), (256, 8)]), side=st.sampled_from([16, 32]),
+           batch=st.integers(1, 2), shifted=st.booleans(), modu=st.booleans(), masked=st.booleans(), fp32=st.booleans(), seed=st.integers(0, 2 ** 16))
+    def run(ch, side, batch, shifted, modu, masked, fp32, seed):
+        dim, heads = ch
+        shift = 8 if (shifted and side > 16) else 0
+        blk = U.LeWinTransformerBlock(dim, (32, 32), heads, win_size=16, shift_size=shift, modulator=modu).eval()
+        assert blk.win_size == 16 and not blk.attn.tma_gather()
+        blk.residual_fp32 = fp32
+        st_ = randomize_state(blk.state_dict(), seed)
+        blk.load_state_dict(st_)
+        g = torch.Generator().manual_seed(seed)
+        x = torch.randn(batch, side * side, dim, generator=g).to(torch.bfloat16)
+        mask = (torch.rand(batch, 1, side, side, generator=g) > 0.5).float() if (masked and not (shift > 0 and batch > 1)) else None
+        with KM.patched(), torch.no_grad():
+            y = blk(x, mask=mask).float()
+        ref = O.lewin_block(x.float(), st_, "", heads, 16, shift, input_mask=mask)
+        assert rel_l2(y, ref) < TOL, (ch, side, batch, shift, modu, masked, fp32, rel_l2(y, ref))
+
+    run()
+
+
 def _data_parallel_replica(mod):
     """What torch.nn.parallel.replicate builds for one device (it needs CUDA, so it is re-enacted here): every module is
     `_replicate_for_data_parallel()`-ed (its `_parameters` becomes {}), the broadcast copies of the parameters — autograd

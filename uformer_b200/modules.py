@@ -366,8 +366,9 @@ class Upsample(nn.Module):
 
 # -------------------------------------------------------------------------------------------------
 class LeWinTransformerBlock(nn.Module):
-    """model.py:850-1008.  forward(x (B, HW, C), mask=None) -> (B, HW, C), three kernel launches:
-    fused W-MSA (LN1..first residual), LeFF part 1 (LN2+Linear1+GELU), LeFF part 2 (dwconv..second residual)."""
+    """model.py:850-1008.  forward(x (B, HW, C), mask=None) -> (B, HW, C): two kernel launches for C <= 256 — fused W-MSA
+    (LN1 .. first residual; 8x8 or 16x16 windows) and fused LeFF (LN2 .. second residual) — three at C = 512, where LeFF is
+    split into part 1 (LN2 + Linear1 + GELU) and part 2 (dwconv .. second residual)."""
 
     def __init__(self, dim, input_resolution, num_heads, win_size=8, shift_size=0, mlp_ratio=4., qkv_bias=True,
                  qk_scale=None, drop=0., attn_drop=0., drop_path=0., act_layer=nn.GELU, norm_layer=nn.LayerNorm,
