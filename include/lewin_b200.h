@@ -195,7 +195,12 @@ typedef struct lw_up_args {
 } lw_up_args;
 int lw_upsample_fwd(const lw_up_args* a, lw_stream_t stream);
 
-/* ---- caller-side projections, HBM-bound direct convolutions ----
+/* ---- caller-side projections, HBM-bound 3x3 convolutions that also change the layout ----
+ * Both take the reference's raw fp32 conv weight (no host packing).  The usual widths run on the tensor core (csrc/proj.cuh):
+ * InputProj with Cin = 3 and E in {16, 32} (im2col rows built in shared memory; image and weight split into bf16 hi + lo terms,
+ * products fp32-accurate), OutputProj with Cin in {32, 64} and Cout <= 3 (one GEMM per TMA-loaded halo'd token tile, then the nine
+ * taps; the weight split into two bf16 halves; the output planes leave through TMA tensor stores when W % 4 == 0 and `out` is
+ * 16-byte aligned).  Other widths take direct SIMT kernels.  W must be even; tokens 16-byte aligned.
  * InputProj (model.py:781-812): y = LeakyReLU_0.01(conv3x3(x)), NCHW fp32 image -> bf16 tokens. */
 int lw_input_proj_fwd(const float* img, const float* w /* (E,Cin,3,3) */, const float* b, void* tokens,
                       int32_t B, int32_t Cin, int32_t H, int32_t W, int32_t E, lw_stream_t stream);
