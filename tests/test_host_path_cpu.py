@@ -362,6 +362,25 @@ def test_block_ws16_property_through_contract_model():
     run()
 
 
+def test_uformer_with_16x16_windows_through_contract_model():
+    """A whole Uformer built with win_size = 16 (the reference's Uformer(win_size=...) argument, model.py:1076): the engine's own
+    caller wires 16x16-window blocks (shifted by 8 on odd blocks), the construction-time clamp turns the 16x16-token stages into
+    un-shifted single-window blocks and the 8x8-token bottleneck into 8x8-window blocks (model.py:863-865), and the whole
+    forward through the kernel contracts equals the oracle."""
+    from oracle import lewin_oracle as O
+    cfg = dict(img_size=128, embed_dim=16, depths=[2] * 9, win_size=16, token_projection="linear", token_mlp="leff", modulator=False)
+    net = U.Uformer(**cfg).eval()
+    st = randomize_state(net.state_dict(), 31)
+    net.load_state_dict(st)
+    blocks = [m for m in net.modules() if isinstance(m, U.LeWinTransformerBlock)]
+    assert {(b.win_size, b.shift_size) for b in blocks} == {(16, 0), (16, 8), (8, 0)}
+    x = torch.rand(1, 3, 128, 128, generator=torch.Generator().manual_seed(5))
+    with KM.patched(), torch.no_grad():
+        y = net(x).float()
+    ref = O.uformer_forward(x, st, 128, 16, [2] * 9, win_size=16)
+    assert rel_l2(y, ref) < TOL and rel_l2(y - x, ref - x) < 2 * TOL, (rel_l2(y, ref), rel_l2(y - x, ref - x))
+
+
 def _data_parallel_replica(mod):
     """What torch.nn.parallel.replicate builds for one device (it needs CUDA, so it is re-enacted here): every module is
     `_replicate_for_data_parallel()`-ed (its `_parameters` becomes {}), the broadcast copies of the parameters — autograd
