@@ -60,3 +60,21 @@ def test_install_builds_reference_uformer_on_engine():
     finally:
         uformer_b200.uninstall(m)
     assert m.Uformer(**cfg).encoderlayer_0.blocks[0].__class__.__module__ == "model"
+
+
+def test_uformer_win16_live():
+    """A whole reference Uformer built with win_size = 16 (16x16 windows, shift 8, the clamp of model.py:863-865 at the 16x16- and
+    8x8-token stages) against the oracle — the pin behind tests/test_host_path_cpu.py::test_uformer_with_16x16_windows_..."""
+    from oracle import lewin_oracle as O
+    from paramgen import randomize_state
+    from refshim import import_reference_model
+    m = import_reference_model()
+    cfg = dict(img_size=128, embed_dim=16, depths=[2] * 9, win_size=16, token_projection="linear", token_mlp="leff", modulator=False)
+    net = m.Uformer(**cfg).eval()
+    st = randomize_state(net.state_dict(), 31)
+    net.load_state_dict(st)
+    x = torch.rand(1, 3, 128, 128, generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        ref = net(x)
+    got = O.uformer_forward(x.double(), {k: (v.double() if torch.is_floating_point(v) else v) for k, v in st.items()}, 128, 16, [2] * 9, win_size=16)
+    assert ((got.float() - ref).norm() / ref.norm()).item() < 1e-5
