@@ -133,6 +133,33 @@ def test_reference_model_with_engine_installed_through_contract_model():
         U.uninstall(m)
 
 
+def test_reference_model_win16_with_engine_installed_through_contract_model():
+    """The same drop-in with win_size = 16: the reference's Uformer(win_size=16) builds on the engine's modules and its forward
+    through the kernel contracts equals its own forward on the reference's modules (same weights)."""
+    from refshim import import_reference_model, reference_available
+    if not reference_available():
+        pytest.skip("reference not mounted")
+    m = import_reference_model()
+    cfg = dict(img_size=128, embed_dim=16, depths=[2] * 9, win_size=16, token_projection="linear", token_mlp="leff", modulator=False)
+    ref_net = m.Uformer(**cfg).eval()
+    st = randomize_state(ref_net.state_dict(), 31)
+    ref_net.load_state_dict(st)
+    x = torch.rand(1, 3, 128, 128, generator=torch.Generator().manual_seed(6))
+    with torch.no_grad():
+        want = ref_net(x)
+    U.install(m)
+    try:
+        net = m.Uformer(**cfg)
+        assert isinstance(net.encoderlayer_0.blocks[1], U.LeWinTransformerBlock) and net.encoderlayer_0.blocks[1].shift_size == 8
+        net.load_state_dict(st, strict=True)
+        net.eval()
+        with KM.patched() as calls, torch.no_grad():
+            y = net(x)
+        assert calls["wmsa"] == 18 and rel_l2(y, want) < TOL
+    finally:
+        U.uninstall(m)
+
+
 def test_arbitrary_resolution_restore_through_contract_model():
     """BASELINE configs[3]: model built for 128x128 restores a 200x150 image (padded to 256x256 by expand2square,
     test/test_sidd.py:79-108); compared with the reference's own model driven by the reference's own host code when it
