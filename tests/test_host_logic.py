@@ -111,7 +111,7 @@ def test_pack_roundtrip_property():
     """hypothesis: pack/unpack is the identity on bf16-representable matrices for every legal (N, K, nch, order)."""
     from hypothesis import given, settings, strategies as st
 
-    @settings(max_examples=25, deadline=None)
+    @settings(max_examples=25, deadline=None, derandomize=True)
     @given(nchunks=st.integers(1, 4), nch=st.sampled_from([16, 32, 48, 64, 96, 128, 256]), k=st.sampled_from([16, 32, 64, 96, 128, 320]),
            order=st.sampled_from(["nk", "kn"]), seed=st.integers(0, 2 ** 16))
     def run(nchunks, nch, k, order, seed):

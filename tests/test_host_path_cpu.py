@@ -333,7 +333,7 @@ def test_block_property_random_shapes_through_contract_model():
     from hypothesis import given, settings, strategies as st
     from oracle import lewin_oracle as O
 
-    @settings(max_examples=12, deadline=None)
+    @settings(max_examples=12, deadline=None, derandomize=True)
     @given(ch=st.sampled_from([(16, 1), (32, 1), (32, 2), (64, 2), (64, 4), (128, 4)]), side=st.sampled_from([8, 16, 24, 40]),
            batch=st.integers(1, 3), shifted=st.booleans(), modu=st.booleans(), masked=st.booleans(), seed=st.integers(0, 2 ** 16))
     def run(ch, side, batch, shifted, modu, masked, seed):
@@ -367,7 +367,7 @@ def test_block_ws16_property_through_contract_model():
     from hypothesis import given, settings, strategies as st
     from oracle import lewin_oracle as O
 
-    @settings(max_examples=8, deadline=None)
+    @settings(max_examples=8, deadline=None, derandomize=True)
     @given(ch=st.sampled_from([(16, 1), (32, 2), (32, 1), (64, 2), (64, 1), (128, 8), (128, 2), (256, 8)]), side=st.sampled_from([16, 32]),
            batch=st.integers(1, 2), shifted=st.booleans(), modu=st.booleans(), masked=st.booleans(), fp32=st.booleans(), seed=st.integers(0, 2 ** 16))
     def run(ch, side, batch, shifted, modu, masked, fp32, seed):
